@@ -1,0 +1,27 @@
+// Activation functions of the reference's [convolutional] blocks (models.py:51-64), evaluated in fp32.
+#pragma once
+#include "../../include/dyk_b200.h"
+
+namespace dyk {
+
+__device__ __forceinline__ float mish_f(float x) {
+  // x * tanh(softplus(x)) = x * n / (n + 2),  n = e^x (e^x + 2); for large x the ratio is 1 in fp32.
+  if (x > 20.f) return x;
+  const float e = __expf(x);
+  const float n = e * (e + 2.f);
+  return x * __fdividef(n, n + 2.f);
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case DYK_ACT_LEAKY: return x > 0.f ? x : 0.1f * x;
+    case DYK_ACT_MISH: return mish_f(x);
+    case DYK_ACT_RELU: return fmaxf(x, 0.f);
+    case DYK_ACT_RELU6: return fminf(fmaxf(x, 0.f), 6.f);
+    case DYK_ACT_HARDSWISH: return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    case DYK_ACT_HARDSIGMOID: return fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    default: return x;
+  }
+}
+
+}  // namespace dyk

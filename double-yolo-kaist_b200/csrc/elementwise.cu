@@ -1,0 +1,382 @@
+// HBM-bound NHWC kernels of the hot path: weighted fusion add, channel-slice copy, max-pool, nearest
+// upsample, squeeze-excitation, layout conversion and weight packing.  All of them move 16-byte
+// (8-channel) vectors with the channel index fastest so that a warp touches contiguous memory.
+#include "common.h"
+#include "vec.cuh"
+
+namespace dyk {
+
+static inline int grid_for(long long work, int block) {
+  long long g = (work + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------ WeightedFeatureFusion
+// reference: build_utils/layers.py:63-85   x*w[0] + a*w[1]  (or plain x + a)
+template <bool kBf16>
+__global__ void fused_add_kernel(const uint8_t* __restrict__ a, long long as, const uint8_t* __restrict__ b,
+                                 long long bs, uint8_t* __restrict__ y, long long ys, long long npix, int cv,
+                                 const float* __restrict__ wts) {
+  float w0 = 1.f, w1 = 1.f;
+  if (wts) { w0 = __ldg(wts); w1 = __ldg(wts + 1); }
+  const long long total = npix * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int c = (int)(i - pix * cv);
+    const uint4 va = __ldg(reinterpret_cast<const uint4*>(a + (pix * as) * 2) + c);
+    const uint4 vb = __ldg(reinterpret_cast<const uint4*>(b + (pix * bs) * 2) + c);
+    float fa[8], fb[8], fo[8];
+    unpack8<kBf16>(va, fa);
+    unpack8<kBf16>(vb, fb);
+    if (wts) {
+      // reference order: x = x * w0 (rounded to the tensor dtype), a = a * w1 (rounded), then x + a
+#pragma unroll
+      for (int k = 0; k < 8; ++k) fo[k] = fa[k] * w0 + fb[k] * w1;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) fo[k] = fa[k] + fb[k];
+    }
+    *(reinterpret_cast<uint4*>(y + (pix * ys) * 2) + c) = pack8<kBf16>(fo);
+  }
+}
+
+__global__ void fusion_weights_kernel(const float* __restrict__ w_raw, float* __restrict__ w_out, int n) {
+  const int i = threadIdx.x;
+  if (i < n) w_out[i] = (1.f / (1.f + expf(-w_raw[i]))) * (2.f / n);
+}
+
+// ------------------------------------------------------------------ FeatureConcat fallback copy
+__global__ void copy_slice_kernel(const uint8_t* __restrict__ src, long long ss, uint8_t* __restrict__ dst,
+                                  long long ds, long long npix, int cv) {
+  const long long total = npix * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int c = (int)(i - pix * cv);
+    *(reinterpret_cast<uint4*>(dst + (pix * ds) * 2) + c) = __ldg(reinterpret_cast<const uint4*>(src + (pix * ss) * 2) + c);
+  }
+}
+
+// ------------------------------------------------------------------ MaxPool2d(k, stride, (k-1)//2)
+// reference: models.py:91-94; padding behaves as -inf (window clipped to the image).
+template <bool kBf16>
+__global__ void maxpool_kernel(const uint8_t* __restrict__ x, long long xs, uint8_t* __restrict__ y, long long ys,
+                               int N, int H, int W, int cv, int k, int stride, int pad, int Ho, int Wo) {
+  const long long total = (long long)N * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    long long t = i / cv;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float m[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) m[q] = -INFINITY;
+    const int h0 = ho * stride - pad, w0 = wo * stride - pad;
+    for (int r = 0; r < k; ++r) {
+      const int h = h0 + r;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < k; ++s) {
+        const int w = w0 + s;
+        if (w < 0 || w >= W) continue;
+        const long long pix = ((long long)n * H + h) * W + w;
+        float f[8];
+        unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(x + pix * xs * 2) + c), f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) m[q] = fmaxf(m[q], f[q]);
+      }
+    }
+    const long long opix = ((long long)n * Ho + ho) * Wo + wo;
+    *(reinterpret_cast<uint4*>(y + opix * ys * 2) + c) = pack8<kBf16>(m);
+  }
+}
+
+// ------------------------------------------------------------------ nn.Upsample(scale_factor=s), nearest
+__global__ void upsample_kernel(const uint8_t* __restrict__ x, long long xs, uint8_t* __restrict__ y, long long ys,
+                                int N, int H, int W, int cv, int s) {
+  const int Ho = H * s, Wo = W * s;
+  const long long total = (long long)N * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    long long t = i / cv;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const long long pix = ((long long)n * H + ho / s) * W + wo / s;
+    const long long opix = ((long long)n * Ho + ho) * Wo + wo;
+    *(reinterpret_cast<uint4*>(y + opix * ys * 2) + c) = __ldg(reinterpret_cast<const uint4*>(x + pix * xs * 2) + c);
+  }
+}
+
+// ------------------------------------------------------------------ SqueezeExcitation
+// reference: build_utils/layers.py:184-190
+// (1) pooled[n][c] += sum over a slab of pixels  (fp32 atomics into a zeroed scratch)
+template <bool kBf16>
+__global__ void se_pool_kernel(const uint8_t* __restrict__ x, long long xs, int HW, int C, int slabs,
+                               float* __restrict__ pooled) {
+  // block: 32 pixel lanes x 8 channel-vectors (64 channels); grid: (C/64 ceil, slabs, N)
+  const int cvec = blockIdx.x * 8 + (threadIdx.x & 7);
+  const int plane = threadIdx.x >> 3;  // 0..31
+  const int n = blockIdx.z;
+  const int per = (HW + slabs - 1) / slabs;
+  const int p0 = blockIdx.y * per;
+  const int p1 = min(HW, p0 + per);
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+  if (cvec * 8 < C) {
+    for (int pidx = p0 + plane; pidx < p1; pidx += 32) {
+      const long long pix = (long long)n * HW + pidx;
+      float f[8];
+      unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(x + pix * xs * 2) + cvec), f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += f[q];
+    }
+  }
+  __shared__ float red[32][8][8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) red[plane][threadIdx.x & 7][q] = acc[q];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int cv = threadIdx.x >> 3, q = threadIdx.x & 7;
+    float s = 0.f;
+    for (int l = 0; l < 32; ++l) s += red[l][cv][q];
+    const int c = (blockIdx.x * 8 + cv) * 8 + q;
+    if (c < C) atomicAdd(&pooled[(long long)n * C + c], s);
+  }
+}
+// (2) gate[n][:] = hardsigmoid(W2 relu(W1 mean + b1) + b2); one block per image
+__global__ void se_mlp_kernel(const float* __restrict__ pooled, float inv_hw, int C, int Csq,
+                              const float* __restrict__ w1, const float* __restrict__ b1,
+                              const float* __restrict__ w2, const float* __restrict__ b2,
+                              float* __restrict__ gate) {
+  extern __shared__ float sm[];
+  float* mean = sm;        // [C]
+  float* hid = sm + C;     // [Csq]
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pooled[(long long)n * C + c] * inv_hw;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < Csq; j += nwarps) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += __ldg(&w1[(long long)j * C + c]) * mean[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) hid[j] = fmaxf(s + __ldg(&b1[j]), 0.f);
+  }
+  __syncthreads();
+  for (int c = warp; c < C; c += nwarps) {
+    float s = 0.f;
+    for (int j = lane; j < Csq; j += 32) s += __ldg(&w2[(long long)c * Csq + j]) * hid[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      const float v = s + __ldg(&b2[c]);
+      gate[(long long)n * C + c] = fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    }
+  }
+}
+// (3) y = x * gate[n][c]
+template <bool kBf16>
+__global__ void scale_channels_kernel(const uint8_t* __restrict__ x, long long xs, const float* __restrict__ gate,
+                                      uint8_t* __restrict__ y, long long ys, int N, int HW, int C) {
+  const int cv = C / 8;
+  const long long total = (long long)N * HW * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    const long long pix = i / cv;
+    const int n = (int)(pix / HW);
+    float f[8];
+    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(x + pix * xs * 2) + c), f);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + (long long)n * C + c * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + (long long)n * C + c * 8) + 1);
+    f[0] *= g0.x; f[1] *= g0.y; f[2] *= g0.z; f[3] *= g0.w;
+    f[4] *= g1.x; f[5] *= g1.y; f[6] *= g1.z; f[7] *= g1.w;
+    *(reinterpret_cast<uint4*>(y + pix * ys * 2) + c) = pack8<kBf16>(f);
+  }
+}
+
+// ------------------------------------------------------------------ packing / layout
+template <bool kBf16>
+__global__ void pack_ohwi_kernel(const float* __restrict__ w, void* __restrict__ out, int O, int I, int kh, int kw) {
+  const long long total = (long long)O * I * kh * kw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // i indexes the output [o][r][s][ci]
+    const int ci = (int)(i % I);
+    long long t = i / I;
+    const int s = (int)(t % kw); t /= kw;
+    const int r = (int)(t % kh);
+    const int o = (int)(t / kh);
+    store1<kBf16>(out, i, __ldg(&w[(((long long)o * I + ci) * kh + r) * kw + s]));
+  }
+}
+
+// [N][C][HW] fp32 -> [N][HW][ys] dtype through a 32x32 smem transpose
+template <bool kBf16>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, void* __restrict__ y, long long ys, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && p < HW) ? __ldg(&x[((long long)n * C + c) * HW + p]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int p = p0 + j, c = c0 + threadIdx.x;
+    if (c < C && p < HW) store1<kBf16>(y, ((long long)n * HW + p) * ys + c, tile[threadIdx.x][j]);
+  }
+}
+template <bool kBf16>
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, long long xs, float* __restrict__ y, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int p = p0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && p < HW) ? load1<kBf16>(x, ((long long)n * HW + p) * xs + c) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, p = p0 + threadIdx.x;
+    if (c < C && p < HW) y[((long long)n * C + c) * HW + p] = tile[threadIdx.x][j];
+  }
+}
+
+}  // namespace dyk
+
+using namespace dyk;
+
+#define DYK_ALIGNED16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+
+extern "C" __attribute__((visibility("default"))) int dyk_fused_add(const void* a, int64_t as, const void* b, int64_t bs, void* y, int64_t ys,
+                             int64_t npix, int32_t C, const float* wts, int32_t dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYK_REQUIRE(a && b && y, "dyk_fused_add: null pointer");
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && as % 8 == 0 && bs % 8 == 0 && ys % 8 == 0,
+              "dyk_fused_add: C and strides must be multiples of 8 (C=%d)", C);
+  DYK_REQUIRE(DYK_ALIGNED16(a) && DYK_ALIGNED16(b) && DYK_ALIGNED16(y), "dyk_fused_add: 16-byte alignment");
+  if (npix == 0) return DYK_OK;
+  const int cv = C / 8;
+  const int grid = grid_for(npix * cv, 256);
+  DYK_DISPATCH_DTYPE(dtype, (fused_add_kernel<kBf16><<<grid, 256, 0, stream>>>(
+                                (const uint8_t*)a, as, (const uint8_t*)b, bs, (uint8_t*)y, ys, npix, cv, wts)));
+  DYK_LAUNCH_OK("fused_add_kernel");
+  return DYK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dyk_fusion_weights(const float* w_raw, float* w_out, int32_t n, void* stream_) {
+  DYK_REQUIRE(w_raw && w_out && n > 0 && n <= 32, "dyk_fusion_weights: bad arguments");
+  fusion_weights_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_)>>>(w_raw, w_out, n);
+  DYK_LAUNCH_OK("fusion_weights_kernel");
+  return DYK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dyk_copy_slice(const void* src, int64_t ss, void* dst, int64_t ds, int64_t npix, int32_t C,
+                              int32_t dtype, void* stream_) {
+  (void)dtype;
+  DYK_REQUIRE(src && dst, "dyk_copy_slice: null pointer");
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && ss % 8 == 0 && ds % 8 == 0, "dyk_copy_slice: C/strides must be multiples of 8");
+  DYK_REQUIRE(DYK_ALIGNED16(src) && DYK_ALIGNED16(dst), "dyk_copy_slice: 16-byte alignment");
+  if (npix == 0) return DYK_OK;
+  const int cv = C / 8;
+  copy_slice_kernel<<<grid_for(npix * cv, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      (const uint8_t*)src, ss, (uint8_t*)dst, ds, npix, cv);
+  DYK_LAUNCH_OK("copy_slice_kernel");
+  return DYK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dyk_maxpool2d(const void* x, int64_t xs, void* y, int64_t ys, int32_t N, int32_t H, int32_t W,
+                             int32_t C, int32_t k, int32_t stride, int32_t dtype, void* stream_) {
+  DYK_REQUIRE(x && y, "dyk_maxpool2d: null pointer");
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && xs % 8 == 0 && ys % 8 == 0, "dyk_maxpool2d: C/strides must be multiples of 8");
+  DYK_REQUIRE(k >= 1 && stride >= 1, "dyk_maxpool2d: k=%d stride=%d", k, stride);
+  const int pad = (k - 1) / 2;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  DYK_REQUIRE(Ho > 0 && Wo > 0, "dyk_maxpool2d: empty output");
+  const int cv = C / 8;
+  const int grid = grid_for((long long)N * Ho * Wo * cv, 256);
+  DYK_DISPATCH_DTYPE(dtype, (maxpool_kernel<kBf16><<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+                                (const uint8_t*)x, xs, (uint8_t*)y, ys, N, H, W, cv, k, stride, pad, Ho, Wo)));
+  DYK_LAUNCH_OK("maxpool_kernel");
+  return DYK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dyk_upsample_nearest(const void* x, int64_t xs, void* y, int64_t ys, int32_t N, int32_t H,
+                                    int32_t W, int32_t C, int32_t s, int32_t dtype, void* stream_) {
+  (void)dtype;
+  DYK_REQUIRE(x && y, "dyk_upsample_nearest: null pointer");
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && xs % 8 == 0 && ys % 8 == 0 && s >= 1, "dyk_upsample_nearest: bad shape");
+  const int cv = C / 8;
+  upsample_kernel<<<grid_for((long long)N * H * s * W * s * cv, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      (const uint8_t*)x, xs, (uint8_t*)y, ys, N, H, W, cv, s);
+  DYK_LAUNCH_OK("upsample_kernel");
+  return DYK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dyk_se_gate(const void* x, int64_t xs, int32_t N, int32_t HW, int32_t C, const float* w1,
+                           const float* b1, const float* w2, const float* b2, int32_t Csq, float* pooled,
+                           float* gate, int32_t dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYK_REQUIRE(x && w1 && b1 && w2 && b2 && pooled && gate, "dyk_se_gate: null pointer");
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && xs % 8 == 0 && Csq > 0 && N > 0 && HW > 0, "dyk_se_gate: bad shape");
+  DYK_REQUIRE((size_t)(C + Csq) * 4 <= 48 * 1024, "dyk_se_gate: C + Csq too large");
+  DYK_CUDA_OK(cudaMemsetAsync(pooled, 0, sizeof(float) * (size_t)N * C, stream));
+  int slabs = HW / 256;
+  if (slabs < 1) slabs = 1;
+  if (slabs > 32) slabs = 32;
+  const dim3 grid((C + 63) / 64, slabs, N);
+  DYK_DISPATCH_DTYPE(dtype, (se_pool_kernel<kBf16><<<grid, 256, 0, stream>>>((const uint8_t*)x, xs, HW, C, slabs, pooled)));
+  DYK_LAUNCH_OK("se_pool_kernel");
+  se_mlp_kernel<<<N, 256, (C + Csq) * sizeof(float), stream>>>(pooled, 1.f / (float)HW, C, Csq, w1, b1, w2, b2, gate);
+  DYK_LAUNCH_OK("se_mlp_kernel");
+  return DYK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dyk_scale_channels(const void* x, int64_t xs, const float* gate, void* y, int64_t ys, int32_t N,
+                                  int32_t HW, int32_t C, int32_t dtype, void* stream_) {
+  DYK_REQUIRE(x && gate && y, "dyk_scale_channels: null pointer");
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && xs % 8 == 0 && ys % 8 == 0, "dyk_scale_channels: bad shape");
+  const int grid = grid_for((long long)N * HW * (C / 8), 256);
+  DYK_DISPATCH_DTYPE(dtype, (scale_channels_kernel<kBf16><<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+                                (const uint8_t*)x, xs, gate, (uint8_t*)y, ys, N, HW, C)));
+  DYK_LAUNCH_OK("scale_channels_kernel");
+  return DYK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dyk_pack_weights_ohwi(const float* w, void* out, int32_t O, int32_t I, int32_t kh, int32_t kw,
+                                     int32_t dtype, void* stream_) {
+  DYK_REQUIRE(w && out && O > 0 && I > 0 && kh > 0 && kw > 0, "dyk_pack_weights_ohwi: bad arguments");
+  const int grid = grid_for((long long)O * I * kh * kw, 256);
+  DYK_DISPATCH_DTYPE(dtype, (pack_ohwi_kernel<kBf16><<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(w, out, O, I, kh, kw)));
+  DYK_LAUNCH_OK("pack_ohwi_kernel");
+  return DYK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dyk_nchw_f32_to_nhwc(const float* x, void* y, int64_t ys, int32_t N, int32_t C, int32_t H, int32_t W,
+                                    int32_t dtype, void* stream_) {
+  DYK_REQUIRE(x && y && N > 0 && C > 0 && H > 0 && W > 0 && ys >= C, "dyk_nchw_f32_to_nhwc: bad arguments");
+  const int HW = H * W;
+  const dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  DYK_DISPATCH_DTYPE(dtype, (nchw_to_nhwc_kernel<kBf16><<<grid, block, 0, static_cast<cudaStream_t>(stream_)>>>(x, y, ys, C, HW)));
+  DYK_LAUNCH_OK("nchw_to_nhwc_kernel");
+  return DYK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dyk_nhwc_to_nchw_f32(const void* x, int64_t xs, float* y, int32_t N, int32_t C, int32_t H, int32_t W,
+                                    int32_t dtype, void* stream_) {
+  DYK_REQUIRE(x && y && N > 0 && C > 0 && H > 0 && W > 0 && xs >= C, "dyk_nhwc_to_nchw_f32: bad arguments");
+  const int HW = H * W;
+  const dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  DYK_DISPATCH_DTYPE(dtype, (nhwc_to_nchw_kernel<kBf16><<<grid, block, 0, static_cast<cudaStream_t>(stream_)>>>(x, xs, y, C, HW)));
+  DYK_LAUNCH_OK("nhwc_to_nchw_kernel");
+  return DYK_OK;
+}
