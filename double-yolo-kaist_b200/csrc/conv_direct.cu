@@ -11,9 +11,18 @@ namespace dyk {
 // ------------------------------------------------------------------ stem: NCHW fp32 -> NHWC dtype
 // One thread = one output pixel x COUT_T output channels; consecutive threads walk along W, so the
 // per-plane input reads are coalesced and each thread stores COUT_T*2 contiguous bytes.
-template <int COUT_T, bool kBf16>
+template <typename TIn>
+__device__ __forceinline__ float load_frame(const TIn* p);
+template <>
+__device__ __forceinline__ float load_frame<float>(const float* p) { return __ldg(p); }
+// uint8 frames are normalised exactly as the reference's callers do: img.float() / 255.0
+// (train_utils/kaist_train_eval_utils.py:54-55, evaluate.py:67-68)
+template <>
+__device__ __forceinline__ float load_frame<uint8_t>(const uint8_t* p) { return __fdiv_rn((float)__ldg(p), 255.f); }
+
+template <int COUT_T, bool kBf16, typename TIn>
 __global__ void __launch_bounds__(128)
-stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
+stem_conv_kernel(const TIn* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
                  const float* __restrict__ bias, uint8_t* __restrict__ y, long long ys, int N, int H, int W,
                  int Cin, int Cout, int k, int stride, int pad, int Ho, int Wo, int act) {
   extern __shared__ float wsm[];  // [k*k*Cin][COUT_T] for this block's channel group
@@ -42,7 +51,7 @@ stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const
         const int ww = w0 + s;
         if (ww < 0 || ww >= W) continue;
         for (int ci = 0; ci < Cin; ++ci) {
-          const float v = __ldg(&x[(((long long)n * Cin + ci) * H + h) * W + ww]);
+          const float v = load_frame<TIn>(&x[(((long long)n * Cin + ci) * H + h) * W + ww]);
           const float* wp = &wsm[((r * k + s) * Cin + ci) * COUT_T];
 #pragma unroll
           for (int c = 0; c < COUT_T; ++c) acc[c] = fmaf(v, wp[c], acc[c]);
@@ -119,12 +128,13 @@ dwconv_kernel(const uint8_t* __restrict__ x, long long xs, const float* __restri
 
 using namespace dyk;
 
-extern "C" __attribute__((visibility("default"))) int dyk_conv2d_stem_nchw_fwd(const float* x, const float* w, const float* scale, const float* bias,
+extern "C" __attribute__((visibility("default"))) int dyk_conv2d_stem_nchw_fwd(const void* x, const float* w, const float* scale, const float* bias,
                                         void* y, int64_t ys, int32_t N, int32_t H, int32_t W, int32_t Cin,
                                         int32_t Cout, int32_t k, int32_t stride, int32_t pad, int32_t act,
-                                        int32_t dtype, void* stream_) {
+                                        int32_t dtype, int32_t x_kind, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DYK_REQUIRE(x && w && y, "dyk_conv2d_stem_nchw_fwd: null pointer");
+  DYK_REQUIRE(x_kind == 0 || x_kind == 1, "dyk_conv2d_stem_nchw_fwd: x_kind=%d (0 = fp32, 1 = uint8)", x_kind);
   DYK_REQUIRE(Cin >= 1 && Cin <= 4, "dyk_conv2d_stem_nchw_fwd: Cin=%d (expects 1..4)", Cin);
   DYK_REQUIRE(Cout > 0 && Cout % 8 == 0 && ys % 8 == 0 && ys >= Cout, "dyk_conv2d_stem_nchw_fwd: Cout=%d ys=%lld",
               Cout, (long long)ys);
@@ -139,13 +149,16 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_stem_nchw_fwd(c
   if (gx > cap) gx = cap;
   const dim3 grid((unsigned)gx, (Cout + ct - 1) / ct);
   const size_t smem = (size_t)k * k * Cin * ct * sizeof(float);
+#define DYK_STEM_LAUNCH(CT, TIN)                                                                              \
+  DYK_DISPATCH_DTYPE(dtype, (stem_conv_kernel<CT, kBf16, TIN><<<grid, 128, smem, stream>>>(                     \
+                                static_cast<const TIN*>(x), w, scale, bias, (uint8_t*)y, ys, N, H, W, Cin, Cout, \
+                                k, stride, pad, Ho, Wo, act)))
   if (ct == 32) {
-    DYK_DISPATCH_DTYPE(dtype, (stem_conv_kernel<32, kBf16><<<grid, 128, smem, stream>>>(
-                                  x, w, scale, bias, (uint8_t*)y, ys, N, H, W, Cin, Cout, k, stride, pad, Ho, Wo, act)));
+    if (x_kind == 0) DYK_STEM_LAUNCH(32, float); else DYK_STEM_LAUNCH(32, uint8_t);
   } else {
-    DYK_DISPATCH_DTYPE(dtype, (stem_conv_kernel<16, kBf16><<<grid, 128, smem, stream>>>(
-                                  x, w, scale, bias, (uint8_t*)y, ys, N, H, W, Cin, Cout, k, stride, pad, Ho, Wo, act)));
+    if (x_kind == 0) DYK_STEM_LAUNCH(16, float); else DYK_STEM_LAUNCH(16, uint8_t);
   }
+#undef DYK_STEM_LAUNCH
   DYK_LAUNCH_OK("stem_conv_kernel");
   return DYK_OK;
 }

@@ -1,0 +1,624 @@
+"""Execution-plan compiler for ``models.YOLO``.
+
+The reference executes a model by walking ``module_list`` and keeping a side table ``out[]`` of routed
+tensors (models.py:279-315), one library kernel per primitive.  Here the same block list is compiled,
+per (mode, batch, H, W, dtype), into a short list of native launches over channels-last buffers:
+
+  * [convolutional] = conv + folded BN + activation in one tcgen05 kernel; a following un-weighted
+    [shortcut] becomes the conv's residual operand and a following [upsample] x2 its store pattern;
+  * [route] with one source is an alias; with several sources the *producers* are redirected to write
+    straight into channel slices of the concat buffer, so no concat kernel runs at all (a copy is only
+    emitted when a tensor would have to live in two concat buffers);
+  * weighted [shortcut] (modality fusion), [maxpool], [se], [depthwiseconvolutional], [yolo] each map to
+    their kernel; the three heads write into one (B, rows, no) prediction tensor;
+  * buffers are recycled by liveness, and everything after the two stem convolutions is captured in a
+    CUDA graph (the stems read the caller's NCHW tensors directly and therefore stay outside).
+
+Parameters stay in the stock nn modules; packed / BN-folded copies live in a WeightBank that is refreshed
+in place whenever a parameter's version counter or storage changes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _native as nat
+from . import ops
+from .ops import View
+
+
+class Value:
+    """One logical activation tensor (N, H, W, C) produced by one op."""
+    __slots__ = ("C", "H", "W", "uses", "ext", "f32", "place", "view", "kind", "first", "last", "name")
+
+    def __init__(self, C_, H, W, kind, name="", ext=False, f32=False):
+        self.C, self.H, self.W = C_, H, W
+        self.uses = 0
+        self.ext = ext
+        self.f32 = f32
+        self.place = None   # (parent Value, channel offset) when it lives inside a concat buffer
+        self.view = None
+        self.kind = kind
+        self.first = None
+        self.last = None
+        self.name = name
+
+
+class Op:
+    kind = "op"
+
+    def inputs(self):
+        return []
+
+
+class ConvOp(Op):
+    kind = "conv"
+
+    def __init__(self, layer, src, out, conv, bn, act, tag=""):
+        self.layer, self.src, self.out, self.conv, self.bn, self.act = layer, src, out, conv, bn, act
+        self.res = None
+        self.upsample2x = False
+        self.out_f32 = False
+        self.tag = tag
+
+    @property
+    def flavor(self):
+        c = self.conv
+        if c.groups == 1:
+            return "stem" if self.src.ext else "dense"
+        if c.groups == c.in_channels == c.out_channels:
+            return "dw"
+        raise nat.NativeError(f"layer {self.layer}: grouped convolution groups={c.groups} "
+                              f"({c.in_channels}->{c.out_channels}) has no native kernel")
+
+    def inputs(self):
+        return [self.src] + ([self.res] if self.res is not None else [])
+
+
+class AddOp(Op):
+    kind = "add"
+
+    def __init__(self, layer, x, others, out, module):
+        self.layer, self.x, self.others, self.out, self.module = layer, x, others, out, module
+
+    def inputs(self):
+        return [self.x] + list(self.others)
+
+
+class ConcatOp(Op):
+    kind = "concat"
+
+    def __init__(self, layer, srcs, out):
+        self.layer, self.srcs, self.out = layer, srcs, out
+        self.copies = []  # (src Value, channel offset) that could not be placed
+
+    def inputs(self):
+        return list(self.srcs)
+
+
+class PoolOp(Op):
+    kind = "maxpool"
+
+    def __init__(self, layer, src, out, k, stride):
+        self.layer, self.src, self.out, self.k, self.stride = layer, src, out, k, stride
+
+    def inputs(self):
+        return [self.src]
+
+
+class UpOp(Op):
+    kind = "upsample"
+
+    def __init__(self, layer, src, out, s):
+        self.layer, self.src, self.out, self.s = layer, src, out, s
+
+    def inputs(self):
+        return [self.src]
+
+
+class SEOp(Op):
+    kind = "se"
+
+    def __init__(self, layer, src, out, module):
+        self.layer, self.src, self.out, self.module = layer, src, out, module
+
+    def inputs(self):
+        return [self.src]
+
+
+class YoloOp(Op):
+    kind = "yolo"
+
+    def __init__(self, layer, src, module, index):
+        self.layer, self.src, self.module, self.index = layer, src, module, index
+        self.out = None
+
+    def inputs(self):
+        return [self.src]
+
+
+def _conv_out(h, k, s, p):
+    return (h + 2 * p - k) // s + 1
+
+
+# ---------------------------------------------------------------------------------------------- graph building
+def build_ops(model, H, W, dual):
+    """Block list -> raw op list + the Value visible at every layer index (the reference's `out[]`)."""
+    defs, mods = model.module_defs, model.module_list
+    second = model.net_info.get("second_index") if dual else None
+    if not dual and "second_index" in model.net_info:
+        # the reference would feed a deep feature map into the 3-channel LWIR stem and fail in conv2d
+        raise ValueError("this cfg defines second_index: call model(visible, lwir) with both modalities")
+    img0 = Value(3, H, W, "input", "visible", ext=True)
+    img1 = Value(3, H, W, "input", "lwir", ext=True) if dual else None
+    ops_, vals = [], []
+    cur = img0
+    yolo_idx = 0
+
+    def use(v):
+        v.uses += 1
+        return v
+
+    def add_conv(layer, src, conv, bn, act, tag=""):
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        if conv.kernel_size[0] != conv.kernel_size[1] or conv.stride[0] != conv.stride[1]:
+            raise nat.NativeError(f"layer {layer}: non-square kernels/strides have no native kernel")
+        if conv.in_channels != src.C:
+            raise ValueError(f"layer {layer}: conv expects {conv.in_channels} channels, got {src.C}")
+        out = Value(conv.out_channels, _conv_out(src.H, k, s, p), _conv_out(src.W, k, s, p), "conv", f"L{layer}{tag}")
+        ops_.append(ConvOp(layer, use(src), out, conv, bn, act, tag))
+        return out
+
+    def add_cba(layer, src, cba, tag):
+        mods_ = list(cba.conv)
+        bn = mods_[1] if len(mods_) > 1 and isinstance(mods_[1], nn.BatchNorm2d) else None
+        from build_utils.layers import activation_name
+        return add_conv(layer, src, mods_[0], bn, activation_name(mods_[-1]), tag)
+
+    for i, (d, m) in enumerate(zip(defs, mods)):
+        t = d["type"]
+        if t == "convolutional":
+            src = img1 if (second is not None and i == second) else cur
+            bn = m[1] if d["batch_normalize"] else None
+            cur = add_conv(i, src, m[0], bn, d["activation"])
+        elif t == "depthwiseconvolutional":
+            mid = add_conv(i, cur, m.conv[0], m.conv[1], "relu6", ".dw")
+            cur = add_conv(i, mid, m.conv[3], m.conv[4], "relu6", ".pw")
+        elif t == "inception":
+            x = cur
+            b1 = add_cba(i, x, m.branch1[0], ".b1")
+            b2 = add_cba(i, add_cba(i, x, m.branch2[0], ".b2a"), m.branch2[1], ".b2b")
+            b3 = add_cba(i, add_cba(i, add_cba(i, x, m.branch3[0], ".b3a"), m.branch3[1], ".b3b"), m.branch3[2], ".b3c")
+            pooled = Value(x.C, x.H, x.W, "maxpool", f"L{i}.pool")
+            ops_.append(PoolOp(i, use(x), pooled, 3, 1))
+            b4 = add_cba(i, pooled, m.branch4[1], ".b4")
+            srcs = [b1, b2, b3, b4]
+            cur = Value(sum(s.C for s in srcs), x.H, x.W, "concat", f"L{i}")
+            ops_.append(ConcatOp(i, [use(s) for s in srcs], cur))
+        elif t == "dropout":
+            pass  # identity in eval mode
+        elif t == "se":
+            out = Value(cur.C, cur.H, cur.W, "se", f"L{i}")
+            ops_.append(SEOp(i, use(cur), out, m))
+            cur = out
+        elif t == "maxpool":
+            k, s = d["size"], d["stride"]
+            p = (k - 1) // 2
+            out = Value(cur.C, _conv_out(cur.H, k, s, p), _conv_out(cur.W, k, s, p), "maxpool", f"L{i}")
+            ops_.append(PoolOp(i, use(cur), out, k, s))
+            cur = out
+        elif t == "upsample":
+            s = d["stride"]
+            out = Value(cur.C, cur.H * s, cur.W * s, "upsample", f"L{i}")
+            ops_.append(UpOp(i, use(cur), out, s))
+            cur = out
+        elif t == "route":
+            srcs = [vals[l] for l in m.layers]
+            if len(srcs) == 1:
+                cur = srcs[0]  # alias, like FeatureConcat with a single layer (layers.py:44)
+            else:
+                if any((s.H, s.W) != (srcs[0].H, srcs[0].W) for s in srcs):
+                    raise ValueError(f"layer {i}: route sources have different spatial sizes")
+                cur = Value(sum(s.C for s in srcs), srcs[0].H, srcs[0].W, "concat", f"L{i}")
+                ops_.append(ConcatOp(i, [use(s) for s in srcs], cur))
+        elif t == "shortcut":
+            others = [vals[l] for l in m.layers]
+            out = Value(cur.C, cur.H, cur.W, "add", f"L{i}")
+            ops_.append(AddOp(i, use(cur), [use(o) for o in others], out, m))
+            cur = out
+        elif t == "yolo":
+            ops_.append(YoloOp(i, use(cur), m, yolo_idx))
+            yolo_idx += 1
+        elif t == "avgpool":
+            raise nat.NativeError(f"layer {i}: [avgpool] is not part of any detection cfg and has no native kernel")
+        else:
+            pass  # the reference only prints a warning and passes x through an empty Sequential
+        vals.append(cur)
+    return ops_, vals, img0, img1
+
+
+def fuse(ops_):
+    """Peephole fusion: conv -> (+ residual) -> (upsample x2)."""
+    out, k = [], 0
+    while k < len(ops_):
+        op = ops_[k]
+        if isinstance(op, ConvOp) and op.flavor == "dense":
+            nxt = ops_[k + 1] if k + 1 < len(ops_) else None
+            if (isinstance(nxt, AddOp) and not nxt.module.weight and len(nxt.others) == 1 and op.out.uses == 1
+                    and (nxt.x is op.out or nxt.others[0] is op.out) and nxt.x is not nxt.others[0]):
+                other = nxt.others[0] if nxt.x is op.out else nxt.x
+                if (other.C, other.H, other.W) == (op.out.C, op.out.H, op.out.W) and not other.ext:
+                    op.res = other
+                    op.out = nxt.out
+                    op.out.kind = "conv"
+                    k += 1
+                    nxt = ops_[k + 1] if k + 1 < len(ops_) else None
+            if (isinstance(nxt, UpOp) and nxt.s == 2 and nxt.src is op.out and op.out.uses == 1
+                    and op.res is None):
+                op.upsample2x = True
+                op.out = nxt.out
+                op.out.kind = "conv"
+                k += 1
+        out.append(op)
+        k += 1
+    return out
+
+
+def mark_heads(ops_):
+    """Head convs (no BN, linear) that only feed [yolo] blocks keep their logits in fp32."""
+    consumers = {}
+    for op in ops_:
+        for v in op.inputs():
+            consumers.setdefault(id(v), []).append(op)
+    for op in ops_:
+        if isinstance(op, ConvOp) and op.flavor == "dense" and op.bn is None and op.act == "linear" \
+                and op.res is None and not op.upsample2x:
+            cons = consumers.get(id(op.out), [])
+            if cons and all(isinstance(c, YoloOp) for c in cons):
+                op.out_f32 = True
+                op.out.f32 = True
+
+
+def place_concats(ops_):
+    """Let producers write directly into the channel slices of concat buffers."""
+    for op in ops_:
+        if not isinstance(op, ConcatOp):
+            continue
+        off = 0
+        seen = set()
+        for s in op.srcs:
+            can_place = (s.place is None and not s.ext and s.kind != "concat" and not s.f32 and id(s) not in seen
+                         and s.C % 8 == 0 and off % 8 == 0)
+            if can_place:
+                s.place = (op.out, off)
+            else:
+                op.copies.append((s, off))
+            seen.add(id(s))
+            off += s.C
+
+
+def liveness(ops_):
+    for k, op in enumerate(ops_):
+        outs = [op.out] if getattr(op, "out", None) is not None else []
+        for v in outs:
+            if v.first is None:
+                # stem outputs are written by the eager stem launches that precede the (graph) body
+                v.first = -1 if (isinstance(op, ConvOp) and op.flavor == "stem") else k
+            v.last = k if v.last is None else max(v.last, k)
+        for v in op.inputs():
+            v.last = k if v.last is None else max(v.last, k)
+            if v.first is None:
+                v.first = 0
+
+
+class WeightBank:
+    """Packed weights / folded BN vectors per conv module, refreshed in place when parameters change."""
+
+    def __init__(self):
+        self.entries = {}     # (id(conv), dtype, flavor) -> dict
+        self.signature = None
+
+    @staticmethod
+    def model_signature(tensors):
+        return tuple(t._version for t in tensors)
+
+    def get(self, conv, bn, dtype, flavor):
+        key = (id(conv), dtype, flavor)
+        e = self.entries.get(key)
+        if e is None:
+            e = {"conv": conv, "bn": bn, "dtype": dtype, "flavor": flavor}
+            self._fill(e, first=True)
+            self.entries[key] = e
+        return e
+
+    def _fill(self, e, first):
+        conv, bn, dtype, flavor = e["conv"], e["bn"], e["dtype"], e["flavor"]
+        k = conv.kernel_size[0]
+        if flavor == "dense":
+            w = ops.pack_conv_weight(conv.weight, dtype)
+        elif flavor == "stem":
+            w = conv.weight.detach().float().permute(0, 2, 3, 1).contiguous()
+        else:  # depthwise: [k][k][C] fp32
+            w = conv.weight.detach().float().reshape(conv.out_channels, k, k).permute(1, 2, 0).contiguous()
+        scale, bias = ops.fold_bn(conv, bn)
+        if first:
+            e["w"], e["scale"], e["bias"] = w, scale, bias
+        else:  # keep device addresses stable: captured graphs hold them
+            e["w"].copy_(w)
+            if scale is not None:
+                e["scale"].copy_(scale)
+            if bias is not None:
+                e["bias"].copy_(bias)
+
+    def refresh(self):
+        for e in self.entries.values():
+            self._fill(e, first=False)
+
+
+class Plan:
+    def __init__(self, model, bank, B, H, W, dtype, dual, device):
+        self.B, self.dtype, self.device, self.dual = B, dtype, device, dual
+        raw, vals, self.img0, self.img1 = build_ops(model, H, W, dual)
+        self.ops = fuse(raw)
+        mark_heads(self.ops)
+        place_concats(self.ops)
+        liveness(self.ops)
+        self._allocate()
+        self._bind(model, bank)
+        self.graph = None
+        self.graph_failed = False
+
+    # ---- storage --------------------------------------------------------------------------------
+    def _allocate(self):
+        reuse = os.environ.get("DYK_NO_REUSE", "0") != "1"
+        roots = {}
+        order = []
+        for op in self.ops:
+            v = getattr(op, "out", None)
+            if v is None:
+                continue
+            root = v.place[0] if v.place else v
+            if id(root) not in roots:
+                roots[id(root)] = [root, v.first, v.last]
+                order.append(id(root))
+            r = roots[id(root)]
+            r[1] = min(r[1], v.first)
+            r[2] = max(r[2], v.last if v.last is not None else v.first)
+        # a concat root's own first/last (its ConcatOp index and its consumers) were merged above through
+        # the ConcatOp's `out`; members extend the interval backwards to their producers.
+        free = {}     # (shape, dtype) -> list of (tensor, free_after_op)
+        self.bytes_allocated = 0
+        for rid in sorted(order, key=lambda r: roots[r][1]):
+            root, first, last = roots[rid]
+            dt = torch.float32 if root.f32 else self.dtype
+            shape = (self.B, root.H, root.W, root.C)
+            buf = None
+            if reuse:
+                lst = free.get((shape, dt), [])
+                for j, (t, free_after) in enumerate(lst):
+                    if free_after < first:
+                        buf = t
+                        lst.pop(j)
+                        break
+            if buf is None:
+                buf = torch.empty(shape, dtype=dt, device=self.device)
+                self.bytes_allocated += buf.numel() * buf.element_size()
+            free.setdefault((shape, dt), []).append((buf, last))
+            root.view = View(buf, 0, root.C)
+        for op in self.ops:
+            v = getattr(op, "out", None)
+            if v is not None and v.place:
+                parent, off = v.place
+                v.view = View(parent.view.buf, off, v.C)
+
+    # ---- launches -------------------------------------------------------------------------------
+    def _bind(self, model, bank):
+        self.stem_steps, self.steps = [], []
+        self.yolo = []
+        yolos = [op for op in self.ops if isinstance(op, YoloOp)]
+        rows_total = sum(op.module.na * op.src.H * op.src.W for op in yolos)
+        no = yolos[0].module.no if yolos else 0
+        self.io = torch.empty((self.B, rows_total, no), dtype=torch.float32, device=self.device) if yolos else None
+        self.p_outs = []
+        row_off = 0
+        dev = self.device
+        for op in self.ops:
+            if isinstance(op, ConvOp):
+                fl = op.flavor
+                e = bank.get(op.conv, op.bn, self.dtype, fl)
+                k, s, p = op.conv.kernel_size[0], op.conv.stride[0], op.conv.padding[0]
+                if fl == "stem":
+                    which = 0 if op.src is self.img0 else 1
+                    self.stem_steps.append((which, e, op.out.view, dict(k=k, stride=s, pad=p, act=op.act)))
+                elif fl == "dense":
+                    kw = dict(k=k, stride=s, pad=p, act=op.act, res=op.res.view if op.res is not None else None,
+                              upsample2x=op.upsample2x, out_f32=op.out_f32)
+                    self.steps.append(_ConvStep(op.src.view, e, op.out.view, kw))
+                else:
+                    self.steps.append(_Call(ops.nhwc_dwconv, op.src.view, e["w"], e["scale"], e["bias"], op.out.view,
+                                            k=k, stride=s, pad=p, act=op.act))
+            elif isinstance(op, AddOp):
+                self._bind_add(op)
+            elif isinstance(op, ConcatOp):
+                for s, off in op.copies:
+                    if s.f32:
+                        raise nat.NativeError(f"layer {op.layer}: cannot concatenate an fp32 head tensor")
+                    self.steps.append(_Call(ops.nhwc_copy, s.view, View(op.out.view.buf, op.out.view.c_off + off, s.C)))
+            elif isinstance(op, PoolOp):
+                self.steps.append(_Call(ops.nhwc_maxpool, op.src.view, op.out.view, op.k, op.stride))
+            elif isinstance(op, UpOp):
+                self.steps.append(_Call(ops.nhwc_upsample, op.src.view, op.out.view, op.s))
+            elif isinstance(op, SEOp):
+                w1, b1, w2, b2 = ops.se_weights(op.module.fc1, op.module.fc2)
+                hold = {"w1": w1, "b1": b1, "w2": w2, "b2": b2, "mod": op.module}
+                self._se_holds = getattr(self, "_se_holds", []) + [hold]
+                pooled = torch.empty((self.B, op.src.C), dtype=torch.float32, device=dev)
+                gate = torch.empty((self.B, op.src.C), dtype=torch.float32, device=dev)
+                self.steps.append(_Call(ops.nhwc_se, op.src.view, op.out.view, w1, b1, w2, b2, pooled, gate))
+            elif isinstance(op, YoloOp):
+                m = op.module
+                ny, nx = op.src.H, op.src.W
+                if (m.nx, m.ny) != (nx, ny) or m.grid is None or m.anchor_vec.device != dev:
+                    m.create_grids((nx, ny), dev)
+                if not op.src.f32:
+                    raise nat.NativeError(f"layer {op.layer}: [yolo] must follow a linear conv without batch norm")
+                p_out = torch.empty((self.B, m.na, ny, nx, m.no), dtype=torch.float32, device=dev)
+                self.p_outs.append(p_out)
+                anchor = m.anchor_vec.to(dev).float().contiguous()
+                self.steps.append(_Call(ops.yolo_decode, op.src.view.buf, op.src.view.stride, p_out, self.io,
+                                        N=self.B, ny=ny, nx=nx, na=m.na, no=m.no, anchor_vec=anchor, stride=m.stride,
+                                        v4=m.bf_type == "yolov4", rows_total=rows_total, row_off=row_off, in_kind=2))
+                if m.bf_type not in ("yolov3", "yolov4"):
+                    raise TypeError("bounding box predication error")
+                row_off += m.na * ny * nx
+        self.launches_per_forward = len(self.stem_steps) + sum(s.launches for s in self.steps)
+
+    def _bind_add(self, op):
+        m = op.module
+        x = op.x
+        n = len(op.others) + 1
+        wall = None
+        if m.weight:
+            wall = torch.empty(n, dtype=torch.float32, device=self.device)
+            self.steps.append(_Call(ops.fusion_weights, m.w, wall))
+        cur = x.view
+        for i, a in enumerate(op.others):
+            last = i == len(op.others) - 1
+            if a.C != x.C or (m.weight and n > 2):
+                raise nat.NativeError(
+                    f"layer {op.layer}: channel-mismatched / >2-way weighted shortcut is only available through "
+                    "build_utils.layers.WeightedFeatureFusion.forward (no shipped cfg uses it)")
+            dst = op.out.view if last else ops.new_view(self.B, x.H, x.W, x.C, self.dtype, self.device)
+            self.steps.append(_Call(ops.nhwc_add, cur, a.view, dst, wall))
+            cur = dst
+
+    def refresh_se(self):
+        for h in getattr(self, "_se_holds", []):
+            w1, b1, w2, b2 = ops.se_weights(h["mod"].fc1, h["mod"].fc2)
+            h["w1"].copy_(w1); h["b1"].copy_(b1); h["w2"].copy_(w2); h["b2"].copy_(b2)
+
+    # ---- execution ------------------------------------------------------------------------------
+    def run_stems(self, x, y):
+        for which, e, out, kw in self.stem_steps:
+            ops.nhwc_stem(x if which == 0 else y, e["w"], e["scale"], e["bias"], out, **kw)
+
+    def run_body(self):
+        for s in self.steps:
+            s()
+
+    def capture(self):
+        g = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(g):
+                self.run_body()
+            self.graph = g
+        except Exception:  # noqa: BLE001 - fall back to eager launches of the same native kernels
+            self.graph_failed = True
+            self.graph = None
+            torch.cuda.synchronize()
+
+
+class _Call:
+    launches = 1
+
+    def __init__(self, fn, *args, **kw):
+        self.fn, self.args, self.kw = fn, args, kw
+        if fn is ops.nhwc_se:
+            self.launches = 4
+
+    def __call__(self):
+        self.fn(*self.args, **self.kw)
+
+
+class _ConvStep:
+    launches = 1
+
+    def __init__(self, x, e, y, kw):
+        self.x, self.e, self.y, self.kw = x, e, y, kw
+
+    def __call__(self):
+        e = self.e
+        ops.nhwc_conv(self.x, e["w"], e["scale"], e["bias"], self.y, cout=e["conv"].out_channels, **self.kw)
+
+
+class PlanCache:
+    """Per-model cache of compiled plans, keyed on everything that changes the launch list."""
+
+    def __init__(self, model):
+        self.model = model
+        self.plans = {}
+        self.bank = WeightBank()
+        self.last_plan = None
+        self._tensors = None
+
+    def invalidate(self):
+        """Parameter storage moved (Module._apply: .to() / .half() / .cuda()): drop plans and packed weights."""
+        self.plans.clear()
+        self.bank = WeightBank()
+        self._tensors = None
+
+    def run(self, x, y):
+        model = self.model
+        if not isinstance(x, torch.Tensor) or x.dim() != 4:
+            raise ValueError("YOLO.forward expects (B, 3, H, W) tensors")
+        ops._require_cuda(x, "YOLO.forward")
+        if model.training:
+            raise nat.NativeError(
+                "YOLO.forward in training mode: the train-mode (batch-statistics BatchNorm + backward) kernels are "
+                "not built yet; call model.eval() — there is no PyTorch fallback")
+        if y is not None and (y.shape != x.shape or y.device != x.device):
+            raise ValueError("visible and LWIR batches must have the same shape and device")
+        dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else model.compute_dtype
+        if dtype not in (torch.float16, torch.bfloat16):
+            raise nat.NativeError(f"compute dtype {dtype} is not supported (float16 / bfloat16)")
+
+        def prep(t):
+            if t is None:
+                return None
+            if t.dtype not in (torch.float32, torch.uint8):
+                t = t.float()
+            return t.contiguous()
+
+        x, y = prep(x), prep(y)
+        if y is not None and y.dtype != x.dtype:
+            raise ValueError("visible and LWIR batches must have the same dtype")
+        B, _, H, W = x.shape
+        p0 = next(model.parameters())
+        if p0.device != x.device:
+            raise ValueError(f"model is on {p0.device} but the input is on {x.device}")
+        if self._tensors is None:
+            self._tensors = list(model.parameters()) + list(model.buffers())
+        sig = WeightBank.model_signature(self._tensors)
+        if self.bank.signature is not None and sig != self.bank.signature:
+            # in-place updates (optimizer.step, load_state_dict): re-pack into the same device buffers
+            self.bank.refresh()
+            for pl in self.plans.values():
+                pl.refresh_se()
+        self.bank.signature = sig
+        key = (B, H, W, dtype, y is not None, x.device)
+        plan = self.plans.get(key)
+        with torch.cuda.device(x.device):
+            if plan is None:
+                plan = Plan(model, self.bank, B, H, W, dtype, y is not None, x.device)
+                self.plans[key] = plan
+            self.last_plan = plan
+            plan.run_stems(x, y)
+            if model.use_cuda_graph and not plan.graph_failed and not torch.cuda.is_current_stream_capturing():
+                if plan.graph is None:
+                    plan.run_body()          # warm-up: one-time attribute / driver-entry-point setup
+                    torch.cuda.synchronize()
+                    plan.run_stems(x, y)
+                    plan.capture()
+                if plan.graph is not None:
+                    plan.graph.replay()
+                    nat.count_launches(plan.launches_per_forward - len(plan.stem_steps))
+                else:
+                    plan.run_body()
+            else:
+                plan.run_body()
+        io = plan.io.clone()
+        p = tuple(t.clone() for t in plan.p_outs)
+        return io, p

@@ -80,15 +80,17 @@ typedef struct dyk_conv_params {
 } dyk_conv_params;
 int dyk_conv2d_fwd(const dyk_conv_params* p, void* stream);
 
-/* ---- first-layer convolution reading the caller's NCHW fp32 frames ---------------------------
+/* ---- first-layer convolution reading the caller's NCHW frames ----------------------------------
  * Replaces the stem nn.Conv2d+BN+act (models.py:35-36: in_channels=3, also at second_index) fused
  * with the NCHW->NHWC / fp32->dtype conversion.  Direct (CUDA-core) kernel, Cin <= 4.
- * w is fp32 [Cout][kh][kw][Cin].
+ * w is fp32 [Cout][kh][kw][Cin].  x_kind 0: x is fp32; x_kind 1: x is uint8 and is normalised as the
+ * reference's callers do (`imgs.float() / 255.0`, train_utils/kaist_train_eval_utils.py:54-55,
+ * evaluate.py:67-68) inside the kernel.
  */
-int dyk_conv2d_stem_nchw_fwd(const float* x_nchw, const float* w, const float* scale, const float* bias,
+int dyk_conv2d_stem_nchw_fwd(const void* x_nchw, const float* w, const float* scale, const float* bias,
                              void* y, int64_t y_pix_stride, int32_t N, int32_t H, int32_t W, int32_t Cin,
                              int32_t Cout, int32_t k, int32_t stride, int32_t pad, int32_t act,
-                             int32_t dtype, void* stream);
+                             int32_t dtype, int32_t x_kind, void* stream);
 
 /* ---- depthwise convolution + BN + activation ---------------------------------------------------
  * Replaces nn.Conv2d(groups=C) (+BN+act): models.py:41 (groups key) and
