@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Headline benchmark: paired RGB+LWIR 640x512 frames/s through the dual-stream YOLO hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--cfg NAME] [--batch B]
+
+A step = one batch of synthetic paired frames through ``model(visible, lwir)`` (eval) followed by the batched
+``non_max_suppression`` — what evaluate.py does per batch (reference evaluate.py:70-73).  Workload at N=1 is
+BASELINE.json configs[1]: kaist_dyolov3_add_sl.cfg, 512x640 (HxW), batch 16, fp16.  With N>1 (torchrun, one
+rank per GPU) every rank runs the same per-GPU batch on its own shard of frames — the path has no exchange
+step in inference, so scaling is "weak" and there is no data-path collective; only the timing is reduced
+(max over ranks).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` goes through the public API
+with pinned host uint8 frames (H2D inside the timed region, detections read back), `roofline` is for the
+tcgen05 convolution kernel family (FLOPs of all dense convs in the step / their summed CUDA-event time),
+`cpu_baseline` is the oracle port timed on this box's host cores on a bounded sample.
+`--impl reference` times that CPU port alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent
+PKG = REPO / "double-yolo-kaist_b200"
+for p in (str(REPO), str(PKG)):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "paired RGB+LWIR 640x512 frames/sec (forward + batched NMS, eval)"
+UNIT = "frames/s"
+H, W = 512, 640
+CONF, IOU = 0.01, 0.6   # evaluate.py:73
+FALLBACK_PEAK_TFLOPS, FALLBACK_PEAK_GBS = 1590.0, 6650.0   # B200_PROFILING.md fallback
+
+
+def peaks():
+    f = REPO / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            d = json.loads(f.read_text())
+            return float(d.get("bf16_tflops", FALLBACK_PEAK_TFLOPS)), float(d.get("hbm_gbs", FALLBACK_PEAK_GBS)), "measured"
+        except Exception:  # noqa: BLE001
+            pass
+    return FALLBACK_PEAK_TFLOPS, FALLBACK_PEAK_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_frames(B, seed):
+    g = torch.Generator().manual_seed(seed)
+    v = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=g)
+    l = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=g)
+    return v, l
+
+
+def oracle_objects(cfg_name):
+    from dyk import cfg_zoo
+    from oracle import darknet_ref as dr
+    from oracle import weights as ow
+    path = cfg_zoo.materialize(cfg_name)
+    ref = dr.DarknetRef(path)
+    st = ow.make_calibrated_state(ref, seed=0)
+    return path, ref, st
+
+
+def time_cpu_port(ref, st, frames_per_step, steps, warmup, budget_s=25.0):
+    """The reference's algorithm (oracle port: same torch CPU ops the reference dispatches to + numpy NMS
+    restatement) on the host cores.  Returns (frames/s, steps actually timed)."""
+    from oracle import nms_ref
+    dual = "second_index" in ref.net
+    v8, l8 = synthetic_frames(frames_per_step, seed=100)
+    v, l = v8.float() / 255.0, (l8.float() / 255.0 if dual else None)
+
+    def step():
+        with torch.no_grad():
+            io, _ = ref.forward(st, v, l)
+        nms_ref.non_max_suppression(io.numpy(), CONF, IOU, multi_label=False)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        step()
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return frames_per_step * done / dt, done, dt
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    _, ref, st = oracle_objects(args.cfg)
+    fps, done, dt = time_cpu_port(ref, st, args.ref_frames, args.steps, min(args.warmup, 1), budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "warmup": min(args.warmup, 1), "ms_per_step": dt / done * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.cfg} {W}x{H} eval forward + NMS", "batch_per_step": args.ref_frames,
+                   "note": "CPU port of the reference path (same torch CPU ops); bounded sample of the bs-16 workload"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{done} steps of {args.ref_frames} paired frames, fp32, torch threads={os.cpu_count()}"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def conv_breakdown(plan, x, y, iters=3):
+    """Per-launch CUDA-event timing of the captured plan run eagerly: time and FLOPs of the tcgen05 conv
+    launches and total of everything else (each launch is bracketed by events on the launching stream)."""
+    from dyk.plan import _ConvStep
+    per = []
+    for it in range(iters + 1):
+        plan.run_stems(x, y)
+        evs = []
+        for s in plan.steps:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            s()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        if it == 0:
+            continue
+        per.append([a.elapsed_time(b) for a, b in evs])
+    mean = [sum(col) / len(col) for col in zip(*per)]
+    conv_ms = sum(t for t, s in zip(mean, plan.steps) if isinstance(s, _ConvStep))
+    other_ms = sum(t for t, s in zip(mean, plan.steps) if not isinstance(s, _ConvStep))
+    flops = 0.0
+    n_conv = 0
+    for s in plan.steps:
+        if isinstance(s, _ConvStep):
+            n_conv += 1
+            k = s.kw["k"]
+            up = 4 if s.kw["upsample2x"] else 1
+            opix = s.y.N * s.y.H * s.y.W // up
+            flops += 2.0 * opix * s.e["conv"].out_channels * s.x.C * k * k
+    return conv_ms, other_ms, flops, n_conv
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--cfg", default="kaist_dyolov3_add_sl.cfg")
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--ref-frames", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import models
+    from build_utils.utils import nms_raw
+    from dyk import _native as nat
+
+    path, ref, st = oracle_objects(args.cfg)
+    model = models.YOLO(path, (H, W))
+    model.load_state_dict(st, strict=True)
+    model = model.to(dev).eval()
+    model.compute_dtype = torch.float16 if args.dtype == "fp16" else torch.bfloat16
+    dual = "second_index" in model.net_info
+    B = args.batch
+
+    # distinct frames per rank and per step slot (a ring of host batches; pinned for the e2e leg)
+    ring = 4
+    host = [tuple(t.pin_memory() for t in synthetic_frames(B, seed=1000 * rank + i)) for i in range(ring)]
+    resident = [(v.to(dev), l.to(dev)) for v, l in host]
+
+    def step_resident(i):
+        v, l = resident[i % ring]
+        with torch.no_grad():
+            io, _ = model(v, l) if dual else model(v)
+        return nms_raw(io, CONF, IOU, False, None, False, 100)
+
+    def step_e2e(i):
+        v, l = host[i % ring]
+        v, l = v.to(dev, non_blocking=True), l.to(dev, non_blocking=True)
+        with torch.no_grad():
+            io, _ = model(v, l) if dual else model(v)
+        out, counts = nms_raw(io, CONF, IOU, False, None, False, 100)
+        return out.cpu(), counts.cpu()     # detections read back: the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(args.warmup):
+        step_resident(i)
+        step_e2e(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = nat.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = nat.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps)
+
+    value = world * B * args.steps / (ms / 1e3)
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        plan = model._plans.last_plan
+        v, l = resident[0]
+        conv_ms, other_ms, flops, n_conv = conv_breakdown(plan, v, l if dual else None)
+        peak_tf, peak_gb, peak_kind = peaks()
+        achieved = flops / (conv_ms / 1e3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"{args.cfg} {W}x{H} eval forward + batched NMS, batch {B}/GPU, seeded calibrated "
+                                   f"random weights", "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"dp{world} (independent shards, no data-path collective)",
+                       "l2": "per-step working set (231 MB weights + >5 GB activations) exceeds the 126 MB L2; "
+                             "4 distinct input batches cycled; no explicit flush",
+                       "conf_thres": CONF, "iou_thres": IOU},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": 2 * B * 3 * H * W, "d2h_bytes_per_step": B * 100 * 6 * 4 + B * 4},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_kind,
+                         "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all dense convs of the step)",
+                         "launches_per_step": n_conv, "conv_ms_per_step": conv_ms, "other_kernels_ms_per_step": other_ms,
+                         "algorithmic_gflop_per_step": flops / 1e9},
+            "cuda_graph": plan.graph is not None,
+        }
+        if not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count())
+            fps, done, dt = time_cpu_port(ref, st, args.ref_frames, 6, 1, budget_s=20.0)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"{done} steps of {args.ref_frames} paired frames (fp32 oracle port, "
+                                              f"torch threads={os.cpu_count()}, {dt:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -12,6 +12,18 @@ __device__ __forceinline__ float mish_f(float x) {
   return x * __fdividef(n, n + 2.f);
 }
 
+// compile-time activation (conv epilogue)
+template <int kAct>
+__device__ __forceinline__ float act_apply(float x) {
+  if constexpr (kAct == DYK_ACT_LEAKY) return fmaxf(x, 0.1f * x);
+  else if constexpr (kAct == DYK_ACT_MISH) return mish_f(x);
+  else if constexpr (kAct == DYK_ACT_RELU) return fmaxf(x, 0.f);
+  else if constexpr (kAct == DYK_ACT_RELU6) return fminf(fmaxf(x, 0.f), 6.f);
+  else if constexpr (kAct == DYK_ACT_HARDSWISH) return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  else if constexpr (kAct == DYK_ACT_HARDSIGMOID) return fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  else return x;
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
     case DYK_ACT_LEAKY: return x > 0.f ? x : 0.1f * x;

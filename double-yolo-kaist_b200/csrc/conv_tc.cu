@@ -20,8 +20,8 @@
 //  * epilogue: tcgen05.ld -> scale/bias/activation (+ residual) in fp32 -> fp16/bf16 -> swizzled smem
 //              staging -> TMA store (clipped at tensor edges; 4 parity stores when upsampling).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_idx & 3).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quarter = warp_idx & 3; two warps per quarter split the columns).
 #include "common.h"
 #include "ptx.cuh"
 #include "act.cuh"
@@ -54,7 +54,9 @@ struct ConvKArgs {
   long long res_pix_stride;
 };
 
-constexpr int kNumThreads = 192;
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumEpiThreads = kNumEpiWarps * 32;
+constexpr int kNumThreads = 64 + kNumEpiThreads;   // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue
 constexpr int kBlockM = 128;
 
 template <int BLOCK_N, int BLOCK_K>
@@ -65,15 +67,17 @@ struct ConvSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = kBlockM * kStoreC * 2;          // one store group
   static constexpr int kNumStaging = 2;
+  static constexpr int kVecBytes = 2 * BLOCK_N * 4;                    // per-tile scale + bias vectors
   static constexpr int kBarrierBytes = 1024;
-  static constexpr int kBudget = 227 * 1024 - kBarrierBytes - kNumStaging * kStagingBytes - 1024 /*align*/;
+  static constexpr int kBudget = 227 * 1024 - kBarrierBytes - kVecBytes - kNumStaging * kStagingBytes - 1024 /*align*/;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kTotal = kStages * kStageBytes + kNumStaging * kStagingBytes + kBarrierBytes + 1024;
+  static constexpr int kTotal =
+      kStages * kStageBytes + kNumStaging * kStagingBytes + kVecBytes + kBarrierBytes + 1024;
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiThreads) : "memory"); }
 
 template <bool kBf16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -94,14 +98,150 @@ __device__ __forceinline__ float2 unpack2(uint32_t v) {
   }
 }
 
+struct TileCoord {
+  int nblk, w0, h0, n0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const ConvKArgs& p, int tile) {
+  TileCoord t;
+  t.nblk = tile % p.n_blocks;
+  const int mt = tile / p.n_blocks;
+  const int tww = mt % p.tiles_w;
+  const int thh = (mt / p.tiles_w) % p.tiles_h;
+  const int tb = mt / (p.tiles_w * p.tiles_h);
+  t.w0 = tww * p.tw;
+  t.h0 = thh * p.th;
+  t.n0 = tb * p.tn;
+  return t;
+}
+
+// Epilogue of one 128 x BLOCK_N accumulator tile, executed by the 8 epilogue warps.
+// Thread (q = warp & 3, lane, half = epilogue warp >> 2) owns tile row q*32+lane and, in every store group of
+// kStoreC channels, the `half`-th half of the group's columns.  kAct is a compile-time activation so that
+// only one code path is resident in the instruction cache.
+template <int BLOCK_N, int BLOCK_K, bool kBf16, int kAct>
+__device__ __forceinline__ void epilogue_tile(const ConvTmaps& tm, const ConvKArgs& p, const TileCoord& tc,
+                                              uint32_t t_row, uint8_t* staging, float* svec, int& sbuf,
+                                              uint64_t* tempty, int q, int lane, int half, bool store_thread) {
+  using S = ConvSmem<BLOCK_N, BLOCK_K>;
+  constexpr int kStoreC = S::kStoreC;
+  constexpr int kStoreRowBytes = kStoreC * 2;       // 128 or 64
+  constexpr int kCols = kStoreC / 2;                // columns per thread per group: 32 or 16
+  constexpr int kGroups = BLOCK_N / kStoreC;
+  const int row = q * 32 + lane;
+  const int wi = row % p.tw;
+  const int hi = (row / p.tw) % p.th;
+  const int ni = row / (p.tw * p.th);
+  const int wo = tc.w0 + wi, ho = tc.h0 + hi, nn = tc.n0 + ni;
+  const bool pix_ok = (wo < p.Wo) && (ho < p.Ho) && (nn < p.N);
+  const long long pix = (static_cast<long long>(nn) * p.Ho + ho) * p.Wo + wo;
+  const int n_base = tc.nblk * BLOCK_N;
+  const bool has_res = p.res != nullptr;
+
+  // per-tile scale / bias vectors -> shared memory (one element per epilogue thread)
+  {
+    const int t = (half * 4 + q) * 32 + lane;
+    if (t < BLOCK_N) {
+      svec[t] = p.scale ? __ldg(p.scale + n_base + t) : 1.f;
+      svec[BLOCK_N + t] = p.bias ? __ldg(p.bias + n_base + t) : 0.f;
+    }
+  }
+  // residual values of this thread's columns in group 0 are fetched while the MMAs still run
+  uint4 rres[kCols / 8];
+  auto load_res = [&](int g) {
+    const int c0 = n_base + g * kStoreC + half * kCols;
+    const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (pix * p.res_pix_stride + c0) * 2;
+#pragma unroll
+    for (int j = 0; j < kCols / 8; ++j) {
+      rres[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (has_res && pix_ok && c0 + j * 8 < p.Cout_store) rres[j] = __ldg(reinterpret_cast<const uint4*>(rp) + j);
+    }
+  };
+  load_res(0);
+
+#pragma unroll 1
+  for (int g = 0; g < kGroups; ++g) {
+    const int cg0 = n_base + g * kStoreC;   // first output channel of this store group
+    if (cg0 >= p.Cout_store) break;          // uniform: whole group is beyond the tensor
+    const bool last_group = (g == kGroups - 1) || (cg0 + kStoreC >= p.Cout_store);
+    if (!p.out_f32 && store_thread) tma_store_wait_read<1>();  // staging[sbuf] no longer read by an older store
+    epi_bar_sync();                                            // (also publishes svec on g == 0)
+    uint8_t* sbase = staging + sbuf * S::kStagingBytes;
+
+    uint32_t v[kCols];
+    if constexpr (kCols == 32) tmem_ld_32x32b_x32(t_row + g * kStoreC + half * kCols, v);
+    else tmem_ld_32x32b_x16(t_row + g * kStoreC + half * kCols, v);
+    tmem_ld_wait();
+    if (last_group) {
+      // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+    }
+    const int cl = g * kStoreC + half * kCols;   // first column (within the tile) of this thread
+    float o[kCols];
+#pragma unroll
+    for (int j = 0; j < kCols; j += 4) {
+      const float4 sc = *reinterpret_cast<const float4*>(svec + cl + j);
+      const float4 bi = *reinterpret_cast<const float4*>(svec + BLOCK_N + cl + j);
+      o[j + 0] = act_apply<kAct>(fmaf(__uint_as_float(v[j + 0]), sc.x, bi.x));
+      o[j + 1] = act_apply<kAct>(fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y));
+      o[j + 2] = act_apply<kAct>(fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z));
+      o[j + 3] = act_apply<kAct>(fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w));
+    }
+    if (has_res) {
+#pragma unroll
+      for (int j = 0; j < kCols / 8; ++j) {
+        const uint32_t rr[4] = {rres[j].x, rres[j].y, rres[j].z, rres[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack2<kBf16>(rr[e]);
+          o[j * 8 + e * 2 + 0] += f.x;
+          o[j * 8 + e * 2 + 1] += f.y;
+        }
+      }
+      if (!last_group) load_res(g + 1);
+    }
+    if (p.out_f32) {
+      if (pix_ok) {
+        float* yo = reinterpret_cast<float*>(p.y_f32) + pix * p.y_pix_stride + n_base + cl;
+#pragma unroll
+        for (int j = 0; j < kCols; ++j)
+          if (n_base + cl + j < p.Cout_store) yo[j] = o[j];
+      }
+      continue;
+    }
+    // swizzled staging write: row `row`, this thread's 16-byte chunks of the store row
+#pragma unroll
+    for (int ch = 0; ch < kCols / 8; ++ch) {
+      const int chunk = half * (kCols / 8) + ch;
+      int phys;
+      if constexpr (kStoreRowBytes == 128) phys = chunk ^ (row & 7);
+      else phys = chunk ^ ((row >> 1) & 3);
+      const uint4 val = make_uint4(pack2<kBf16>(o[ch * 8 + 0], o[ch * 8 + 1]), pack2<kBf16>(o[ch * 8 + 2], o[ch * 8 + 3]),
+                                   pack2<kBf16>(o[ch * 8 + 4], o[ch * 8 + 5]), pack2<kBf16>(o[ch * 8 + 6], o[ch * 8 + 7]));
+      *reinterpret_cast<uint4*>(sbase + row * kStoreRowBytes + phys * 16) = val;
+    }
+    fence_proxy_async_smem();
+    epi_bar_sync();
+    if (store_thread) {
+      if (p.upsample2x) {
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) tma_store_4d(&tm.y[pp], sbase, cg0, tc.w0, tc.h0, tc.n0);
+      } else {
+        tma_store_4d(&tm.y[0], sbase, cg0, tc.w0, tc.h0, tc.n0);
+      }
+      tma_store_commit();
+    }
+    sbuf ^= 1;
+  }
+}
+
 template <int BLOCK_N, int BLOCK_K, bool kBf16>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
   using S = ConvSmem<BLOCK_N, BLOCK_K>;
   constexpr int kSwz = BLOCK_K * 2;            // bytes per smem operand row == swizzle span (128 / 64)
   constexpr int kStages = S::kStages;
-  constexpr int kStoreC = S::kStoreC;
-  constexpr int kStoreRowBytes = kStoreC * 2;  // 128 or 64
   constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
   static_assert(BLOCK_K == 64 || BLOCK_K == 32, "BLOCK_K");
@@ -110,7 +250,8 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
   uint8_t* staging = smem + kStages * S::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + S::kNumStaging * S::kStagingBytes);
+  float* svec = reinterpret_cast<float*>(staging + S::kNumStaging * S::kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(svec) + S::kVecBytes);
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + kStages;            // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;        // [2]
@@ -132,7 +273,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], kNumEpiWarps);
     }
     fence_mbar_init();
   }
@@ -142,20 +283,13 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int m_tiles_per_img_grid = p.tiles_w * p.tiles_h;
-
   if (warp_idx == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int nblk = tile % p.n_blocks;
-        const int mt = tile / p.n_blocks;
-        const int tww = mt % p.tiles_w;
-        const int thh = (mt / p.tiles_w) % p.tiles_h;
-        const int tb = mt / m_tiles_per_img_grid;
-        const int w0 = tww * p.tw, h0 = thh * p.th, n0 = tb * p.tn;
+        const TileCoord tc = tile_coord(p, tile);
         for (int tap = 0; tap < taps; ++tap) {
           const int r = tap / p.kw, s = tap - r * p.kw;
           int dh = r - p.pad, dw = s - p.pad;
@@ -172,8 +306,8 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
             uint8_t* sa = stage_base + stage * S::kStageBytes;
             uint8_t* sb = sa + S::kABytes;
             mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-            tma_load_4d(sa, amap, &full_bar[stage], kc * BLOCK_K, w0 + dw, h0 + dh, n0);
-            tma_load_3d(sb, &tm.b, &full_bar[stage], kc * BLOCK_K, tap, nblk * BLOCK_N);
+            tma_load_4d(sa, amap, &full_bar[stage], kc * BLOCK_K, tc.w0 + dw, tc.h0 + dh, tc.n0);
+            tma_load_3d(sb, &tm.b, &full_bar[stage], kc * BLOCK_K, tap, tc.nblk * BLOCK_N);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -210,122 +344,35 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps)
-    const int q = warp_idx & 3;            // TMEM lane quarter owned by this warp
-    const int row = q * 32 + lane;         // row of the 128-row tile == TMEM lane
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int ew = warp_idx - 2;
+    const int q = warp_idx & 3;            // TMEM lane quarter this warp may access
+    const int half = ew >> 2;              // which half of each store group's columns
     const bool store_thread = (threadIdx.x == 64);
-    const int wi = row % p.tw;
-    const int hi = (row / p.tw) % p.th;
-    const int ni = row / (p.tw * p.th);
     int tl = 0;
     int sbuf = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
       const int as = tl & 1;
       const uint32_t aphase = (tl >> 1) & 1;
-      const int nblk = tile % p.n_blocks;
-      const int mt = tile / p.n_blocks;
-      const int tww = mt % p.tiles_w;
-      const int thh = (mt / p.tiles_w) % p.tiles_h;
-      const int tb = mt / m_tiles_per_img_grid;
-      const int w0 = tww * p.tw, h0 = thh * p.th, n0 = tb * p.tn;
-      const int wo = w0 + wi, ho = h0 + hi, nn = n0 + ni;
-      const bool pix_ok = (wo < p.Wo) && (ho < p.Ho) && (nn < p.N);
-      const long long pix = (static_cast<long long>(nn) * p.Ho + ho) * p.Wo + wo;
-
+      const TileCoord tc = tile_coord(p, tile);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
+      // The accumulator wait sits inside the activation-specialised body's caller so that residual / vector
+      // prefetches of the *next* tile are not hoisted above it by accident.
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after_sync();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
-
-#pragma unroll 1
-      for (int g = 0; g < BLOCK_N / kStoreC; ++g) {
-        const int cg0 = nblk * BLOCK_N + g * kStoreC;   // first output channel of this store group
-        if (cg0 >= p.Cout_store) break;                  // uniform: whole group is beyond the tensor
-        if (!p.out_f32) {
-          // staging buffer `sbuf` must no longer be read by an earlier TMA store
-          if (store_thread) tma_store_wait_read<1>();
-          epi_bar_sync();
-        }
-        uint8_t* sbase = staging + sbuf * S::kStagingBytes;
-#pragma unroll
-        for (int cc = 0; cc < kStoreC / 32; ++cc) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_row + g * kStoreC + cc * 32, v);
-          tmem_ld_wait();
-          const int c0 = cg0 + cc * 32;
-          uint32_t packed[16];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + j));
-            if (p.bias) bi = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-            float o0 = apply_act(fmaf(__uint_as_float(v[j + 0]), sc.x, bi.x), p.act);
-            float o1 = apply_act(fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y), p.act);
-            float o2 = apply_act(fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z), p.act);
-            float o3 = apply_act(fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w), p.act);
-            v[j + 0] = __float_as_uint(o0);
-            v[j + 1] = __float_as_uint(o1);
-            v[j + 2] = __float_as_uint(o2);
-            v[j + 3] = __float_as_uint(o3);
-          }
-          if (p.res != nullptr && pix_ok) {
-            const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (pix * p.res_pix_stride + c0) * 2;
-#pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              if (c0 + j8 * 8 < p.Cout_store) {
-                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp) + j8);
-                const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack2<kBf16>(rr[e]);
-                  v[j8 * 8 + e * 2 + 0] = __float_as_uint(__uint_as_float(v[j8 * 8 + e * 2 + 0]) + f.x);
-                  v[j8 * 8 + e * 2 + 1] = __float_as_uint(__uint_as_float(v[j8 * 8 + e * 2 + 1]) + f.y);
-                }
-              }
-            }
-          }
-          if (p.out_f32) {
-            if (pix_ok) {
-              float* yo = reinterpret_cast<float*>(p.y_f32) + pix * p.y_pix_stride + c0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c0 + j < p.Cout_store) yo[j] = __uint_as_float(v[j]);
-            }
-            continue;
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            packed[j] = pack2<kBf16>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-          // swizzled staging write: row `row`, 16-byte chunks cc*4 .. cc*4+3 of the store row
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const int chunk = cc * 4 + ch;
-            int phys;
-            if constexpr (kStoreRowBytes == 128) phys = chunk ^ (row & 7);
-            else phys = chunk ^ ((row >> 1) & 3);
-            uint4 val = make_uint4(packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
-            *reinterpret_cast<uint4*>(sbase + row * kStoreRowBytes + phys * 16) = val;
-          }
-        }
-        if (g == BLOCK_N / kStoreC - 1 || cg0 + kStoreC >= p.Cout_store) {
-          // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
-          tc_fence_before_sync();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[as]);
-        }
-        if (p.out_f32) continue;
-        fence_proxy_async_smem();
-        epi_bar_sync();
-        if (store_thread) {
-          if (p.upsample2x) {
-#pragma unroll
-            for (int pp = 0; pp < 4; ++pp) tma_store_4d(&tm.y[pp], sbase, cg0, w0, h0, n0);
-          } else {
-            tma_store_4d(&tm.y[0], sbase, cg0, w0, h0, n0);
-          }
-          tma_store_commit();
-        }
-        sbuf ^= 1;
+#define DYK_EPI(ACT)                                                                                         \
+  epilogue_tile<BLOCK_N, BLOCK_K, kBf16, ACT>(tm, p, tc, t_row, staging, svec, sbuf, &tempty_bar[as], q, lane, \
+                                              half, store_thread)
+      switch (p.act) {
+        case DYK_ACT_LEAKY: DYK_EPI(DYK_ACT_LEAKY); break;
+        case DYK_ACT_MISH: DYK_EPI(DYK_ACT_MISH); break;
+        case DYK_ACT_RELU: DYK_EPI(DYK_ACT_RELU); break;
+        case DYK_ACT_RELU6: DYK_EPI(DYK_ACT_RELU6); break;
+        case DYK_ACT_HARDSWISH: DYK_EPI(DYK_ACT_HARDSWISH); break;
+        case DYK_ACT_HARDSIGMOID: DYK_EPI(DYK_ACT_HARDSIGMOID); break;
+        default: DYK_EPI(DYK_ACT_LINEAR); break;
       }
+#undef DYK_EPI
     }
     if (store_thread) tma_store_wait_all<0>();
   }
@@ -403,8 +450,9 @@ static int dispatch_n(int block_n, const ConvTmaps& tm, const ConvKArgs& ka, cud
   return fail(DYK_EINVAL, "bad BLOCK_N %d", block_n);
 }
 
-// Picks the N tile: fewest "waves x tile cost" over the SM count; cost of a tile ~ max(BLOCK_N, 64).
-static int pick_block_n(int cout_store, long long m_tiles) {
+// Picks the N tile by a small cycle model: a k-block costs max(MMA issue, L2->SM operand fetch at ~42 B/clk/SM),
+// a tile adds a fixed epilogue/hand-off cost, and the grid runs in waves over the SMs.
+static int pick_block_n(int cout_store, long long m_tiles, int num_kb, int block_k) {
   const int sms = num_sms();
   int best_n = 32;
   double best_cost = 1e30;
@@ -414,7 +462,9 @@ static int pick_block_n(int cout_store, long long m_tiles) {
     if (bn > 32 && bn / 2 >= cout_store) continue;  // more than 2x wider than the layer
     const long long tiles = m_tiles * ceil_div(cout_store, bn);
     const long long waves = (tiles + sms - 1) / sms;
-    const double tile_cost = (bn < 64 ? 64 : bn) + 24;  // + fixed per-tile overhead
+    const double l2 = (128.0 * block_k * 2 + (double)bn * block_k * 2) / 42.0;
+    const double mma = (block_k / 16) * (bn < 64 ? 32.0 : bn / 2.0);
+    const double tile_cost = num_kb * (l2 > mma ? l2 : mma) + 1200.0 + 6.0 * bn;
     const double cost = (double)waves * tile_cost;
     if (cost < best_cost - 1e-9) { best_cost = cost; best_n = bn; }
   }
@@ -494,7 +544,7 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   }
   const int taps = p->kh * p->kw;
   const long long m_tiles = (long long)ceil_div(gW, tw) * ceil_div(gH, th) * ceil_div(gN, tn);
-  const int BN = pick_block_n(p->Cout_store, m_tiles);
+  const int BN = pick_block_n(p->Cout_store, m_tiles, taps * ceil_div(p->Cin, BK), BK);
   {
     const cuuint64_t dims[3] = {(cuuint64_t)p->Cin, (cuuint64_t)taps, (cuuint64_t)p->Cout};
     const cuuint64_t str[2] = {(cuuint64_t)p->Cin * 2, (cuuint64_t)p->Cin * 2 * taps};

@@ -17,6 +17,7 @@
 // All IoU arithmetic uses explicitly rounded fp32 operations (no FMA contraction) in the same order as
 // torchvision's CPU kernel, so kept indices are bit-exact against it.
 #include "common.h"
+#include <cmath>
 
 namespace dyk {
 
@@ -315,7 +316,7 @@ extern "C" __attribute__((visibility("default"))) int64_t dyk_nms_workspace_byte
 }
 
 extern "C" __attribute__((visibility("default"))) int dyk_nms_batched(const float* pred, int32_t B, int32_t rows, int32_t nc, float conf_thres,
-                               float iou_thres, int32_t multi_label, uint64_t classes_mask, int32_t agnostic,
+                               double iou_thres_d, int32_t multi_label, uint64_t classes_mask, int32_t agnostic,
                                int32_t max_num, float* out, int32_t* out_count, void* workspace,
                                int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -323,6 +324,10 @@ extern "C" __attribute__((visibility("default"))) int dyk_nms_batched(const floa
   DYK_REQUIRE(B > 0 && rows > 0 && nc > 0, "dyk_nms_batched: B=%d rows=%d nc=%d", B, rows, nc);
   DYK_REQUIRE(max_num > 0 && max_num <= kMaxKeep, "dyk_nms_batched: max_num=%d (1..%d)", max_num, kMaxKeep);
   multi_label = (multi_label && nc > 1) ? 1 : 0;  // utils.py:404
+  // torchvision's CPU kernel evaluates `float iou > double threshold`.  For fp32 x that is equivalent to
+  // x > t with t the largest fp32 value <= threshold, so the device compares in fp32 against t.
+  float iou_thres = static_cast<float>(iou_thres_d);
+  if (static_cast<double>(iou_thres) > iou_thres_d) iou_thres = nextafterf(iou_thres, -INFINITY);
   DYK_REQUIRE((long long)rows * nc < (1ll << 31), "dyk_nms_batched: too many candidates");
   const int64_t need = dyk_nms_workspace_bytes(B, rows, nc, multi_label);
   DYK_REQUIRE(workspace_bytes >= need, "dyk_nms_batched: workspace %lld < %lld bytes", (long long)workspace_bytes,

@@ -40,8 +40,7 @@ SIGNATURES = {
     "dyk_last_error": (C.c_char_p, []),
     "dyk_check_device": (_i32, []),
     "dyk_conv2d_fwd": (_i32, [C.POINTER(ConvParams), _vp]),
-    "dyk_conv2d_stem_nchw_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
-                                        _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dyk_conv2d_stem_nchw_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64] + [_i32] * 11 + [_vp]),
     "dyk_dwconv2d_fwd": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
                                 _i32, _i32, _i32, _vp]),
     "dyk_fused_add": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _i32, _vp]),
@@ -54,7 +53,7 @@ SIGNATURES = {
     "dyk_yolo_decode": (_i32, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _f32, _i32, _i64,
                                _i64, _i32, _vp]),
     "dyk_nms_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
-    "dyk_nms_batched": (_i32, [_vp, _i32, _i32, _i32, _f32, _f32, _i32, C.c_uint64, _i32, _i32, _vp, _vp,
+    "dyk_nms_batched": (_i32, [_vp, _i32, _i32, _i32, _f32, C.c_double, _i32, C.c_uint64, _i32, _i32, _vp, _vp,
                                _vp, _i64, _vp]),
     "dyk_pack_weights_ohwi": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_nchw_f32_to_nhwc": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),

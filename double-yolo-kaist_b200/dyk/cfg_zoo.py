@@ -98,9 +98,10 @@ def _net_v3(second_index=None):
     return net
 
 
-def _net_v4(second_index):
-    return [("batch", 64), ("subdivisions", 8), ("width", 512), ("height", 512), (";width", 608),
-            (";height", 608), ("channels", 3), ("momentum", "0.949"), ("decay", "0.0005"), ("angle", 0),
+def _net_v4(second_index, commented_size=True):
+    size_notes = [(";width", 608), (";height", 608)] if commented_size else []
+    return [("batch", 64), ("subdivisions", 8), ("width", 512), ("height", 512)] + size_notes + [
+            ("channels", 3), ("momentum", "0.949"), ("decay", "0.0005"), ("angle", 0),
             ("saturation", "1.5"), ("exposure", "1.5"), ("hue", ".1"), ("second_index", second_index),
             ("learning_rate", "0.0013"), ("burn_in", 1000), ("max_batches", 500500), ("policy", "steps"),
             ("steps", "400000,450000"), ("scales", ".1,.1"), ("mosaic", 1)]
@@ -257,10 +258,115 @@ def kaist_dyolov4_fshare_global_concat_se3() -> str:
     return b.text()
 
 
+# ----------------------------------------------------------------------------------------- MobileNetV3
+def _bneck(b: CfgBuilder, exp: int, k: int, out: int, se: bool, act: str, stride: int = 1, res: bool = False):
+    """MobileNetV3 bottleneck as the reference writes it: 1x1 expand (carries the stride) -> depthwise kxk
+    -> [SE] -> 1x1 linear projection -> [residual]."""
+    b.conv(exp, 1, stride=stride, act=act)
+    b.conv(exp, k, groups=exp, act=act)
+    if se:
+        b.se(4)
+    last = b.conv(out, 1, act="linear")
+    if res:
+        last = b.shortcut(-5 if se else -4)
+    return last
+
+
+def _mnv3_front(b: CfgBuilder):
+    b.conv(16, 3, stride=2, act="hard-swish")
+    b.conv(16, 3, groups=16, act="relu")
+    b.conv(16, 1, act="linear")
+    _bneck(b, 64, 3, 24, False, "relu", stride=2)
+    _bneck(b, 72, 3, 24, False, "relu", res=True)
+    _bneck(b, 72, 5, 40, True, "relu", stride=2)
+    _bneck(b, 120, 5, 40, True, "relu", res=True)
+    return _bneck(b, 120, 5, 40, True, "relu", res=True)
+
+
+def _mnv3_stage4(b: CfgBuilder):
+    hs = "hard-swish"
+    _bneck(b, 240, 3, 80, False, hs, stride=2)
+    _bneck(b, 200, 3, 80, False, hs, res=True)
+    _bneck(b, 184, 3, 80, False, hs, res=True)
+    _bneck(b, 184, 3, 80, False, hs, res=True)
+    _bneck(b, 480, 3, 112, True, hs)
+    return _bneck(b, 672, 3, 112, True, hs, res=True)
+
+
+def _mnv3_stage5(b: CfgBuilder):
+    hs = "hard-swish"
+    _bneck(b, 672, 5, 160, True, hs, stride=2)
+    _bneck(b, 960, 5, 160, True, hs, res=True)
+    return _bneck(b, 960, 5, 160, True, hs, res=True)
+
+
+def _cse_light(b: CfgBuilder, a: int, c: int, ch: int):
+    """Lightweight concat-SE fusion: route(a, c) -> depthwise 3x3 (ReLU6) -> SE -> 1x1 linear.
+    Returns (depthwise layer, projection layer)."""
+    b.route(a, c)
+    dw = b.conv(2 * ch, 3, groups=2 * ch, act="relu6")
+    b.se(4)
+    return dw, b.conv(ch, 1, act="linear")
+
+
+def kaist_dyolov4_mobilenetv3_fshare_global_cse3() -> str:
+    """Dual MobileNetV3-large backbones with FSNet re-injection and light concat-SE fusion, SPP + PANet neck
+    built from depthwise-separable convs (reference config/kaist_dyolov4_mobilenetv3_fshare_global_cse3.cfg)."""
+    b = CfgBuilder(_net_v4(second_index=24, commented_size=False))
+    v3 = _mnv3_front(b)
+    assert b.n == 24
+    l3 = _mnv3_front(b)
+    lwir_se3 = l3 - 2                      # SE output inside the last LWIR bottleneck (PANet lateral tap)
+    _, f1 = _cse_light(b, v3, l3, 40)
+    b.shortcut(v3, weighted=True)
+    v4 = _mnv3_stage4(b)
+    b.route(f1)
+    b.shortcut(l3, weighted=True)
+    l4 = _mnv3_stage4(b)
+    dw2, f2 = _cse_light(b, v4, l4, 112)
+    b.shortcut(v4, weighted=True)
+    v5 = _mnv3_stage5(b)
+    b.route(f2)
+    b.shortcut(l4, weighted=True)
+    l5 = _mnv3_stage5(b)
+    _cse_light(b, v5, l5, 160)
+    r6 = "relu6"
+    b.conv(512, 1, act=r6); b.dsconv(1024); b.conv(512, 1, act=r6)
+    _spp(b)
+    b.conv(512, 1, act=r6); b.dsconv(1024); b.conv(512, 1, act=r6)
+    for width, lateral, n_pairs in ((256, dw2, 2), (128, lwir_se3, 2)):
+        b.conv(width, 1, act=r6)
+        b.upsample(2)
+        b.route(lateral)
+        b.conv(width, 1, act=r6)
+        b.route(-1, -3)
+        for _ in range(n_pairs):
+            b.conv(width, 1, act=r6)
+            b.dsconv(width * 2)
+        b.conv(width, 1, act=r6)
+    v4_extra = lambda sxy, rnd=False: ([("random", 1)] if rnd else []) + [
+        ("scale_x_y", sxy), ("iou_thresh", "0.213"), ("cls_normalizer", "1.0"), ("iou_normalizer", "0.07"),
+        ("iou_loss", "ciou"), ("nms_kind", "greedynms"), ("beta_nms", "0.6")]
+    b.dsconv(256)
+    b.conv(18, 1, act="linear", bn=False)
+    b.yolo((0, 1, 2), ANCHORS_V4, v4_extra("1.2"))
+    for width, mask, back, sxy, first_act in ((256, (3, 4, 5), -16, "1.1", r6), (512, (6, 7, 8), -37, "1.05", "leaky")):
+        b.route(-4)
+        b.dsconv(width, stride=2)
+        b.route(-1, back)
+        b.conv(width, 1, act=first_act); b.dsconv(width * 2)
+        b.conv(width, 1, act=r6); b.dsconv(width * 2)
+        b.conv(width, 1, act=r6); b.dsconv(width * 2)
+        b.conv(18, 1, act="linear", bn=False)
+        b.yolo(mask, ANCHORS_V4, v4_extra(sxy, rnd=mask[0] == 6))
+    return b.text()
+
+
 ZOO = {
     "kaist_yolov3.cfg": kaist_yolov3,
     "kaist_dyolov3_add_sl.cfg": kaist_dyolov3_add_sl,
     "kaist_dyolov4_fshare_global_concat_se3.cfg": kaist_dyolov4_fshare_global_concat_se3,
+    "kaist_dyolov4_mobilenetv3_fshare_global_cse3.cfg": kaist_dyolov4_mobilenetv3_fshare_global_cse3,
 }
 
 

@@ -515,7 +515,10 @@ class Plan:
             with torch.cuda.graph(g):
                 self.run_body()
             self.graph = g
-        except Exception:  # noqa: BLE001 - fall back to eager launches of the same native kernels
+        except Exception as exc:  # noqa: BLE001 - fall back to eager launches of the same native kernels
+            import warnings
+            warnings.warn(f"CUDA graph capture of the plan failed ({type(exc).__name__}: {exc}); "
+                          "running the same native kernels as individual launches")
             self.graph_failed = True
             self.graph = None
             torch.cuda.synchronize()

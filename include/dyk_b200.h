@@ -152,10 +152,12 @@ int dyk_yolo_decode(const void* p_nhwc, int64_t p_pix_stride, float* p_out, floa
  * out:  fp32 [B][max_num][6] (x1,y1,x2,y2,score,label), out_count: int32 [B] (0 => reference None).
  * classes_mask: bit k set => class k allowed (0 = no filter; nc <= 64 when used).
  * workspace: device scratch of dyk_nms_workspace_bytes(B, rows, nc, multi_label) bytes.
+ * conf_thres is compared in fp32 (torch compares an fp32 tensor with a Python scalar in fp32); iou_thres
+ * is a double because torchvision's CPU nms compares the fp32 IoU against the double threshold.
  */
 int64_t dyk_nms_workspace_bytes(int32_t B, int32_t rows, int32_t nc, int32_t multi_label);
 int dyk_nms_batched(const float* pred, int32_t B, int32_t rows, int32_t nc, float conf_thres,
-                    float iou_thres, int32_t multi_label, uint64_t classes_mask, int32_t agnostic,
+                    double iou_thres, int32_t multi_label, uint64_t classes_mask, int32_t agnostic,
                     int32_t max_num, float* out, int32_t* out_count, void* workspace,
                     int64_t workspace_bytes, void* stream);
 

@@ -1,0 +1,214 @@
+"""Per-kernel parity on a B200: every native kernel against the same op in plain PyTorch fp32 (the ops the
+reference dispatches to).  Inputs and weights are first rounded to the kernel's storage dtype so the only
+differences left are accumulation order and the final fp16/bf16 rounding; tolerances are written per test."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _setup(native_lib):
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from dyk import _native
+    _native.check_device()
+
+
+def _q(t, dtype):
+    return t.to(dtype).float()
+
+
+def _close(got, want, rtol, atol, what=""):
+    got, want = got.float().cpu(), want.float().cpu()
+    err = (got - want).abs()
+    tol = atol + rtol * want.abs()
+    bad = err > tol
+    assert not bool(bad.any()), (f"{what}: {int(bad.sum())}/{bad.numel()} elements off, max err "
+                                 f"{float(err.max()):.4g} at ref {float(want.flatten()[err.argmax()]):.4g}")
+
+
+def _act_ref(x, act):
+    return {"linear": lambda v: v, "leaky": lambda v: F.leaky_relu(v, 0.1), "mish": F.mish, "relu": F.relu,
+            "relu6": F.relu6, "hard-swish": F.hardswish, "hard-sigmoid": F.hardsigmoid}[act](x)
+
+
+CONV_CASES = [
+    # (N, Cin, H, W, Cout, k, stride, act, residual, upsample, bn)
+    (2, 64, 16, 20, 64, 1, 1, "leaky", False, False, True),
+    (2, 64, 16, 20, 128, 3, 1, "leaky", False, False, True),
+    (2, 128, 16, 20, 128, 3, 1, "mish", True, False, True),
+    (1, 32, 32, 40, 64, 3, 2, "leaky", False, False, True),
+    (2, 64, 17, 23, 96, 3, 2, "mish", False, False, True),      # odd sizes: parity planes + edge clipping
+    (2, 256, 8, 10, 512, 3, 1, "leaky", True, False, True),
+    (2, 512, 4, 5, 256, 1, 1, "leaky", False, True, True),      # fused 2x upsample
+    (1, 1024, 4, 5, 18, 1, 1, "linear", False, False, False),   # detection head (fp32 out path is in the model test)
+    (3, 24, 12, 12, 72, 1, 1, "hard-swish", False, False, True),
+    (2, 40, 10, 14, 120, 1, 1, "relu", False, False, True),
+    (2, 16, 20, 20, 64, 1, 2, "relu6", False, False, True),     # 1x1 stride 2 (MobileNet expansion)
+    (1, 200, 9, 9, 80, 1, 1, "linear", True, False, True),
+    (2, 128, 33, 41, 256, 3, 1, "leaky", False, False, True),
+    (4, 512, 16, 20, 1024, 3, 1, "leaky", False, False, True),
+    (2, 2048, 8, 10, 512, 1, 1, "leaky", False, False, True),
+    (1, 8, 64, 80, 32, 3, 1, "mish", False, False, True),
+    (2, 64, 12, 12, 64, 5, 1, "relu", False, False, True),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_bn_act(case, dtype):
+    from dyk import ops
+    N, Cin, H, W, Cout, k, s, act, res, up, bn = case
+    g = torch.Generator().manual_seed(hash(case) % 2 ** 31)
+    conv = nn.Conv2d(Cin, Cout, k, s, k // 2, bias=not bn)
+    bnm = nn.BatchNorm2d(Cout) if bn else None
+    with torch.no_grad():
+        conv.weight.copy_(_q(torch.randn(conv.weight.shape, generator=g) / (Cin * k * k) ** 0.5, dtype))
+        if bn:
+            bnm.weight.copy_(torch.rand(Cout, generator=g) + 0.5)
+            bnm.bias.copy_(torch.randn(Cout, generator=g) * 0.2)
+            bnm.running_mean.copy_(torch.randn(Cout, generator=g) * 0.2)
+            bnm.running_var.copy_(torch.rand(Cout, generator=g) + 0.5)
+        else:
+            conv.bias.copy_(torch.randn(Cout, generator=g))
+    x = _q(torch.randn((N, Cin, H, W), generator=g), dtype)
+    conv, x = conv.to(DEV).eval(), x.to(DEV)
+    bnm = bnm.to(DEV).eval() if bn else None
+    with torch.no_grad():
+        want = conv(x)
+        if bn:
+            want = bnm(want)
+        want = _act_ref(want, act)
+        r = None
+        if res:
+            r = _q(torch.randn(want.shape, generator=g), dtype).to(DEV)
+            want = want + r
+        if up:
+            want = F.interpolate(want, scale_factor=2, mode="nearest")
+    got = ops.conv_bn_act(x, conv, bnm, act, dtype=dtype, residual=r, upsample2x=up)
+    assert got.shape == want.shape
+    eps = 2e-3 if dtype == torch.float16 else 1.6e-2
+    _close(got, want, rtol=eps, atol=eps, what=f"conv {case} {dtype}")
+
+
+@pytest.mark.parametrize("in_dtype", [torch.float32, torch.uint8])
+def test_stem_conv_reads_nchw_frames(in_dtype):
+    from dyk import ops
+    g = torch.Generator().manual_seed(3)
+    conv = nn.Conv2d(3, 32, 3, 1, 1, bias=False)
+    bn = nn.BatchNorm2d(32)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(32, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(32, generator=g) * 0.1)
+        bn.running_mean.copy_(torch.randn(32, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(32, generator=g) + 0.5)
+    conv, bn = conv.to(DEV).eval(), bn.to(DEV).eval()
+    if in_dtype == torch.uint8:
+        x = torch.randint(0, 256, (2, 3, 40, 56), dtype=torch.uint8, generator=g).to(DEV)
+        xf = x.float() / 255.0
+    else:
+        x = torch.rand((2, 3, 40, 56), generator=g).to(DEV)
+        xf = x
+    with torch.no_grad():
+        want = F.leaky_relu(bn(conv(xf)), 0.1)
+    got = ops.conv_bn_act(x, conv, bn, "leaky", dtype=torch.float16)
+    _close(got, want, rtol=2e-3, atol=2e-3, what="stem")
+
+
+@pytest.mark.parametrize("k,stride,C", [(3, 1, 64), (3, 2, 72), (5, 1, 120), (5, 2, 40), (3, 1, 960)])
+def test_depthwise_conv(k, stride, C):
+    from dyk import ops
+    g = torch.Generator().manual_seed(11)
+    conv = nn.Conv2d(C, C, k, stride, k // 2, groups=C, bias=False)
+    bn = nn.BatchNorm2d(C)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(C, generator=g) * 0.1)
+        bn.running_mean.copy_(torch.randn(C, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(C, generator=g) + 0.5)
+    conv, bn = conv.to(DEV).eval(), bn.to(DEV).eval()
+    x = _q(torch.randn((2, C, 13, 17), generator=g), torch.float16).to(DEV)
+    with torch.no_grad():
+        want = F.relu6(bn(conv(x)))
+    got = ops.conv_bn_act(x, conv, bn, "relu6", dtype=torch.float16)
+    _close(got, want, rtol=2e-3, atol=2e-3, what="dwconv")
+
+
+def test_weighted_fusion_and_plain_shortcut():
+    from dyk import ops
+    g = torch.Generator().manual_seed(5)
+    x = _q(torch.randn((2, 64, 9, 11), generator=g), torch.float16).to(DEV)
+    a = _q(torch.randn((2, 64, 9, 11), generator=g), torch.float16).to(DEV)
+    w = torch.tensor([0.3, -0.7], device=DEV)
+    ww = torch.sigmoid(w) * (2 / 2)
+    _close(ops.weighted_fusion(x, [a], w), x * ww[0] + a * ww[1], 2e-3, 2e-3, "weighted add")
+    _close(ops.weighted_fusion(x, [a], None), x + a, 2e-3, 2e-3, "plain add")
+    # channel mismatch rules (layers.py:78-83)
+    a_small = a[:, :32].contiguous()
+    want = x.clone()
+    want[:, :32] = want[:, :32] + a_small
+    _close(ops.weighted_fusion(x, [a_small], None), want, 2e-3, 2e-3, "slice input")
+    x_small = x[:, :32].contiguous()
+    _close(ops.weighted_fusion(x_small, [a], None), x_small + a[:, :32], 2e-3, 2e-3, "slice feature")
+    wx = x * ww[0]
+    wx[:, :32] = wx[:, :32] + a_small * ww[1]
+    _close(ops.weighted_fusion(x, [a_small], w), wx, 2e-3, 2e-3, "weighted slice input")
+
+
+@pytest.mark.parametrize("k", [3, 5, 9, 13])
+def test_maxpool_same(k):
+    from dyk import ops
+    g = torch.Generator().manual_seed(k)
+    x = _q(torch.randn((2, 64, 16, 20), generator=g), torch.float16).to(DEV)
+    want = F.max_pool2d(x, k, 1, (k - 1) // 2)
+    got = ops.maxpool(x, k, 1)
+    assert torch.equal(got, want), "max-pool must be exact"
+
+
+def test_upsample_and_concat_exact():
+    from dyk import ops
+    g = torch.Generator().manual_seed(1)
+    x = _q(torch.randn((2, 32, 5, 7), generator=g), torch.float16).to(DEV)
+    y = _q(torch.randn((2, 16, 5, 7), generator=g), torch.float16).to(DEV)
+    assert torch.equal(ops.upsample(x, 2), F.interpolate(x, scale_factor=2, mode="nearest"))
+    assert torch.equal(ops.concat_channels([x, y, x]), torch.cat([x, y, x], 1))
+
+
+@pytest.mark.parametrize("C,HW", [(256, (16, 20)), (72, (7, 9)), (1024, (4, 5)), (512, (64, 80))])
+def test_squeeze_excitation(C, HW):
+    from dyk import ops
+    from build_utils.layers import SqueezeExcitation
+    torch.manual_seed(C)
+    se = SqueezeExcitation(C, 4).to(DEV)
+    x = _q(torch.randn((2, C, *HW)), torch.float16).to(DEV)
+    with torch.no_grad():
+        s = F.adaptive_avg_pool2d(x, (1, 1))
+        s = F.hardsigmoid(se.fc2(F.relu(se.fc1(s))))
+        want = s * x
+    got = ops.squeeze_excitation(x, se.fc1, se.fc2)
+    _close(got, want, rtol=2e-3, atol=2e-3, what="SE")
+
+
+@pytest.mark.parametrize("v4", [False, True])
+def test_yolo_decode(v4):
+    from models import YOLOLayer
+    from oracle.darknet_ref import yolo_layer
+    g = torch.Generator().manual_seed(9)
+    anchors = np.array([[16., 42.], [22., 44.], [20., 53.]])
+    p = (torch.randn((2, 18, 8, 10), generator=g) * 2).to(DEV)
+    layer = YOLOLayer(anchors, 1, (64, 80), 8, "yolov4" if v4 else "yolov3").to(DEV).eval()
+    io, pp = layer(p)
+    io_ref, p_ref = yolo_layer(p.cpu(), torch.tensor(anchors, dtype=torch.float32), 8, 1, v4, False)
+    assert torch.equal(pp.cpu(), p_ref)
+    # sigmoid/exp are the device's libm vs the host's: a few ulp
+    _close(io, io_ref, rtol=2e-6, atol=2e-6, what="decode")
+    layer.train()
+    assert torch.equal(layer(p).cpu(), p_ref)
+    assert (layer.nx, layer.ny) == (10, 8)
