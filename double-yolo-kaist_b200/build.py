@@ -48,16 +48,21 @@ def up_to_date() -> bool:
     return LIB.exists() and LIB.stat().st_mtime >= _deps_mtime()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and up_to_date():
-        return LIB
+def build(force: bool = False, verbose: bool = False, profile: bool = False) -> Path:
+    """profile=True builds libdyk_b200_prof.so: same sources with -DDYK_CONV_PROFILE (role-cycle counters in the
+    tcgen05 conv kernel, see dyk_conv_set_profile); select it at run time with DYK_B200_LIB=<path>."""
+    lib = LIB.with_name("libdyk_b200_prof.so") if profile else LIB
+    if not force and lib.exists() and lib.stat().st_mtime >= _deps_mtime():
+        return lib
     nvcc = _nvcc()
-    OBJ.mkdir(exist_ok=True)
+    objdir = OBJ / "prof" if profile else OBJ
+    objdir.mkdir(exist_ok=True, parents=True)
     srcs = _sources()
+    extra = ["-DDYK_CONV_PROFILE"] if profile else []
 
     def compile_one(src: Path) -> Path:
-        obj = OBJ / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        obj = objdir / (src.stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -69,15 +74,15 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    tmp = LIB.with_suffix(".so.tmp")
+    tmp = lib.with_suffix(".so.tmp")
     cmd = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    os.replace(tmp, LIB)
-    return LIB
+    os.replace(tmp, lib)
+    return lib
 
 
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, profile="--profile" in sys.argv)
     print(p)

@@ -52,8 +52,20 @@ struct ConvKArgs {
   const float* bias;               // may be null
   const void* res;                 // may be null
   long long res_pix_stride;
+  unsigned long long* prof;        // optional role-cycle counters (dyk_conv_set_profile), may be null
 };
 
+// Role-cycle counters (diagnostics): where the three pipelines of the kernel wait.
+enum { PROF_PRODUCER_WAIT_EMPTY = 0, PROF_PRODUCER_TOTAL, PROF_MMA_WAIT_FULL, PROF_MMA_WAIT_TEMPTY, PROF_MMA_TOTAL,
+       PROF_EPI_WAIT_TFULL, PROF_EPI_TOTAL, PROF_CTAS, PROF_COUNT };
+
+// Role-cycle counters are compiled in only with -DDYK_CONV_PROFILE (libdyk_b200_prof.so, tools/conv_bench.py):
+// they cost registers in the single-thread producer / MMA roles.
+#ifdef DYK_CONV_PROFILE
+constexpr bool kProf = true;
+#else
+constexpr bool kProf = false;
+#endif
 constexpr int kNumEpiWarps = 8;
 constexpr int kNumEpiThreads = kNumEpiWarps * 32;
 constexpr int kNumThreads = 64 + kNumEpiThreads;   // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue
@@ -61,23 +73,23 @@ constexpr int kBlockM = 128;
 
 template <int BLOCK_N, int BLOCK_K>
 struct ConvSmem {
-  static constexpr int kStoreC = BLOCK_N < 64 ? BLOCK_N : 64;          // channels per TMA store box
+  // Every epilogue warp owns rows [32q, 32q+32) of the tile and every second chunk of kColsW output channels;
+  // it stages and TMA-stores its own 32 x kColsW sub-boxes, so the epilogue needs no CTA-wide barrier.
+  static constexpr int kColsW = BLOCK_N >= 64 ? 32 : BLOCK_N / 2;     // channels per warp chunk (32 or 16)
+  static constexpr int kChunkBytes = 32 * kColsW * 2;                   // one staged sub-box: 2 KB or 1 KB
   static constexpr int kABytes = kBlockM * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kBlockM * kStoreC * 2;          // one store group
-  static constexpr int kNumStaging = 2;
-  static constexpr int kVecBytes = 2 * BLOCK_N * 4;                    // per-tile scale + bias vectors
+  static constexpr int kStagingBytes = kNumEpiWarps * 2 * 2048;        // 2 buffers per warp, 2 KB apart
+  static constexpr int kVecFloats = BLOCK_N;                            // per warp: scale + bias of its BLOCK_N/2 columns
+  static constexpr int kVecBytes = kNumEpiWarps * kVecFloats * 4;
   static constexpr int kBarrierBytes = 1024;
-  static constexpr int kBudget = 227 * 1024 - kBarrierBytes - kVecBytes - kNumStaging * kStagingBytes - 1024 /*align*/;
+  static constexpr int kBudget = 227 * 1024 - kBarrierBytes - kStagingBytes - kVecBytes - 1024 /*align*/;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kTotal =
-      kStages * kStageBytes + kNumStaging * kStagingBytes + kVecBytes + kBarrierBytes + 1024;
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kVecBytes + kBarrierBytes + 1024;
   static_assert(kStages >= 3, "pipeline too shallow");
 };
-
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kNumEpiThreads) : "memory"); }
 
 template <bool kBf16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -114,19 +126,19 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvKArgs& p, int tile) {
   return t;
 }
 
-// Epilogue of one 128 x BLOCK_N accumulator tile, executed by the 8 epilogue warps.
-// Thread (q = warp & 3, lane, half = epilogue warp >> 2) owns tile row q*32+lane and, in every store group of
-// kStoreC channels, the `half`-th half of the group's columns.  kAct is a compile-time activation so that
-// only one code path is resident in the instruction cache.
+// Epilogue of one 128 x BLOCK_N accumulator tile, executed independently by each of the 8 epilogue warps.
+// Warp (q = warp & 3, half = epilogue warp >> 2): thread `lane` owns tile row q*32+lane (TMEM lane) and the
+// column chunks half, half+2, ... of kColsW channels.  Per chunk: tcgen05.ld -> scale/bias/activation
+// (+ residual) in fp32 -> 16-bit -> swizzled warp-private staging -> one TMA store of the 32-row sub-box issued
+// by lane 0.  kAct is a compile-time activation so that only one code path is resident in the instruction cache.
 template <int BLOCK_N, int BLOCK_K, bool kBf16, int kAct>
 __device__ __forceinline__ void epilogue_tile(const ConvTmaps& tm, const ConvKArgs& p, const TileCoord& tc,
-                                              uint32_t t_row, uint8_t* staging, float* svec, int& sbuf,
-                                              uint64_t* tempty, int q, int lane, int half, bool store_thread) {
+                                              uint32_t t_row, uint8_t* wstage, float* wvec, int& sbuf,
+                                              uint64_t* tempty, int q, int lane, int half) {
   using S = ConvSmem<BLOCK_N, BLOCK_K>;
-  constexpr int kStoreC = S::kStoreC;
-  constexpr int kStoreRowBytes = kStoreC * 2;       // 128 or 64
-  constexpr int kCols = kStoreC / 2;                // columns per thread per group: 32 or 16
-  constexpr int kGroups = BLOCK_N / kStoreC;
+  constexpr int kCols = S::kColsW;                  // 32 or 16
+  constexpr int kRowBytes = kCols * 2;              // 64 or 32 (== TMA store swizzle span)
+  constexpr int kChunks = BLOCK_N / kCols;          // column chunks per tile
   const int row = q * 32 + lane;
   const int wi = row % p.tw;
   const int hi = (row / p.tw) % p.th;
@@ -136,19 +148,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvTmaps& tm, const ConvKAr
   const long long pix = (static_cast<long long>(nn) * p.Ho + ho) * p.Wo + wo;
   const int n_base = tc.nblk * BLOCK_N;
   const bool has_res = p.res != nullptr;
+  // origin of this warp's 32-row sub-box inside the tile (warp-uniform)
+  const int r0 = q * 32;
+  const int sw0 = tc.w0 + r0 % p.tw, sh0 = tc.h0 + (r0 / p.tw) % p.th, sn0 = tc.n0 + r0 / (p.tw * p.th);
 
-  // per-tile scale / bias vectors -> shared memory (one element per epilogue thread)
-  {
-    const int t = (half * 4 + q) * 32 + lane;
-    if (t < BLOCK_N) {
-      svec[t] = p.scale ? __ldg(p.scale + n_base + t) : 1.f;
-      svec[BLOCK_N + t] = p.bias ? __ldg(p.bias + n_base + t) : 0.f;
-    }
-  }
-  // residual values of this thread's columns in group 0 are fetched while the MMAs still run
   uint4 rres[kCols / 8];
-  auto load_res = [&](int g) {
-    const int c0 = n_base + g * kStoreC + half * kCols;
+  auto load_res = [&](int c) {
+    const int c0 = n_base + c * kCols;
     const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (pix * p.res_pix_stride + c0) * 2;
 #pragma unroll
     for (int j = 0; j < kCols / 8; ++j) {
@@ -156,83 +162,108 @@ __device__ __forceinline__ void epilogue_tile(const ConvTmaps& tm, const ConvKAr
       if (has_res && pix_ok && c0 + j * 8 < p.Cout_store) rres[j] = __ldg(reinterpret_cast<const uint4*>(rp) + j);
     }
   };
-  load_res(0);
+  // this warp's scale / bias values -> warp-private shared memory: wvec[2*(j*kCols + col) + {0,1}] for its j-th chunk
+  __syncwarp();   // the previous tile's reads of wvec are complete
+  if (lane < kCols) {
+#pragma unroll
+    for (int j = 0; j < kChunks / 2; ++j) {
+      const int col = n_base + (half + 2 * j) * kCols + lane;
+      wvec[j * kCols + lane] = p.scale ? __ldg(p.scale + col) : 1.f;
+      wvec[(kChunks / 2) * kCols + j * kCols + lane] = p.bias ? __ldg(p.bias + col) : 0.f;
+    }
+  }
+  __syncwarp();
+  const float* wscale = wvec;
+  const float* wbias = wvec + (kChunks / 2) * kCols;
 
 #pragma unroll 1
-  for (int g = 0; g < kGroups; ++g) {
-    const int cg0 = n_base + g * kStoreC;   // first output channel of this store group
-    if (cg0 >= p.Cout_store) break;          // uniform: whole group is beyond the tensor
-    const bool last_group = (g == kGroups - 1) || (cg0 + kStoreC >= p.Cout_store);
-    if (!p.out_f32 && store_thread) tma_store_wait_read<1>();  // staging[sbuf] no longer read by an older store
-    epi_bar_sync();                                            // (also publishes svec on g == 0)
-    uint8_t* sbase = staging + sbuf * S::kStagingBytes;
-
+  for (int c = half; c < kChunks; c += 2) {
+    const int cl = c * kCols;                // first column of the chunk within the tile
+    const int cg0 = n_base + cl;             // first output channel of the chunk
+    const bool beyond = cg0 >= p.Cout_store; // warp-uniform: the chunk lies outside the tensor
+    const bool last = (c + 2 >= kChunks) || (cg0 + 2 * kCols >= p.Cout_store);
+    if (beyond) {   // nothing to read: release the accumulator stage and stop
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+      break;
+    }
+    if (has_res) load_res(c);   // in flight while the accumulator chunk is read from TMEM
     uint32_t v[kCols];
-    if constexpr (kCols == 32) tmem_ld_32x32b_x32(t_row + g * kStoreC + half * kCols, v);
-    else tmem_ld_32x32b_x16(t_row + g * kStoreC + half * kCols, v);
+    if constexpr (kCols == 32) tmem_ld_32x32b_x32(t_row + cl, v);
+    else tmem_ld_32x32b_x16(t_row + cl, v);
     tmem_ld_wait();
-    if (last_group) {
-      // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+    if (last) {
+      // all TMEM reads of this warp for this accumulator stage are done -> hand it back to the MMA warp
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty);
     }
-    const int cl = g * kStoreC + half * kCols;   // first column (within the tile) of this thread
-    float o[kCols];
-#pragma unroll
-    for (int j = 0; j < kCols; j += 4) {
-      const float4 sc = *reinterpret_cast<const float4*>(svec + cl + j);
-      const float4 bi = *reinterpret_cast<const float4*>(svec + BLOCK_N + cl + j);
-      o[j + 0] = act_apply<kAct>(fmaf(__uint_as_float(v[j + 0]), sc.x, bi.x));
-      o[j + 1] = act_apply<kAct>(fmaf(__uint_as_float(v[j + 1]), sc.y, bi.y));
-      o[j + 2] = act_apply<kAct>(fmaf(__uint_as_float(v[j + 2]), sc.z, bi.z));
-      o[j + 3] = act_apply<kAct>(fmaf(__uint_as_float(v[j + 3]), sc.w, bi.w));
+    uint8_t* sbase = wstage + sbuf * 2048;
+    if (!p.out_f32) {
+      // staging[sbuf] may still be read by the store issued two chunks ago
+      if (lane == 0) tma_store_wait_read<1>();
+      __syncwarp();
     }
-    if (has_res) {
+    float* yo = reinterpret_cast<float*>(p.y_f32) + pix * p.y_pix_stride + cg0;   // only used when out_f32
+    // 8 channels at a time keeps the live register set small (v[] + 8 outputs + their scale/bias)
 #pragma unroll
-      for (int j = 0; j < kCols / 8; ++j) {
-        const uint32_t rr[4] = {rres[j].x, rres[j].y, rres[j].z, rres[j].w};
+    for (int ch = 0; ch < kCols / 8; ++ch) {
+      float o[8];
+      const int vo = (c >> 1) * kCols + ch * 8;
+      const float4 sc0 = *reinterpret_cast<const float4*>(wscale + vo);
+      const float4 sc1 = *reinterpret_cast<const float4*>(wscale + vo + 4);
+      const float4 bi0 = *reinterpret_cast<const float4*>(wbias + vo);
+      const float4 bi1 = *reinterpret_cast<const float4*>(wbias + vo + 4);
+      o[0] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 0]), sc0.x, bi0.x));
+      o[1] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 1]), sc0.y, bi0.y));
+      o[2] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 2]), sc0.z, bi0.z));
+      o[3] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 3]), sc0.w, bi0.w));
+      o[4] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 4]), sc1.x, bi1.x));
+      o[5] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 5]), sc1.y, bi1.y));
+      o[6] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 6]), sc1.z, bi1.z));
+      o[7] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 7]), sc1.w, bi1.w));
+      if (has_res) {
+        const uint32_t rr[4] = {rres[ch].x, rres[ch].y, rres[ch].z, rres[ch].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 f = unpack2<kBf16>(rr[e]);
-          o[j * 8 + e * 2 + 0] += f.x;
-          o[j * 8 + e * 2 + 1] += f.y;
+          o[e * 2 + 0] += f.x;
+          o[e * 2 + 1] += f.y;
         }
       }
-      if (!last_group) load_res(g + 1);
+      if (p.out_f32) {
+        if (pix_ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (cg0 + ch * 8 + j < p.Cout_store) yo[ch * 8 + j] = o[j];
+        }
+      } else {
+        int phys;
+        if constexpr (kRowBytes == 64) phys = ch ^ ((lane >> 1) & 3);
+        else phys = ch ^ ((lane >> 2) & 1);
+        const uint4 val = make_uint4(pack2<kBf16>(o[0], o[1]), pack2<kBf16>(o[2], o[3]), pack2<kBf16>(o[4], o[5]),
+                                     pack2<kBf16>(o[6], o[7]));
+        *reinterpret_cast<uint4*>(sbase + lane * kRowBytes + phys * 16) = val;
+      }
     }
     if (p.out_f32) {
-      if (pix_ok) {
-        float* yo = reinterpret_cast<float*>(p.y_f32) + pix * p.y_pix_stride + n_base + cl;
-#pragma unroll
-        for (int j = 0; j < kCols; ++j)
-          if (n_base + cl + j < p.Cout_store) yo[j] = o[j];
-      }
+      if (last) break;
       continue;
     }
-    // swizzled staging write: row `row`, this thread's 16-byte chunks of the store row
-#pragma unroll
-    for (int ch = 0; ch < kCols / 8; ++ch) {
-      const int chunk = half * (kCols / 8) + ch;
-      int phys;
-      if constexpr (kStoreRowBytes == 128) phys = chunk ^ (row & 7);
-      else phys = chunk ^ ((row >> 1) & 3);
-      const uint4 val = make_uint4(pack2<kBf16>(o[ch * 8 + 0], o[ch * 8 + 1]), pack2<kBf16>(o[ch * 8 + 2], o[ch * 8 + 3]),
-                                   pack2<kBf16>(o[ch * 8 + 4], o[ch * 8 + 5]), pack2<kBf16>(o[ch * 8 + 6], o[ch * 8 + 7]));
-      *reinterpret_cast<uint4*>(sbase + row * kStoreRowBytes + phys * 16) = val;
-    }
     fence_proxy_async_smem();
-    epi_bar_sync();
-    if (store_thread) {
+    __syncwarp();
+    if (lane == 0) {
       if (p.upsample2x) {
 #pragma unroll
-        for (int pp = 0; pp < 4; ++pp) tma_store_4d(&tm.y[pp], sbase, cg0, tc.w0, tc.h0, tc.n0);
+        for (int pp = 0; pp < 4; ++pp) tma_store_4d(&tm.y[pp], sbase, cg0, sw0, sh0, sn0);
       } else {
-        tma_store_4d(&tm.y[0], sbase, cg0, tc.w0, tc.h0, tc.n0);
+        tma_store_4d(&tm.y[0], sbase, cg0, sw0, sh0, sn0);
       }
       tma_store_commit();
     }
     sbuf ^= 1;
+    if (last) break;
   }
 }
 
@@ -247,11 +278,13 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
   static_assert(BLOCK_K == 64 || BLOCK_K == 32, "BLOCK_K");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by *offset* (not by casting through an integer) so the compiler keeps the shared state space
+  // and emits LDS/STS instead of generic LD/ST for the staging buffer and the scale/bias vectors
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   uint8_t* staging = smem + kStages * S::kStageBytes;
-  float* svec = reinterpret_cast<float*>(staging + S::kNumStaging * S::kStagingBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(svec) + S::kVecBytes);
+  float* vecs = reinterpret_cast<float*>(staging + S::kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(vecs) + S::kVecBytes);
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + kStages;            // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;        // [2]
@@ -288,6 +321,8 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long t_wait = 0;
+      const long long t_begin = clock64();
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const TileCoord tc = tile_coord(p, tile);
         for (int tap = 0; tap < taps; ++tap) {
@@ -302,7 +337,13 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
           }
           const CUtensorMap* amap = &tm.a[map_idx];
           for (int kc = 0; kc < p.k_chunks; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (kProf && p.prof) {
+              const long long t0 = clock64();
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              t_wait += clock64() - t0;
+            } else {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+            }
             uint8_t* sa = stage_base + stage * S::kStageBytes;
             uint8_t* sb = sa + S::kABytes;
             mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
@@ -312,6 +353,11 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
           }
         }
       }
+      if (kProf && p.prof) {
+        atomicAdd(p.prof + PROF_PRODUCER_WAIT_EMPTY, (unsigned long long)t_wait);
+        atomicAdd(p.prof + PROF_PRODUCER_TOTAL, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(p.prof + PROF_CTAS, 1ull);
+      }
     }
   } else if (warp_idx == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
@@ -320,14 +366,24 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
       int stage = 0;
       uint32_t phase = 0;
       int tl = 0;
+      long long t_wfull = 0, t_wtempty = 0;
+      const long long t_begin = clock64();
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
         const int as = tl & 1;
         const uint32_t aphase = (tl >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        {
+          const long long t0 = (kProf && p.prof) ? clock64() : 0;
+          mbar_wait(&tempty_bar[as], aphase ^ 1);
+          if (kProf && p.prof) t_wtempty += clock64() - t0;
+        }
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          {
+            const long long t0 = (kProf && p.prof) ? clock64() : 0;
+            mbar_wait(&full_bar[stage], phase);
+            if (kProf && p.prof) t_wfull += clock64() - t0;
+          }
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(stage_base + stage * S::kStageBytes);
           const uint64_t adesc = umma_desc_kmajor<kSwz>(sa);
@@ -342,15 +398,23 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
         }
         umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
       }
+      if (kProf && p.prof) {
+        atomicAdd(p.prof + PROF_MMA_WAIT_FULL, (unsigned long long)t_wfull);
+        atomicAdd(p.prof + PROF_MMA_WAIT_TEMPTY, (unsigned long long)t_wtempty);
+        atomicAdd(p.prof + PROF_MMA_TOTAL, (unsigned long long)(clock64() - t_begin));
+      }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
     const int ew = warp_idx - 2;
     const int q = warp_idx & 3;            // TMEM lane quarter this warp may access
     const int half = ew >> 2;              // which half of each store group's columns
-    const bool store_thread = (threadIdx.x == 64);
+    uint8_t* wstage = staging + ew * 4096;   // this warp's two 2 KB staging buffers
+    float* wvec = vecs + ew * S::kVecFloats;
     int tl = 0;
     int sbuf = 0;
+    long long t_wtfull = 0;
+    const long long t_begin = clock64();
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
       const int as = tl & 1;
       const uint32_t aphase = (tl >> 1) & 1;
@@ -358,11 +422,14 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
       // The accumulator wait sits inside the activation-specialised body's caller so that residual / vector
       // prefetches of the *next* tile are not hoisted above it by accident.
-      mbar_wait(&tfull_bar[as], aphase);
+      {
+        const long long t0 = (kProf && p.prof) ? clock64() : 0;
+        mbar_wait(&tfull_bar[as], aphase);
+        if (kProf && p.prof) t_wtfull += clock64() - t0;
+      }
       tc_fence_after_sync();
 #define DYK_EPI(ACT)                                                                                         \
-  epilogue_tile<BLOCK_N, BLOCK_K, kBf16, ACT>(tm, p, tc, t_row, staging, svec, sbuf, &tempty_bar[as], q, lane, \
-                                              half, store_thread)
+  epilogue_tile<BLOCK_N, BLOCK_K, kBf16, ACT>(tm, p, tc, t_row, wstage, wvec, sbuf, &tempty_bar[as], q, lane, half)
       switch (p.act) {
         case DYK_ACT_LEAKY: DYK_EPI(DYK_ACT_LEAKY); break;
         case DYK_ACT_MISH: DYK_EPI(DYK_ACT_MISH); break;
@@ -374,7 +441,11 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
       }
 #undef DYK_EPI
     }
-    if (store_thread) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
+    if (kProf && p.prof && ew == 0 && lane == 0) {
+      atomicAdd(p.prof + PROF_EPI_WAIT_TFULL, (unsigned long long)t_wtfull);
+      atomicAdd(p.prof + PROF_EPI_TOTAL, (unsigned long long)(clock64() - t_begin));
+    }
   }
 
   tc_fence_before_sync();
@@ -475,6 +546,15 @@ static int pick_block_n(int cout_store, long long m_tiles, int num_kb, int block
 
 using namespace dyk;
 
+static unsigned long long* g_conv_prof = nullptr;
+
+extern "C" __attribute__((visibility("default"))) int dyk_conv_set_profile(uint64_t* dev_counters) {
+  if (dev_counters != nullptr && !kProf)
+    return fail(DYK_EINVAL, "dyk_conv_set_profile: this library was built without -DDYK_CONV_PROFILE");
+  g_conv_prof = reinterpret_cast<unsigned long long*>(dev_counters);
+  return DYK_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_conv_params* p, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DYK_REQUIRE(p != nullptr, "dyk_conv2d_fwd: null params");
@@ -552,8 +632,12 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
     if ((rc = encode_map(&tm.b, p->w, 3, dims, str, box, swz, "B"))) return rc;
   }
   if (!p->out_f32) {
-    const int storeC = BN < 64 ? BN : 64;
-    const cuuint32_t ybox[4] = {(cuuint32_t)storeC, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+    // every epilogue warp stores 32-row x storeC-channel sub-boxes of the tile (see epilogue_tile)
+    const int storeC = BN >= 64 ? 32 : BN / 2;
+    const int sw = tw < 32 ? tw : 32;
+    const int sh = th < 32 / sw ? th : 32 / sw;
+    const int sn = 32 / (sw * sh);
+    const cuuint32_t ybox[4] = {(cuuint32_t)storeC, (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)sn};
     const long long ys = p->y_pix_stride * 2;
     if (p->upsample2x) {
       const int W2 = 2 * Wo, H2 = 2 * Ho;
@@ -588,6 +672,7 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   ka.y_pix_stride = p->y_pix_stride;
   ka.scale = p->scale; ka.bias = p->bias;
   ka.res = p->res; ka.res_pix_stride = p->res_pix_stride;
+  ka.prof = g_conv_prof;
 
   const bool bf = p->dtype == DYK_BF16;
   if (BK == 64) return bf ? dispatch_n<64, true>(BN, tm, ka, stream) : dispatch_n<64, false>(BN, tm, ka, stream);

@@ -116,7 +116,8 @@ __global__ void upsample_kernel(const uint8_t* __restrict__ x, long long xs, uin
 
 // ------------------------------------------------------------------ SqueezeExcitation
 // reference: build_utils/layers.py:184-190
-// (1) pooled[n][c] += sum over a slab of pixels  (fp32 atomics into a zeroed scratch)
+// (1) pooled[n][slab][c] = sum over a slab of pixels; the slabs are summed in a fixed order by (2), so the result is
+//     deterministic (no atomics)
 template <bool kBf16>
 __global__ void se_pool_kernel(const uint8_t* __restrict__ x, long long xs, int HW, int C, int slabs,
                                float* __restrict__ pooled) {
@@ -148,11 +149,11 @@ __global__ void se_pool_kernel(const uint8_t* __restrict__ x, long long xs, int 
     float s = 0.f;
     for (int l = 0; l < 32; ++l) s += red[l][cv][q];
     const int c = (blockIdx.x * 8 + cv) * 8 + q;
-    if (c < C) atomicAdd(&pooled[(long long)n * C + c], s);
+    if (c < C) pooled[((long long)n * slabs + blockIdx.y) * C + c] = s;
   }
 }
 // (2) gate[n][:] = hardsigmoid(W2 relu(W1 mean + b1) + b2); one block per image
-__global__ void se_mlp_kernel(const float* __restrict__ pooled, float inv_hw, int C, int Csq,
+__global__ void se_mlp_kernel(const float* __restrict__ pooled, int slabs, float inv_hw, int C, int Csq,
                               const float* __restrict__ w1, const float* __restrict__ b1,
                               const float* __restrict__ w2, const float* __restrict__ b2,
                               float* __restrict__ gate) {
@@ -160,7 +161,11 @@ __global__ void se_mlp_kernel(const float* __restrict__ pooled, float inv_hw, in
   float* mean = sm;        // [C]
   float* hid = sm + C;     // [Csq]
   const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = pooled[(long long)n * C + c] * inv_hw;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int sl = 0; sl < slabs; ++sl) s += pooled[((long long)n * slabs + sl) * C + c];
+    mean[c] = s * inv_hw;
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int j = warp; j < Csq; j += nwarps) {
@@ -329,14 +334,13 @@ extern "C" __attribute__((visibility("default"))) int dyk_se_gate(const void* x,
   DYK_REQUIRE(x && w1 && b1 && w2 && b2 && pooled && gate, "dyk_se_gate: null pointer");
   DYK_REQUIRE(C > 0 && C % 8 == 0 && xs % 8 == 0 && Csq > 0 && N > 0 && HW > 0, "dyk_se_gate: bad shape");
   DYK_REQUIRE((size_t)(C + Csq) * 4 <= 48 * 1024, "dyk_se_gate: C + Csq too large");
-  DYK_CUDA_OK(cudaMemsetAsync(pooled, 0, sizeof(float) * (size_t)N * C, stream));
   int slabs = HW / 256;
   if (slabs < 1) slabs = 1;
   if (slabs > 32) slabs = 32;
   const dim3 grid((C + 63) / 64, slabs, N);
   DYK_DISPATCH_DTYPE(dtype, (se_pool_kernel<kBf16><<<grid, 256, 0, stream>>>((const uint8_t*)x, xs, HW, C, slabs, pooled)));
   DYK_LAUNCH_OK("se_pool_kernel");
-  se_mlp_kernel<<<N, 256, (C + Csq) * sizeof(float), stream>>>(pooled, 1.f / (float)HW, C, Csq, w1, b1, w2, b2, gate);
+  se_mlp_kernel<<<N, 256, (C + Csq) * sizeof(float), stream>>>(pooled, slabs, 1.f / (float)HW, C, Csq, w1, b1, w2, b2, gate);
   DYK_LAUNCH_OK("se_mlp_kernel");
   return DYK_OK;
 }

@@ -10,7 +10,8 @@ import ctypes as C
 from pathlib import Path
 
 PKG_ROOT = Path(__file__).resolve().parent.parent
-LIB_PATH = PKG_ROOT / "libdyk_b200.so"
+import os as _os
+LIB_PATH = Path(_os.environ.get("DYK_B200_LIB") or PKG_ROOT / "libdyk_b200.so")   # override: the -DDYK_CONV_PROFILE build
 
 DYK_F16, DYK_BF16 = 0, 1
 ACT_IDS = {
@@ -40,6 +41,7 @@ SIGNATURES = {
     "dyk_last_error": (C.c_char_p, []),
     "dyk_check_device": (_i32, []),
     "dyk_conv2d_fwd": (_i32, [C.POINTER(ConvParams), _vp]),
+    "dyk_conv_set_profile": (_i32, [_vp]),
     "dyk_conv2d_stem_nchw_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64] + [_i32] * 11 + [_vp]),
     "dyk_dwconv2d_fwd": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
                                 _i32, _i32, _i32, _vp]),

@@ -315,7 +315,7 @@ def squeeze_excitation(x: torch.Tensor, fc1, fc2, dtype=None) -> torch.Tensor:
     xv = to_nhwc(x, dtype)
     y = new_view(xv.N, xv.H, xv.W, xv.C, xv.buf.dtype, x.device)
     w1, b1, w2, b2 = se_weights(fc1, fc2)
-    pooled = torch.empty((xv.N, xv.C), dtype=torch.float32, device=x.device)
+    pooled = torch.empty((xv.N, 32, xv.C), dtype=torch.float32, device=x.device)   # DYK_SE_MAX_SLABS partials
     gate = torch.empty((xv.N, xv.C), dtype=torch.float32, device=x.device)
     nhwc_se(xv, y, w1, b1, w2, b2, pooled, gate)
     return to_nchw(y)

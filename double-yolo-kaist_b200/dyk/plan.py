@@ -362,6 +362,7 @@ class Plan:
     def __init__(self, model, bank, B, H, W, dtype, dual, device):
         self.B, self.dtype, self.device, self.dual = B, dtype, device, dual
         raw, vals, self.img0, self.img1 = build_ops(model, H, W, dual)
+        self.layer_vals = vals   # Value visible at every cfg layer index (diagnostics: tools/layer_parity.py)
         self.ops = fuse(raw)
         mark_heads(self.ops)
         place_concats(self.ops)
@@ -455,7 +456,7 @@ class Plan:
                 w1, b1, w2, b2 = ops.se_weights(op.module.fc1, op.module.fc2)
                 hold = {"w1": w1, "b1": b1, "w2": w2, "b2": b2, "mod": op.module}
                 self._se_holds = getattr(self, "_se_holds", []) + [hold]
-                pooled = torch.empty((self.B, op.src.C), dtype=torch.float32, device=dev)
+                pooled = torch.empty((self.B, 32, op.src.C), dtype=torch.float32, device=dev)   # DYK_SE_MAX_SLABS partials
                 gate = torch.empty((self.B, op.src.C), dtype=torch.float32, device=dev)
                 self.steps.append(_Call(ops.nhwc_se, op.src.view, op.out.view, w1, b1, w2, b2, pooled, gate))
             elif isinstance(op, YoloOp):

@@ -80,6 +80,15 @@ typedef struct dyk_conv_params {
 } dyk_conv_params;
 int dyk_conv2d_fwd(const dyk_conv_params* p, void* stream);
 
+/* Diagnostics (no reference counterpart): when dev_counters != NULL, every later dyk_conv2d_fwd launch adds
+ * its role-cycle counters into dev_counters[0..7] (device memory, 8 x uint64, caller zeroes them):
+ *   0 producer cycles waiting for a free smem stage   1 producer total
+ *   2 MMA-issuer cycles waiting for TMA data          3 MMA-issuer cycles waiting for a free accumulator
+ *   4 MMA-issuer total                                5 epilogue (warp 0) cycles waiting for an accumulator
+ *   6 epilogue total                                  7 number of CTAs
+ * Pass NULL to switch the counters off (the default). */
+int dyk_conv_set_profile(uint64_t* dev_counters);
+
 /* ---- first-layer convolution reading the caller's NCHW frames ----------------------------------
  * Replaces the stem nn.Conv2d+BN+act (models.py:35-36: in_channels=3, also at second_index) fused
  * with the NCHW->NHWC / fp32->dtype conversion.  Direct (CUDA-core) kernel, Cin <= 4.
@@ -124,10 +133,13 @@ int dyk_upsample_nearest(const void* x, int64_t x_pix_stride, void* y, int64_t y
                          int32_t H, int32_t W, int32_t C, int32_t s, int32_t dtype, void* stream);
 
 /* ---- SqueezeExcitation (build_utils/layers.py:175-190) ------------------------------------------
- * dyk_se_gate:  gate[n,c] = hardsigmoid(W2 relu(W1 mean_hw(x[n]) + b1) + b2)  (fp32 [N][C])
+ * dyk_se_gate:  gate[n,c] = hardsigmoid(W2 relu(W1 mean_hw(x[n]) + b1) + b2)  (fp32 [N][C]);
+ *               pooled_scratch: N * DYK_SE_MAX_SLABS * C floats (per-slab partial sums, reduced in a fixed order
+ *               so the result is deterministic).
  * dyk_scale_channels: y = x * gate (broadcast over H,W).
  * w1 fp32 [Csq][C], w2 fp32 [C][Csq].
  */
+#define DYK_SE_MAX_SLABS 32
 int dyk_se_gate(const void* x, int64_t x_pix_stride, int32_t N, int32_t HW, int32_t C, const float* w1,
                 const float* b1, const float* w2, const float* b2, int32_t Csq, float* pooled_scratch,
                 float* gate, int32_t dtype, void* stream);

@@ -100,6 +100,7 @@ class DarknetRef:
         self.cfg = cfg_path
         blocks = parse_cfg(cfg_path)
         self.net = blocks[0]
+        self._round = None
         self.defs = blocks[1:]
         self.shapes = OrderedDict()   # state_dict name -> shape
         self.meta = []                # per layer: dict with derived constants
@@ -196,7 +197,10 @@ class DarknetRef:
         return F.batch_norm(x, rm, rv, w, b, False, 0.0, 1e-5)
 
     def _conv_bn_act(self, x, st, pconv, pbn, stride, pad, groups, act, training, mom):
-        x = F.conv2d(x, st[pconv + ".weight"], st.get(pconv + ".bias"), stride, pad, 1, groups)
+        w = st[pconv + ".weight"]
+        if self._round is not None and groups == 1 and w.shape[1] > 4:
+            w = w.to(self._round).float()   # dense tensor-core convs hold their weights in the 16-bit dtype
+        x = F.conv2d(x, w, st.get(pconv + ".bias"), stride, pad, 1, groups)
         if pbn is not None:
             x = self._bn(x, st, pbn, training, mom)
         return activation(x, act)
@@ -207,9 +211,24 @@ class DarknetRef:
 
     # -- models.py:279-315 -------------------------------------------------------------------------
     def forward(self, st: dict, x: torch.Tensor, y: torch.Tensor = None, training: bool = False,
-                bn_momentum=0.1, keep_layers: bool = False):
+                bn_momentum=0.1, keep_layers: bool = False, round_dtype=None, unrounded=(), teacher=None):
         """Returns what YOLO.forward returns: train -> [p...]; eval -> (cat(io, 1), (p...)).
-        With keep_layers=True also returns the list of every layer's output (for per-layer checks)."""
+        With keep_layers=True also returns the list of every layer's output (for per-layer checks).
+
+        round_dtype (torch.float16 / torch.bfloat16) turns this into the *storage-rounding model* of the native
+        path: arithmetic stays fp32, but dense-conv weights and every layer output are rounded to that dtype,
+        except the layers listed in `unrounded` (outputs the native plan never materialises because they are
+        fused into their consumer, and the fp32 head logits).
+
+        teacher ({layer index: NCHW fp32 tensor}) turns the run into a *teacher-forced, layer-by-layer* check: after
+        layer i has been computed (and recorded in the keep_layers list) its output is replaced by teacher[i] — the
+        tensor the native plan actually produced — so every layer is evaluated on exactly the inputs the native
+        kernel saw.  Rounding is a non-linear amplifier (a 1e-7 accumulation-order difference flips a 16-bit
+        rounding somewhere, and within ~5 layers two correct implementations sit a full rounding-noise floor
+        apart), so end-to-end comparisons can only bound drift; the teacher-forced comparison is tight (<= 1-2 ulp
+        of the storage type per layer) for every layer of the real network at its real shape."""
+        self._round = round_dtype
+        rnd = (lambda t: t.to(round_dtype).float()) if round_dtype is not None else (lambda t: t)
         di = "second_index" in self.net and y is not None
         yolo_out, out, every = [], [], []
         routed = set()
@@ -227,15 +246,15 @@ class DarknetRef:
                                       m["pad"], m["groups"], d["activation"], training, bn_momentum)
             elif t == "depthwiseconvolutional":
                 c = x.shape[1]
-                x = self._conv_bn_act(x, st, pre + ".conv.0", pre + ".conv.1", m["stride"], 1, c, "relu6", training,
-                                      bn_momentum)
+                x = rnd(self._conv_bn_act(x, st, pre + ".conv.0", pre + ".conv.1", m["stride"], 1, c, "relu6", training,
+                                          bn_momentum))
                 x = self._conv_bn_act(x, st, pre + ".conv.3", pre + ".conv.4", 1, 0, 1, "relu6", training, bn_momentum)
             elif t == "inception":
                 b1 = self._cba(x, st, pre + ".branch1.0", 1, training, bn_momentum)
-                b2 = self._cba(self._cba(x, st, pre + ".branch2.0", 1, training, bn_momentum), st, pre + ".branch2.1", 3,
+                b2 = self._cba(rnd(self._cba(x, st, pre + ".branch2.0", 1, training, bn_momentum)), st, pre + ".branch2.1", 3,
                                training, bn_momentum)
-                b3 = self._cba(x, st, pre + ".branch3.0", 1, training, bn_momentum)
-                b3 = self._cba(b3, st, pre + ".branch3.1", 3, training, bn_momentum)
+                b3 = rnd(self._cba(x, st, pre + ".branch3.0", 1, training, bn_momentum))
+                b3 = rnd(self._cba(b3, st, pre + ".branch3.1", 3, training, bn_momentum))
                 b3 = self._cba(b3, st, pre + ".branch3.2", 3, training, bn_momentum)
                 b4 = self._cba(F.max_pool2d(x, 3, 1, 1), st, pre + ".branch4.1", 1, training, bn_momentum)
                 x = torch.cat([b1, b2, b3, b4], 1)
@@ -258,9 +277,13 @@ class DarknetRef:
                 x = weighted_fusion(x, [out[l] for l in m["layers"]], st[pre + ".w"] if m["weight"] else None)
             elif t == "yolo":
                 yolo_out.append(yolo_layer(x, m["anchors"], m["stride"], m["nc"], m["v4"], training))
-            out.append(x if i in routed else None)
+            if round_dtype is not None and i not in unrounded and t != "yolo":
+                x = rnd(x)
             if keep_layers:
                 every.append(x)
+            if teacher is not None and i in teacher and t != "yolo":
+                x = teacher[i]
+            out.append(x if i in routed else None)
         if training:
             res = yolo_out
         else:

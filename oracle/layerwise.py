@@ -1,0 +1,70 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Teacher-forced, layer-by-layer comparison of a native plan with the oracle.
+
+Used by tests/test_gpu_model.py, __graft_entry__.smoke() and tools/layer_parity.py.  The native model must have been
+built with DYK_NO_REUSE=1 (no buffer recycling) and run once, so that every materialised layer output is still in
+its buffer.  The oracle (oracle/darknet_ref.py, run as the storage-rounding model of the plan) then recomputes every
+layer from the *native* inputs of that layer; see DarknetRef.forward(teacher=...) for why only this comparison can
+be tight.
+"""
+from __future__ import annotations
+
+import torch
+
+ULP = {torch.float16: 2.0 ** -10, torch.bfloat16: 2.0 ** -7}
+
+
+def native_layers(model):
+    """({layer index: NCHW fp32 CPU tensor} of every materialised layer output, {layers never stored in 16 bits})."""
+    from dyk import ops
+    from dyk.ops import View
+    plan = model._plans.last_plan
+    got, unrounded = {}, set()
+    for i, v in enumerate(plan.layer_vals):
+        if v is None or v.ext:
+            continue
+        if v.view is None or v.f32:
+            unrounded.add(i)
+        if v.view is None:
+            continue
+        vw = v.view
+        if v.f32:
+            got[i] = vw.buf[..., vw.c_off:vw.c_off + vw.C].permute(0, 3, 1, 2).float().cpu().contiguous()
+        else:
+            got[i] = ops.to_nchw(View(vw.buf, vw.c_off, vw.C)).cpu()
+    return got, unrounded
+
+
+def compare(model, ref, st, v, l, dtype):
+    """Returns a list of per-layer records {layer, type, max_diff, over_2ulp, n, frac_diff, rel_rms}.
+    v, l: the fp32 NCHW frames (already /255) the native run was given (l None for single-stream cfgs)."""
+    got, unrounded = native_layers(model)
+    with torch.no_grad():
+        _, every = ref.forward(st, v, l, keep_layers=True, round_dtype=dtype, unrounded=unrounded, teacher=got)
+    ulp = ULP[dtype]
+    rows = []
+    for i, nat_out in sorted(got.items()):
+        want = every[i]
+        if want.shape != nat_out.shape:
+            rows.append(dict(layer=i, type=ref.defs[i]["type"], shape_mismatch=(tuple(want.shape), tuple(nat_out.shape))))
+            continue
+        rms = float(want.pow(2).mean().sqrt())
+        floor = torch.full_like(want, 0.25 * rms)
+        if ref.defs[i]["type"] == "convolutional" and i in unrounded:     # fp32 head logits: accumulation order only
+            tol = 2e-3 * torch.maximum(want.abs(), torch.full_like(want, rms))
+        else:
+            tol = 2.0 * ulp * torch.maximum(want.abs(), floor) + 1e-6
+        diff = (nat_out - want).abs()
+        rows.append(dict(layer=i, type=ref.defs[i]["type"], max_diff=float(diff.max()), over_2ulp=int((diff > tol).sum()),
+                         n=diff.numel(), frac_diff=float((diff > 0.25 * ulp * torch.maximum(want.abs(), floor)).float().mean()),
+                         rel_rms=float(diff.pow(2).mean().sqrt()) / (rms + 1e-12)))
+    return rows
+
+
+def assert_layerwise(rows, n_layers, what=""):
+    checked = 0
+    for r in rows:
+        assert "shape_mismatch" not in r, (what, r)
+        assert r["over_2ulp"] == 0, (what, "layer differs from the oracle by more than 2 ulp of the storage type", r)
+        assert r["frac_diff"] < 0.05, (what, "too many elements differ", r)
+        checked += 1
+    assert checked > n_layers // 3, (what, "too few layers were compared", checked)

@@ -1,12 +1,18 @@
 #!/usr/bin/env python
 """Micro-benchmark of dyk_conv2d_fwd on the BASELINE layer shapes (CUDA events, L2 flushed between runs).
+With DYK_B200_LIB=double-yolo-kaist_b200/libdyk_b200_prof.so (python double-yolo-kaist_b200/build.py --profile)
+it also prints where the producer / MMA / epilogue roles of the kernel wait.
     python tools/conv_bench.py [--only i,j] [--iters n] [--dtype fp16|bf16]"""
 import argparse, sys
 from pathlib import Path
 REPO = Path(__file__).resolve().parent.parent
 sys.path[:0] = [str(REPO), str(REPO / "double-yolo-kaist_b200")]
 import torch
+import ctypes as C
+import os
+PROFILE = os.environ.get("DYK_B200_LIB", "").endswith("_prof.so")   # role-cycle counters need the profile build
 from dyk import ops
+from dyk import _native as nat
 from dyk.ops import View
 
 SHAPES = [  # (N, Cin, H, W, Cout, k, stride, res, act)
@@ -59,5 +65,16 @@ for i in sel:
     us = sorted(times)[len(times) // 2]
     fl = 2.0 * N * Ho * Wo * Cout * Cin * k * k
     by = 2.0 * (N * H * W * Cin + N * Ho * Wo * Cout * (2 if res else 1) + Cout * Cin * k * k)
+    role = ""
+    if PROFILE:
+        prof = torch.zeros(8, dtype=torch.int64, device="cuda")
+        nat.call("dyk_conv_set_profile", C.c_void_p(prof.data_ptr()))
+        ops.nhwc_conv(x, w, scale, bias, y, k=k, stride=s, pad=pad, act=act, res=r)
+        torch.cuda.synchronize()
+        nat.call("dyk_conv_set_profile", None)
+        pr = prof.tolist()
+        n = max(pr[7], 1)
+        role = (f"prod wait-empty {pr[0] / max(pr[1], 1):4.0%} | mma wait-data {pr[2] / max(pr[4], 1):4.0%} wait-acc "
+                f"{pr[3] / max(pr[4], 1):4.0%} | epi wait-acc {pr[5] / max(pr[6], 1):4.0%} | cyc/CTA {pr[4] / n:8.0f}")
     print(f"[{i:2d}] {Cin:5d}->{Cout:5d} k{k} s{s} {H}x{W} res={int(res)} {act:6s}: {us:8.1f} us  {fl / us / 1e6:7.1f} TF/s  {by / us / 1e3:7.0f} GB/s"
-          f"   (roofline {max(fl / 1.59e15, by / 6.65e12) * 1e6:6.1f} us)", flush=True)
+          f"   (roofline {max(fl / 1.59e15, by / 6.65e12) * 1e6:6.1f} us)  {role}", flush=True)
