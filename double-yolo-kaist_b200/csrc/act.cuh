@@ -5,9 +5,9 @@
 namespace dyk {
 
 __device__ __forceinline__ float mish_f(float x) {
-  // x * tanh(softplus(x)) = x * n / (n + 2),  n = e^x (e^x + 2); for large x the ratio is 1 in fp32.
-  if (x > 20.f) return x;
-  const float e = __expf(x);
+  // x * tanh(softplus(x)) = x * n / (n + 2),  n = e^x (e^x + 2); for x >= 20 the ratio rounds to 1 in fp32, so
+  // clamping the exponent (no overflow to inf / NaN) replaces a divergent branch.
+  const float e = __expf(fminf(x, 20.f));
   const float n = e * (e + 2.f);
   return x * __fdividef(n, n + 2.f);
 }

@@ -23,8 +23,11 @@
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2..9 = epilogue (TMEM lane quarter = warp_idx & 3; two warps per quarter split the columns).
 #include "common.h"
+#include <cstdlib>
+#include <cstring>
 #include "ptx.cuh"
 #include "act.cuh"
+#include "conv_common.cuh"
 
 namespace dyk {
 
@@ -35,7 +38,9 @@ struct ConvTmaps {
 };
 
 struct ConvKArgs {
-  int tw, th, tn;                  // A/Y box spatial extents, tw*th*tn == 128
+  int tw, th, tn;                  // A/Y box spatial extents, tw*th*tn == 128 (all powers of two)
+  int tw_log2, th_log2;
+  FastDiv fd_nblocks, fd_tiles_w, fd_tiles_h;
   int tiles_w, tiles_h, tiles_b;   // tile grid over (Wo, Ho, N)
   int n_blocks;                    // ceil(Cout_store / BLOCK_N)
   int num_tiles;
@@ -91,35 +96,17 @@ struct ConvSmem {
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 
-template <bool kBf16>
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  if constexpr (kBf16) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  } else {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
-}
-template <bool kBf16>
-__device__ __forceinline__ float2 unpack2(uint32_t v) {
-  if constexpr (kBf16) {
-    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
-  } else {
-    return __half22float2(*reinterpret_cast<__half2*>(&v));
-  }
-}
-
 struct TileCoord {
   int nblk, w0, h0, n0;
 };
 __device__ __forceinline__ TileCoord tile_coord(const ConvKArgs& p, int tile) {
   TileCoord t;
-  t.nblk = tile % p.n_blocks;
-  const int mt = tile / p.n_blocks;
-  const int tww = mt % p.tiles_w;
-  const int thh = (mt / p.tiles_w) % p.tiles_h;
-  const int tb = mt / (p.tiles_w * p.tiles_h);
+  const unsigned mt = fd_div((unsigned)tile, p.fd_nblocks);
+  t.nblk = tile - (int)(mt * p.fd_nblocks.div);
+  const unsigned rowt = fd_div(mt, p.fd_tiles_w);            // tile row index over (tiles_h * tiles_b)
+  const unsigned tww = mt - rowt * p.fd_tiles_w.div;
+  const unsigned tb = fd_div(rowt, p.fd_tiles_h);
+  const unsigned thh = rowt - tb * p.fd_tiles_h.div;
   t.w0 = tww * p.tw;
   t.h0 = thh * p.th;
   t.n0 = tb * p.tn;
@@ -140,9 +127,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvTmaps& tm, const ConvKAr
   constexpr int kRowBytes = kCols * 2;              // 64 or 32 (== TMA store swizzle span)
   constexpr int kChunks = BLOCK_N / kCols;          // column chunks per tile
   const int row = q * 32 + lane;
-  const int wi = row % p.tw;
-  const int hi = (row / p.tw) % p.th;
-  const int ni = row / (p.tw * p.th);
+  const int wi = row & (p.tw - 1);
+  const int hi = (row >> p.tw_log2) & (p.th - 1);
+  const int ni = row >> (p.tw_log2 + p.th_log2);
   const int wo = tc.w0 + wi, ho = tc.h0 + hi, nn = tc.n0 + ni;
   const bool pix_ok = (wo < p.Wo) && (ho < p.Ho) && (nn < p.N);
   const long long pix = (static_cast<long long>(nn) * p.Ho + ho) * p.Wo + wo;
@@ -150,7 +137,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvTmaps& tm, const ConvKAr
   const bool has_res = p.res != nullptr;
   // origin of this warp's 32-row sub-box inside the tile (warp-uniform)
   const int r0 = q * 32;
-  const int sw0 = tc.w0 + r0 % p.tw, sh0 = tc.h0 + (r0 / p.tw) % p.th, sn0 = tc.n0 + r0 / (p.tw * p.th);
+  const int sw0 = tc.w0 + (r0 & (p.tw - 1)), sh0 = tc.h0 + ((r0 >> p.tw_log2) & (p.th - 1)),
+            sn0 = tc.n0 + (r0 >> (p.tw_log2 + p.th_log2));
 
   uint4 rres[kCols / 8];
   auto load_res = [&](int c) {
@@ -455,9 +443,9 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
 
 // ---------------------------------------------------------------------------------------------- host
 
-static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
-                      const cuuint64_t* strides_bytes /* rank-1 */, const cuuint32_t* box, int swizzle_bytes,
-                      const char* what) {
+int encode_map_generic(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+                       const cuuint64_t* strides_bytes /* rank-1 */, const cuuint32_t* box, int swizzle_bytes,
+                       const char* what) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail(DYK_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -478,6 +466,13 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint
   }
   return DYK_OK;
 }
+
+static inline int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+                             const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle_bytes, const char* what) {
+  return encode_map_generic(map, base, rank, dims, strides_bytes, box, swizzle_bytes, what);
+}
+
+int conv3x3_halo_try(const dyk_conv_params* p, cudaStream_t stream);   // conv_halo.cu
 
 // Spatial box (tw, th, tn) with tw*th*tn == 128 that wastes the fewest output pixels.
 static void pick_tile(int Wo, int Ho, int N, int* tw, int* th, int* tn) {
@@ -544,9 +539,10 @@ static int pick_block_n(int cout_store, long long m_tiles, int num_kb, int block
 
 }  // namespace dyk
 
+namespace dyk {
+unsigned long long* g_conv_prof = nullptr;   // shared with conv_halo.cu
+}
 using namespace dyk;
-
-static unsigned long long* g_conv_prof = nullptr;
 
 extern "C" __attribute__((visibility("default"))) int dyk_conv_set_profile(uint64_t* dev_counters) {
   if (dev_counters != nullptr && !kProf)
@@ -581,6 +577,13 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   const int Ho = (p->H + 2 * p->pad - p->kh) / p->stride + 1;
   const int Wo = (p->W + 2 * p->pad - p->kw) / p->stride + 1;
   DYK_REQUIRE(Ho > 0 && Wo > 0, "dyk_conv2d_fwd: empty output");
+
+  // 3x3 stride-1 layers: halo kernel (every input pixel loaded once per tile instead of once per tap)
+  static const bool no_halo = getenv("DYK_NO_HALO") != nullptr && getenv("DYK_NO_HALO")[0] == '1';
+  if (!no_halo) {
+    const int hr = conv3x3_halo_try(p, stream);
+    if (hr <= 0) return hr;   // launched (0) or failed (< 0); 1 = not eligible
+  }
 
   const int BK = (p->Cin <= 32) ? 32 : 64;
   const int swz = BK * 2;
@@ -658,6 +661,11 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   ka.tw = tw; ka.th = th; ka.tn = tn;
   ka.tiles_w = ceil_div(gW, tw); ka.tiles_h = ceil_div(gH, th); ka.tiles_b = ceil_div(gN, tn);
   ka.n_blocks = ceil_div(p->Cout_store, BN);
+  for (ka.tw_log2 = 0; (1 << ka.tw_log2) < tw; ++ka.tw_log2) {}
+  for (ka.th_log2 = 0; (1 << ka.th_log2) < th; ++ka.th_log2) {}
+  ka.fd_nblocks = make_fastdiv((unsigned)ka.n_blocks);
+  ka.fd_tiles_w = make_fastdiv((unsigned)ka.tiles_w);
+  ka.fd_tiles_h = make_fastdiv((unsigned)ka.tiles_h);
   const long long nt = m_tiles * ka.n_blocks;
   DYK_REQUIRE(nt < (1ll << 31), "dyk_conv2d_fwd: too many tiles");
   ka.num_tiles = (int)nt;
