@@ -392,7 +392,9 @@ static int launch_halo(const HaloTmaps& tm, const HaloKArgs& ka, cudaStream_t st
 
 // Returns DYK_OK after launching, or 1 when the layer is not eligible (the caller then uses conv_tc_kernel).
 int conv3x3_halo_try(const dyk_conv_params* p, cudaStream_t stream) {
-  if (!(p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && !p->upsample2x && !p->out_f32)) return 1;
+  if (!(p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && !p->upsample2x && !p->out_f32 && !p->y_plane &&
+        p->out_h == 0 && p->out_w == 0))
+    return 1;
   if (p->Cout_store < 64 || p->Cin < 16) return 1;
   // Measured on B200 (profiles/): the operand path is bound by shared-memory bandwidth (~100 B/clk/SM effective for
   // MMA operand reads + TMA writes), so removing the 9x re-load of A pays off when the A share is large or the layer

@@ -574,9 +574,12 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
                 "dyk_conv2d_fwd: residual must be 16-byte aligned with stride %% 8 == 0");
     DYK_REQUIRE(!p->upsample2x, "dyk_conv2d_fwd: residual + upsample2x not supported");
   }
-  const int Ho = (p->H + 2 * p->pad - p->kh) / p->stride + 1;
-  const int Wo = (p->W + 2 * p->pad - p->kw) / p->stride + 1;
+  const int Ho = p->out_h > 0 ? p->out_h : (p->H + 2 * p->pad - p->kh) / p->stride + 1;
+  const int Wo = p->out_w > 0 ? p->out_w : (p->W + 2 * p->pad - p->kw) / p->stride + 1;
   DYK_REQUIRE(Ho > 0 && Wo > 0, "dyk_conv2d_fwd: empty output");
+  DYK_REQUIRE(p->y_plane >= 0 && p->y_plane <= 4, "dyk_conv2d_fwd: y_plane %d", p->y_plane);
+  DYK_REQUIRE(!(p->y_plane && (p->res || p->upsample2x || p->out_f32)),
+              "dyk_conv2d_fwd: y_plane cannot be combined with residual / upsample2x / out_f32");
 
   // 3x3 stride-1 layers: halo kernel (every input pixel loaded once per tile instead of once per tap)
   static const bool no_halo = getenv("DYK_NO_HALO") != nullptr && getenv("DYK_NO_HALO")[0] == '1';
@@ -593,7 +596,8 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   memset(&ka, 0, sizeof(ka));
 
   // 1x1 stride-1 convolutions are plain GEMMs over the flattened pixel index.
-  const bool flat = (p->kh == 1 && p->kw == 1 && p->stride == 1 && p->pad == 0 && !p->upsample2x);
+  const bool flat = (p->kh == 1 && p->kw == 1 && p->stride == 1 && p->pad == 0 && !p->upsample2x && !p->y_plane &&
+                     p->out_h == 0 && p->out_w == 0);
   int tw, th, tn;
   int gW = Wo, gH = Ho, gN = p->N;  // logical output grid the tiles run over
   if (flat) {
@@ -642,14 +646,16 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
     const int sn = 32 / (sw * sh);
     const cuuint32_t ybox[4] = {(cuuint32_t)storeC, (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)sn};
     const long long ys = p->y_pix_stride * 2;
-    if (p->upsample2x) {
+    if (p->upsample2x || p->y_plane) {
       const int W2 = 2 * Wo, H2 = 2 * Ho;
       for (int ph = 0; ph < 2; ++ph)
         for (int pw = 0; pw < 2; ++pw) {
+          if (p->y_plane && p->y_plane - 1 != ph * 2 + pw) continue;
           const cuuint64_t dims[4] = {(cuuint64_t)p->Cout_store, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)p->N};
           const cuuint64_t str[3] = {(cuuint64_t)ys * 2, (cuuint64_t)ys * W2 * 2, (cuuint64_t)ys * W2 * H2};
           uint8_t* base = reinterpret_cast<uint8_t*>(p->y) + ((long long)ph * W2 + pw) * ys;
-          if ((rc = encode_map(&tm.y[ph * 2 + pw], base, 4, dims, str, ybox, storeC * 2, "Y/up"))) return rc;
+          // a single parity plane (y_plane) is stored through y[0] like a dense output
+          if ((rc = encode_map(&tm.y[p->y_plane ? 0 : ph * 2 + pw], base, 4, dims, str, ybox, storeC * 2, "Y/plane"))) return rc;
         }
     } else {
       const cuuint64_t dims[4] = {(cuuint64_t)p->Cout_store, (cuuint64_t)gW, (cuuint64_t)gH, (cuuint64_t)gN};

@@ -1,0 +1,711 @@
+// Training-side HBM-bound kernels: train-mode BatchNorm (batch statistics, running-stat update), BN + activation
+// backward, and the backward of the element-wise / pooling / SE / head-permute ops of the Darknet graph.
+//
+// Replaces what PyTorch autograd does for the reference's modules: nn.BatchNorm2d in
+// training mode + activation (models.py:47-64), WeightedFeatureFusion (layers.py:63-85), FeatureConcat (:32-44),
+// nn.MaxPool2d (models.py:91-94), nn.Upsample (:100-101), SqueezeExcitation (layers.py:175-190) and the permute of
+// YOLOLayer.forward (models.py:229).  Convolution gradients are in conv_wgrad.cu (tcgen05) and, for dgrad, the
+// forward kernels run on flipped weights.
+//
+// All per-channel reductions are two-stage with a fixed slab order (no floating-point atomics), so training runs are
+// bit-reproducible.  Tensors are NHWC 16-bit with (base, pixel stride) addressing like the forward kernels.
+#include "common.h"
+#include "vec.cuh"
+#include "act.cuh"
+
+namespace dyk {
+
+constexpr int kMaxSlabs = DYK_TRAIN_MAX_SLABS;
+
+static inline int grid_for_t(long long work, int block) {
+  long long g = (work + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+static inline int slabs_for(long long npix) {
+  long long s = npix / 1024;
+  if (s < 1) s = 1;
+  if (s > kMaxSlabs) s = kMaxSlabs;
+  return (int)s;
+}
+
+// d act(x) / dx as PyTorch's backward formulas define it (incl. the values chosen at the kinks)
+__device__ __forceinline__ float act_grad(float x, int act) {
+  switch (act) {
+    case DYK_ACT_LEAKY: return x > 0.f ? 1.f : 0.1f;
+    case DYK_ACT_MISH: {
+      const float e = __expf(fminf(x, 20.f));
+      const float n = e * (e + 2.f);
+      const float t = __fdividef(n, n + 2.f);            // tanh(softplus(x))
+      const float sg = __fdividef(e, e + 1.f);           // sigmoid(x)
+      return x > 20.f ? 1.f : t + x * sg * (1.f - t * t);
+    }
+    case DYK_ACT_RELU: return x > 0.f ? 1.f : 0.f;
+    case DYK_ACT_RELU6: return (x > 0.f && x < 6.f) ? 1.f : 0.f;
+    case DYK_ACT_HARDSWISH: return x < -3.f ? 0.f : (x <= 3.f ? x * (1.f / 3.f) + 0.5f : 1.f);
+    case DYK_ACT_HARDSIGMOID: return (x > -3.f && x < 3.f) ? (1.f / 6.f) : 0.f;
+    default: return 1.f;
+  }
+}
+
+// ------------------------------------------------------------------ per-channel slab reductions
+// block: 32 pixel lanes x 8 channel-vectors (64 channels); grid: (ceil(C/64), slabs).
+//   kMode 0: part[slab][0][c] = sum z            part[slab][1][c] = sum z*z                 (BN forward statistics)
+//   kMode 1: part[slab][0][c] = sum g            part[slab][1][c] = sum g*xhat              (BN backward), g = dy*act'(zhat)
+//   kMode 2: part[slab][0][c] = sum a            (bias gradient)
+//   kMode 3: part[slab][0][c] = sum a*b          (per-channel dot, reduced over channels later: fusion-weight grads,
+//                                                 and with pixel ranges restricted to one image: SE gate grads)
+template <bool kBf16, int kMode>
+__global__ void __launch_bounds__(256)
+chan_reduce_kernel(const uint8_t* __restrict__ a, long long as, const uint8_t* __restrict__ b, long long bs,
+                   long long pix0, long long npix, int C, int slabs, const float* __restrict__ scale,
+                   const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                   int act, float* __restrict__ part) {
+  const int cvec = blockIdx.x * 8 + (threadIdx.x & 7);
+  const int plane = threadIdx.x >> 3;
+  const long long per = (npix + slabs - 1) / slabs;
+  const long long p0 = blockIdx.y * per;
+  const long long p1 = p0 + per < npix ? p0 + per : npix;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s0[q] = s1[q] = 0.f;
+  if (cvec * 8 < C) {
+    float sc[8], sh[8], mu[8], is[8];
+    if constexpr (kMode == 1) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        sc[q] = __ldg(scale + cvec * 8 + q); sh[q] = __ldg(shift + cvec * 8 + q);
+        mu[q] = __ldg(mean + cvec * 8 + q); is[q] = __ldg(invstd + cvec * 8 + q);
+      }
+    }
+    for (long long pidx = p0 + plane; pidx < p1; pidx += 32) {
+      const long long pix = pix0 + pidx;
+      float fa[8];
+      unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(a + pix * as * 2) + cvec), fa);
+      if constexpr (kMode == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { s0[q] += fa[q]; s1[q] += fa[q] * fa[q]; }
+      } else if constexpr (kMode == 2) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s0[q] += fa[q];
+      } else {
+        float fb[8];
+        unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(b + pix * bs * 2) + cvec), fb);
+        if constexpr (kMode == 3) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) s0[q] += fa[q] * fb[q];
+        } else {   // a = dy, b = z
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float g = fa[q] * act_grad(fmaf(fb[q], sc[q], sh[q]), act);
+            s0[q] += g;
+            s1[q] += g * ((fb[q] - mu[q]) * is[q]);
+          }
+        }
+      }
+    }
+  }
+  __shared__ float red[2][32][8][8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    red[0][plane][threadIdx.x & 7][q] = s0[q];
+    red[1][plane][threadIdx.x & 7][q] = s1[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, cv = (threadIdx.x >> 3) & 7, q = threadIdx.x & 7;
+    float s = 0.f;
+    for (int l = 0; l < 32; ++l) s += red[which][l][cv][q];
+    const int c = (blockIdx.x * 8 + cv) * 8 + q;
+    if (c < C) part[((long long)blockIdx.y * 2 + which) * C + c] = s;
+  }
+}
+
+// BN forward finalize: batch mean / biased variance -> (scale, shift) for y = z*scale + shift, saved (mean, invstd),
+// running statistics updated in place exactly like nn.BatchNorm2d(momentum) (unbiased variance in running_var).
+__global__ void bn_fwd_finalize_kernel(const float* __restrict__ part, int slabs, float count, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, float momentum,
+                                       float* __restrict__ running_mean, float* __restrict__ running_var,
+                                       float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                       float* __restrict__ invstd_out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int sl = 0; sl < slabs; ++sl) {
+    s0 += (double)part[((long long)sl * 2 + 0) * C + c];
+    s1 += (double)part[((long long)sl * 2 + 1) * C + c];
+  }
+  const double m = s0 / count;
+  double var = s1 / count - m * m;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[c] = g * invstd;
+  shift[c] = b - (float)m * g * invstd;
+  mean_out[c] = (float)m;
+  invstd_out[c] = invstd;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+  if (running_var) {
+    const double unbiased = count > 1.f ? var * (double)count / ((double)count - 1.0) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// y = act(z*scale[c] + shift[c])
+template <bool kBf16>
+__global__ void bn_act_apply_kernel(const uint8_t* __restrict__ z, long long zs, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, int act, uint8_t* __restrict__ y, long long ys,
+                                    long long npix, int cv) {
+  const long long total = npix * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int c = (int)(i - pix * cv);
+    float f[8];
+    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(z + pix * zs * 2) + c), f);
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + c * 8)), a1 = __ldg(reinterpret_cast<const float4*>(scale + c * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + c * 8)), b1 = __ldg(reinterpret_cast<const float4*>(shift + c * 8) + 1);
+    const float sc[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] = apply_act(fmaf(f[q], sc[q], sh[q]), act);
+    *(reinterpret_cast<uint4*>(y + pix * ys * 2) + c) = pack8<kBf16>(f);
+  }
+}
+
+// BN backward finalize: dgamma / dbeta (accumulated into the fp32 parameter gradients) and the three per-channel
+// coefficients of  dz = cA*g + cB + cC*xhat,  cA = gamma*invstd, cB = -cA*sum(g)/M, cC = -cA*sum(g*xhat)/M.
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int slabs, float count, const float* __restrict__ gamma,
+                                       const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ coef, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int sl = 0; sl < slabs; ++sl) {
+    s0 += (double)part[((long long)sl * 2 + 0) * C + c];
+    s1 += (double)part[((long long)sl * 2 + 1) * C + c];
+  }
+  if (dgamma) dgamma[c] += (float)s1;
+  if (dbeta) dbeta[c] += (float)s0;
+  const float cA = (gamma ? gamma[c] : 1.f) * invstd[c];
+  coef[c] = cA;
+  coef[C + c] = (float)(-(double)cA * s0 / count);
+  coef[2 * C + c] = (float)(-(double)cA * s1 / count);
+}
+
+template <bool kBf16>
+__global__ void bn_act_bwd_apply_kernel(const uint8_t* __restrict__ dy, long long dys, const uint8_t* __restrict__ z, long long zs,
+                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                                        const float* __restrict__ coef, int C, int act, uint8_t* __restrict__ dz,
+                                        long long dzs, long long npix, int cv) {
+  const long long total = npix * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int c = (int)(i - pix * cv);
+    float g[8], fz[8], o[8];
+    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dy + pix * dys * 2) + c), g);
+    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(z + pix * zs * 2) + c), fz);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int ch = c * 8 + q;
+      const float zhat = fmaf(fz[q], __ldg(scale + ch), __ldg(shift + ch));
+      const float gg = g[q] * act_grad(zhat, act);
+      const float xhat = (fz[q] - __ldg(mean + ch)) * __ldg(invstd + ch);
+      o[q] = __ldg(coef + ch) * gg + __ldg(coef + C + ch) + __ldg(coef + 2 * C + ch) * xhat;
+    }
+    *(reinterpret_cast<uint4*>(dz + pix * dzs * 2) + c) = pack8<kBf16>(o);
+  }
+}
+
+// out[c] (+)= sum over slabs of part[slab][0][c]   (bias gradients)
+__global__ void slab_sum_kernel(const float* __restrict__ part, int slabs, int C, float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int sl = 0; sl < slabs; ++sl) s += part[((long long)sl * 2) * C + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+// dst = alpha*src (+ dst)
+template <bool kBf16>
+__global__ void axpby_kernel(const uint8_t* __restrict__ src, long long ss, const float* __restrict__ alpha_ptr,
+                             uint8_t* __restrict__ dst, long long ds, long long npix, int cv, int accumulate) {
+  const float alpha = alpha_ptr ? __ldg(alpha_ptr) : 1.f;
+  const long long total = npix * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int c = (int)(i - pix * cv);
+    float f[8];
+    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(src + pix * ss * 2) + c), f);
+    uint4* dp = reinterpret_cast<uint4*>(dst + pix * ds * 2) + c;
+    if (accumulate) {
+      float d[8];
+      unpack8<kBf16>(*dp, d);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) f[q] = fmaf(alpha, f[q], d[q]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) f[q] *= alpha;
+    }
+    *dp = pack8<kBf16>(f);
+  }
+}
+
+// WeightedFeatureFusion backward for the raw parameter w: dots[i] = sum(dy * operand_i) was reduced per channel into
+// part_i[slab][0][c];  grad_w[i] += dots[i] * (2/n) * sigmoid(w_i) * (1 - sigmoid(w_i))      (layers.py:66)
+__global__ void fusion_weights_bwd_kernel(const float* __restrict__ w_raw, const float* __restrict__ part0,
+                                          const float* __restrict__ part1, int slabs, int C, int n,
+                                          float* __restrict__ grad_w) {
+  __shared__ double red[2][256];
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = threadIdx.x; i < slabs * C; i += blockDim.x) {
+    const int sl = i / C, c = i - sl * C;
+    s0 += (double)part0[((long long)sl * 2) * C + c];
+    s1 += (double)part1[((long long)sl * 2) * C + c];
+  }
+  red[0][threadIdx.x] = s0;
+  red[1][threadIdx.x] = s1;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + o];
+      red[1][threadIdx.x] += red[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 2) {
+    const float sg = 1.f / (1.f + expf(-w_raw[threadIdx.x]));
+    grad_w[threadIdx.x] += (float)red[threadIdx.x][0] * (2.f / n) * sg * (1.f - sg);
+  }
+}
+
+// ------------------------------------------------------------------ MaxPool2d backward
+// (1) idx[n][ho][wo][c] = position (hi*W + wi) of the first maximum of the window (scan order, strict '>')
+template <bool kBf16>
+__global__ void maxpool_argmax_kernel(const uint8_t* __restrict__ x, long long xs, int N, int H, int W, int C, int k,
+                                      int stride, int pad, int Ho, int Wo, int* __restrict__ idx) {
+  const long long total = (long long)N * Ho * Wo * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float best = -INFINITY;
+    int bi = -1;
+    for (int r = 0; r < k; ++r) {
+      const int hi = ho * stride - pad + r;
+      if (hi < 0 || hi >= H) continue;
+      for (int s = 0; s < k; ++s) {
+        const int wi = wo * stride - pad + s;
+        if (wi < 0 || wi >= W) continue;
+        const float v = load1<kBf16>(x, (((long long)n * H + hi) * W + wi) * xs + c);
+        if (v > best || bi < 0) { best = v; bi = hi * W + wi; }
+      }
+    }
+    idx[i] = bi;
+  }
+}
+// (2) dx[n][hi][wi][c] (+)= sum of dy over the windows whose argmax is this pixel (fixed order -> deterministic)
+template <bool kBf16>
+__global__ void maxpool_bwd_kernel(const uint8_t* __restrict__ dy, long long dys, const int* __restrict__ idx, int N, int H,
+                                   int W, int C, int k, int stride, int pad, int Ho, int Wo, uint8_t* __restrict__ dx,
+                                   long long dxs, int accumulate) {
+  const long long total = (long long)N * H * W * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int wi = (int)(t % W); t /= W;
+    const int hi = (int)(t % H);
+    const int n = (int)(t / H);
+    const int me = hi * W + wi;
+    float s = 0.f;
+    // outputs whose window covers (hi, wi): ho*stride - pad <= hi <= ho*stride - pad + k - 1
+    int ho_lo = (hi + pad - k + 1 + stride - 1) / stride; if (hi + pad - k + 1 < 0) ho_lo = 0;
+    int wo_lo = (wi + pad - k + 1 + stride - 1) / stride; if (wi + pad - k + 1 < 0) wo_lo = 0;
+    const int ho_hi = min(Ho - 1, (hi + pad) / stride), wo_hi = min(Wo - 1, (wi + pad) / stride);
+    for (int ho = ho_lo; ho <= ho_hi; ++ho)
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        const long long o = (((long long)n * Ho + ho) * Wo + wo);
+        if (idx[o * C + c] == me) s += load1<kBf16>(dy, o * dys + c);
+      }
+    const long long di = (((long long)n * H + hi) * W + wi) * dxs + c;
+    if (accumulate) s += load1<kBf16>(dx, di);
+    store1<kBf16>(dx, di, s);
+  }
+}
+
+// ------------------------------------------------------------------ nearest Upsample backward: sum of the s x s block
+template <bool kBf16>
+__global__ void upsample_bwd_kernel(const uint8_t* __restrict__ dy, long long dys, uint8_t* __restrict__ dx, long long dxs,
+                                    int N, int H, int W, int cv, int s, int accumulate) {
+  const long long total = (long long)N * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    long long t = i / cv;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    for (int a = 0; a < s; ++a)
+      for (int b = 0; b < s; ++b) {
+        const long long op = ((long long)n * H * s + h * s + a) * W * s + w * s + b;
+        float f[8];
+        unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dy + op * dys * 2) + c), f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += f[q];
+      }
+    uint4* dp = reinterpret_cast<uint4*>(dx + (((long long)n * H + h) * W + w) * dxs * 2) + c;
+    if (accumulate) {
+      float d[8];
+      unpack8<kBf16>(*dp, d);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += d[q];
+    }
+    *dp = pack8<kBf16>(acc);
+  }
+}
+
+// ------------------------------------------------------------------ SqueezeExcitation backward (layers.py:184-190)
+// One block: recomputes the tiny MLP per image, then
+//   dv2 = dgate * [ -3 < v2 < 3 ] / 6, dW2 += dv2 (x) hid, db2 += dv2, dhid = W2^T dv2, dv1 = dhid * [v1 > 0],
+//   dW1 += dv1 (x) mean, db1 += dv1, dmean = W1^T dv1;   dmean_out[n][c] = dmean / HW   (added to every pixel of dx).
+// Images are processed sequentially so the weight gradients are accumulated in a fixed order.
+__global__ void __launch_bounds__(1024)
+se_mlp_bwd_kernel(const float* __restrict__ pooled, int slabs, float inv_hw, const float* __restrict__ dgate_part,
+                  int dslabs, int N, int C, int Csq, const float* __restrict__ w1, const float* __restrict__ b1,
+                  const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ gw1,
+                  float* __restrict__ gb1, float* __restrict__ gw2, float* __restrict__ gb2, float* __restrict__ dmean_out) {
+  extern __shared__ float sm[];
+  float* mean = sm;            // [C]
+  float* dv2 = mean + C;       // [C]
+  float* hid = dv2 + C;        // [Csq]
+  float* dv1 = hid + Csq;      // [Csq]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+  for (int n = 0; n < N; ++n) {
+    for (int c = tid; c < C; c += nt) {
+      float s = 0.f;
+      for (int sl = 0; sl < slabs; ++sl) s += pooled[((long long)n * slabs + sl) * C + c];
+      mean[c] = s * inv_hw;
+    }
+    __syncthreads();
+    for (int j = warp; j < Csq; j += nwarps) {
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) s += w1[(long long)j * C + c] * mean[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) hid[j] = s + b1[j];          // pre-activation v1 (relu applied on use)
+    }
+    __syncthreads();
+    for (int c = warp; c < C; c += nwarps) {
+      float s = 0.f;
+      for (int j = lane; j < Csq; j += 32) s += w2[(long long)c * Csq + j] * fmaxf(hid[j], 0.f);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) {
+        const float v2 = s + b2[c];
+        float dg = 0.f;
+        for (int sl = 0; sl < dslabs; ++sl) dg += dgate_part[(((long long)n * dslabs + sl) * 2) * C + c];
+        dv2[c] = (v2 > -3.f && v2 < 3.f) ? dg * (1.f / 6.f) : 0.f;
+      }
+    }
+    __syncthreads();
+    // dW2, db2
+    for (long long i = tid; i < (long long)C * Csq; i += nt) {
+      const int c = (int)(i / Csq), j = (int)(i - (long long)c * Csq);
+      gw2[i] += dv2[c] * fmaxf(hid[j], 0.f);
+    }
+    for (int c = tid; c < C; c += nt) gb2[c] += dv2[c];
+    // dhid -> dv1
+    for (int j = warp; j < Csq; j += nwarps) {
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) s += w2[(long long)c * Csq + j] * dv2[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) dv1[j] = hid[j] > 0.f ? s : 0.f;
+    }
+    __syncthreads();
+    for (long long i = tid; i < (long long)Csq * C; i += nt) {
+      const int j = (int)(i / C), c = (int)(i - (long long)j * C);
+      gw1[i] += dv1[j] * mean[c];
+    }
+    for (int j = tid; j < Csq; j += nt) gb1[j] += dv1[j];
+    for (int c = tid; c < C; c += nt) {
+      float s = 0.f;
+      for (int j = 0; j < Csq; ++j) s += w1[(long long)j * C + c] * dv1[j];
+      dmean_out[(long long)n * C + c] = s * inv_hw;
+    }
+    __syncthreads();
+  }
+}
+// dx (+)= dy * gate[n][c] + dmean[n][c]
+template <bool kBf16>
+__global__ void se_bwd_apply_kernel(const uint8_t* __restrict__ dy, long long dys, const float* __restrict__ gate,
+                                    const float* __restrict__ dmean, uint8_t* __restrict__ dx, long long dxs, int N, int HW,
+                                    int C, int accumulate) {
+  const int cv = C / 8;
+  const long long total = (long long)N * HW * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    const long long pix = i / cv;
+    const int n = (int)(pix / HW);
+    float f[8];
+    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dy + pix * dys * 2) + c), f);
+    uint4* dp = reinterpret_cast<uint4*>(dx + pix * dxs * 2) + c;
+    float d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (accumulate) unpack8<kBf16>(*dp, d);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const long long gi = (long long)n * C + c * 8 + q;
+      f[q] = f[q] * __ldg(gate + gi) + __ldg(dmean + gi) + d[q];
+    }
+    *dp = pack8<kBf16>(f);
+  }
+}
+
+// ------------------------------------------------------------------ YOLOLayer (training) backward
+// dz[n][y][x][a*no + o] = dp[n][a][y][x][o]  (inverse of the view+permute of models.py:229), written as 16-bit NHWC
+// with the channel dimension zero-padded to Cpad so the tensor-core dgrad / wgrad kernels can consume it.
+template <bool kBf16>
+__global__ void yolo_train_bwd_kernel(const float* __restrict__ dp, int N, int na, int ny, int nx, int no, void* __restrict__ dz,
+                                      int Cpad) {
+  const long long total = (long long)N * ny * nx * Cpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % Cpad);
+    long long t = i / Cpad;
+    const int x = (int)(t % nx); t /= nx;
+    const int y = (int)(t % ny);
+    const int n = (int)(t / ny);
+    float v = 0.f;
+    if (ch < na * no) {
+      const int a = ch / no, o = ch - a * no;
+      v = dp[((((long long)n * na + a) * ny + y) * nx + x) * no + o];
+    }
+    store1<kBf16>(dz, i, v);
+  }
+}
+
+// ------------------------------------------------------------------ dgrad weight packing
+// OIHW fp32 -> [I][kh][kw][Opad] 16-bit with the taps rotated by 180 degrees: W'[i][r][s][o] = W[o][i][kh-1-r][kw-1-s]
+template <bool kBf16>
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, void* __restrict__ out, int O, int I, int kh, int kw, int Opad) {
+  const long long total = (long long)I * kh * kw * Opad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % Opad);
+    long long t = i / Opad;
+    const int s = (int)(t % kw); t /= kw;
+    const int r = (int)(t % kh);
+    const int ci = (int)(t / kh);
+    float v = 0.f;
+    if (o < O) v = w[(((long long)o * I + ci) * kh + (kh - 1 - r)) * kw + (kw - 1 - s)];
+    store1<kBf16>(out, i, v);
+  }
+}
+
+}  // namespace dyk
+
+using namespace dyk;
+
+#define DYK_EXPORT extern "C" __attribute__((visibility("default")))
+#define DYK_AL16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+
+DYK_EXPORT int dyk_bn_train_stats(const void* z, int64_t zs, int64_t npix, int32_t C, int32_t dtype, const float* gamma,
+                                  const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                                  float* scale, float* shift, float* mean, float* invstd, float* workspace, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYK_REQUIRE(z && scale && shift && mean && invstd && workspace, "dyk_bn_train_stats: null pointer");
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && zs % 8 == 0 && npix > 0 && DYK_AL16(z), "dyk_bn_train_stats: bad shape");
+  const int slabs = slabs_for(npix);
+  const dim3 grid((C + 63) / 64, slabs);
+  DYK_DISPATCH_DTYPE(dtype, (chan_reduce_kernel<kBf16, 0><<<grid, 256, 0, stream>>>(
+                                (const uint8_t*)z, zs, nullptr, 0, 0, npix, C, slabs, nullptr, nullptr, nullptr, nullptr, 0,
+                                workspace)));
+  DYK_LAUNCH_OK("chan_reduce_kernel<0>");
+  bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(workspace, slabs, (float)npix, gamma, beta, eps, momentum,
+                                                             running_mean, running_var, scale, shift, mean, invstd, C);
+  DYK_LAUNCH_OK("bn_fwd_finalize_kernel");
+  return DYK_OK;
+}
+
+DYK_EXPORT int dyk_bn_act_apply(const void* z, int64_t zs, const float* scale, const float* shift, int32_t act, void* y,
+                                int64_t ys, int64_t npix, int32_t C, int32_t dtype, void* stream_) {
+  DYK_REQUIRE(z && scale && shift && y, "dyk_bn_act_apply: null pointer");
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && zs % 8 == 0 && ys % 8 == 0 && DYK_AL16(z) && DYK_AL16(y), "dyk_bn_act_apply: bad shape");
+  if (npix == 0) return DYK_OK;
+  const int cv = C / 8;
+  DYK_DISPATCH_DTYPE(dtype, (bn_act_apply_kernel<kBf16><<<grid_for_t(npix * cv, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+                                (const uint8_t*)z, zs, scale, shift, act, (uint8_t*)y, ys, npix, cv)));
+  DYK_LAUNCH_OK("bn_act_apply_kernel");
+  return DYK_OK;
+}
+
+DYK_EXPORT int dyk_bn_act_bwd(const void* dy, int64_t dys, const void* z, int64_t zs, const float* scale, const float* shift,
+                              const float* mean, const float* invstd, const float* gamma, int32_t act, int64_t npix,
+                              int32_t C, int32_t dtype, void* dz, int64_t dzs, float* dgamma, float* dbeta,
+                              float* workspace, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYK_REQUIRE(dy && z && scale && shift && mean && invstd && dz && workspace, "dyk_bn_act_bwd: null pointer");
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && zs % 8 == 0 && dys % 8 == 0 && dzs % 8 == 0 && npix > 0, "dyk_bn_act_bwd: bad shape");
+  DYK_REQUIRE(DYK_AL16(dy) && DYK_AL16(z) && DYK_AL16(dz), "dyk_bn_act_bwd: 16-byte alignment");
+  const int slabs = slabs_for(npix);
+  float* part = workspace;                                  // [slabs][2][C]
+  float* coef = workspace + (size_t)kMaxSlabs * 2 * C;      // [3][C]
+  const dim3 grid((C + 63) / 64, slabs);
+  DYK_DISPATCH_DTYPE(dtype, (chan_reduce_kernel<kBf16, 1><<<grid, 256, 0, stream>>>(
+                                (const uint8_t*)dy, dys, (const uint8_t*)z, zs, 0, npix, C, slabs, scale, shift, mean, invstd,
+                                act, part)));
+  DYK_LAUNCH_OK("chan_reduce_kernel<1>");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, slabs, (float)npix, gamma, invstd, dgamma, dbeta, coef, C);
+  DYK_LAUNCH_OK("bn_bwd_finalize_kernel");
+  const int cv = C / 8;
+  DYK_DISPATCH_DTYPE(dtype, (bn_act_bwd_apply_kernel<kBf16><<<grid_for_t(npix * cv, 256), 256, 0, stream>>>(
+                                (const uint8_t*)dy, dys, (const uint8_t*)z, zs, scale, shift, mean, invstd, coef, C, act,
+                                (uint8_t*)dz, dzs, npix, cv)));
+  DYK_LAUNCH_OK("bn_act_bwd_apply_kernel");
+  return DYK_OK;
+}
+
+DYK_EXPORT int dyk_chan_sum(const void* x, int64_t xs, int64_t npix, int32_t C, int32_t dtype, float* out,
+                            int32_t accumulate, float* workspace, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYK_REQUIRE(x && out && workspace, "dyk_chan_sum: null pointer");
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && xs % 8 == 0 && npix > 0 && DYK_AL16(x), "dyk_chan_sum: bad shape");
+  const int slabs = slabs_for(npix);
+  const dim3 grid((C + 63) / 64, slabs);
+  DYK_DISPATCH_DTYPE(dtype, (chan_reduce_kernel<kBf16, 2><<<grid, 256, 0, stream>>>(
+                                (const uint8_t*)x, xs, nullptr, 0, 0, npix, C, slabs, nullptr, nullptr, nullptr, nullptr, 0,
+                                workspace)));
+  DYK_LAUNCH_OK("chan_reduce_kernel<2>");
+  slab_sum_kernel<<<(C + 127) / 128, 128, 0, stream>>>(workspace, slabs, C, out, accumulate);
+  DYK_LAUNCH_OK("slab_sum_kernel");
+  return DYK_OK;
+}
+
+DYK_EXPORT int dyk_axpby(const void* src, int64_t ss, const float* alpha, void* dst, int64_t ds, int64_t npix, int32_t C,
+                         int32_t accumulate, int32_t dtype, void* stream_) {
+  DYK_REQUIRE(src && dst, "dyk_axpby: null pointer");
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && ss % 8 == 0 && ds % 8 == 0 && DYK_AL16(src) && DYK_AL16(dst), "dyk_axpby: bad shape");
+  if (npix == 0) return DYK_OK;
+  const int cv = C / 8;
+  DYK_DISPATCH_DTYPE(dtype, (axpby_kernel<kBf16><<<grid_for_t(npix * cv, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+                                (const uint8_t*)src, ss, alpha, (uint8_t*)dst, ds, npix, cv, accumulate)));
+  DYK_LAUNCH_OK("axpby_kernel");
+  return DYK_OK;
+}
+
+DYK_EXPORT int dyk_fusion_weights_bwd(const void* dy, int64_t dys, const void* a, int64_t as, const void* b, int64_t bs,
+                                      int64_t npix, int32_t C, int32_t dtype, const float* w_raw, int32_t n, float* grad_w,
+                                      float* workspace, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYK_REQUIRE(dy && a && b && w_raw && grad_w && workspace, "dyk_fusion_weights_bwd: null pointer");
+  DYK_REQUIRE(n == 2, "dyk_fusion_weights_bwd: only two-operand fusion is supported (n=%d)", n);
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && dys % 8 == 0 && as % 8 == 0 && bs % 8 == 0 && npix > 0, "dyk_fusion_weights_bwd: bad shape");
+  const int slabs = slabs_for(npix);
+  float* part0 = workspace;
+  float* part1 = workspace + (size_t)kMaxSlabs * 2 * C;
+  const dim3 grid((C + 63) / 64, slabs);
+  DYK_DISPATCH_DTYPE(dtype, (chan_reduce_kernel<kBf16, 3><<<grid, 256, 0, stream>>>(
+                                (const uint8_t*)dy, dys, (const uint8_t*)a, as, 0, npix, C, slabs, nullptr, nullptr, nullptr,
+                                nullptr, 0, part0)));
+  DYK_LAUNCH_OK("chan_reduce_kernel<3>");
+  DYK_DISPATCH_DTYPE(dtype, (chan_reduce_kernel<kBf16, 3><<<grid, 256, 0, stream>>>(
+                                (const uint8_t*)dy, dys, (const uint8_t*)b, bs, 0, npix, C, slabs, nullptr, nullptr, nullptr,
+                                nullptr, 0, part1)));
+  DYK_LAUNCH_OK("chan_reduce_kernel<3>");
+  fusion_weights_bwd_kernel<<<1, 256, 0, stream>>>(w_raw, part0, part1, slabs, C, n, grad_w);
+  DYK_LAUNCH_OK("fusion_weights_bwd_kernel");
+  return DYK_OK;
+}
+
+DYK_EXPORT int dyk_maxpool2d_bwd(const void* x, int64_t xs, const void* dy, int64_t dys, void* dx, int64_t dxs, int32_t N,
+                                 int32_t H, int32_t W, int32_t C, int32_t k, int32_t stride, int32_t accumulate, int32_t dtype,
+                                 int32_t* idx_workspace, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYK_REQUIRE(x && dy && dx && idx_workspace, "dyk_maxpool2d_bwd: null pointer");
+  DYK_REQUIRE(C > 0 && k >= 1 && stride >= 1, "dyk_maxpool2d_bwd: bad shape");
+  const int pad = (k - 1) / 2;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  DYK_REQUIRE(Ho > 0 && Wo > 0, "dyk_maxpool2d_bwd: empty output");
+  DYK_DISPATCH_DTYPE(dtype, (maxpool_argmax_kernel<kBf16><<<grid_for_t((long long)N * Ho * Wo * C, 256), 256, 0, stream>>>(
+                                (const uint8_t*)x, xs, N, H, W, C, k, stride, pad, Ho, Wo, idx_workspace)));
+  DYK_LAUNCH_OK("maxpool_argmax_kernel");
+  DYK_DISPATCH_DTYPE(dtype, (maxpool_bwd_kernel<kBf16><<<grid_for_t((long long)N * H * W * C, 256), 256, 0, stream>>>(
+                                (const uint8_t*)dy, dys, idx_workspace, N, H, W, C, k, stride, pad, Ho, Wo, (uint8_t*)dx, dxs,
+                                accumulate)));
+  DYK_LAUNCH_OK("maxpool_bwd_kernel");
+  return DYK_OK;
+}
+
+DYK_EXPORT int dyk_upsample_nearest_bwd(const void* dy, int64_t dys, void* dx, int64_t dxs, int32_t N, int32_t H, int32_t W,
+                                        int32_t C, int32_t s, int32_t accumulate, int32_t dtype, void* stream_) {
+  DYK_REQUIRE(dy && dx, "dyk_upsample_nearest_bwd: null pointer");
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && dys % 8 == 0 && dxs % 8 == 0 && s >= 1, "dyk_upsample_nearest_bwd: bad shape");
+  const int cv = C / 8;
+  DYK_DISPATCH_DTYPE(dtype, (upsample_bwd_kernel<kBf16><<<grid_for_t((long long)N * H * W * cv, 256), 256, 0,
+                                                        static_cast<cudaStream_t>(stream_)>>>(
+                                (const uint8_t*)dy, dys, (uint8_t*)dx, dxs, N, H, W, cv, s, accumulate)));
+  DYK_LAUNCH_OK("upsample_bwd_kernel");
+  return DYK_OK;
+}
+
+DYK_EXPORT int dyk_se_bwd(const void* x, int64_t xs, const void* dy, int64_t dys, void* dx, int64_t dxs, int32_t N, int32_t HW,
+                          int32_t C, const float* w1, const float* b1, const float* w2, const float* b2, int32_t Csq,
+                          const float* pooled, const float* gate, float* gw1, float* gb1, float* gw2, float* gb2,
+                          int32_t accumulate, int32_t dtype, float* workspace, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYK_REQUIRE(x && dy && dx && w1 && b1 && w2 && b2 && pooled && gate && gw1 && gb1 && gw2 && gb2 && workspace,
+              "dyk_se_bwd: null pointer");
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && xs % 8 == 0 && dys % 8 == 0 && dxs % 8 == 0 && Csq > 0 && N > 0 && HW > 0, "dyk_se_bwd: bad shape");
+  DYK_REQUIRE((size_t)(2 * C + 2 * Csq) * 4 <= 48 * 1024, "dyk_se_bwd: C + Csq too large");
+  // forward used slabs = clamp(HW/256, 1, 32) per image for `pooled` (dyk_se_gate)
+  int fslabs = HW / 256; if (fslabs < 1) fslabs = 1; if (fslabs > 32) fslabs = 32;
+  int dslabs = slabs_for(HW); if (dslabs > 32) dslabs = 32;
+  float* dgate_part = workspace;                                   // [N][dslabs][2][C]
+  float* dmean = workspace + (size_t)N * 32 * 2 * C;               // [N][C]
+  const dim3 grid((C + 63) / 64, dslabs);
+  for (int n = 0; n < N; ++n) {   // dgate[n][c] = sum_hw dy * x
+    DYK_DISPATCH_DTYPE(dtype, (chan_reduce_kernel<kBf16, 3><<<grid, 256, 0, stream>>>(
+                                  (const uint8_t*)dy, dys, (const uint8_t*)x, xs, (long long)n * HW, HW, C, dslabs, nullptr,
+                                  nullptr, nullptr, nullptr, 0, dgate_part + (size_t)n * dslabs * 2 * C)));
+    DYK_LAUNCH_OK("chan_reduce_kernel<3> (se)");
+  }
+  se_mlp_bwd_kernel<<<1, 1024, (2 * C + 2 * Csq) * sizeof(float), stream>>>(pooled, fslabs, 1.f / (float)HW, dgate_part, dslabs, N,
+                                                                          C, Csq, w1, b1, w2, b2, gw1, gb1, gw2, gb2, dmean);
+  DYK_LAUNCH_OK("se_mlp_bwd_kernel");
+  DYK_DISPATCH_DTYPE(dtype, (se_bwd_apply_kernel<kBf16><<<grid_for_t((long long)N * HW * (C / 8), 256), 256, 0, stream>>>(
+                                (const uint8_t*)dy, dys, gate, dmean, (uint8_t*)dx, dxs, N, HW, C, accumulate)));
+  DYK_LAUNCH_OK("se_bwd_apply_kernel");
+  return DYK_OK;
+}
+
+DYK_EXPORT int dyk_yolo_train_bwd(const float* dp, int32_t N, int32_t na, int32_t ny, int32_t nx, int32_t no, void* dz,
+                                  int32_t Cpad, int32_t dtype, void* stream_) {
+  DYK_REQUIRE(dp && dz && Cpad >= na * no && Cpad % 8 == 0, "dyk_yolo_train_bwd: bad arguments");
+  DYK_DISPATCH_DTYPE(dtype, (yolo_train_bwd_kernel<kBf16><<<grid_for_t((long long)N * ny * nx * Cpad, 256), 256, 0,
+                                                          static_cast<cudaStream_t>(stream_)>>>(dp, N, na, ny, nx, no, dz, Cpad)));
+  DYK_LAUNCH_OK("yolo_train_bwd_kernel");
+  return DYK_OK;
+}
+
+DYK_EXPORT int dyk_pack_weights_dgrad(const float* w_oihw, void* w_packed, int32_t O, int32_t I, int32_t kh, int32_t kw,
+                                      int32_t Opad, int32_t dtype, void* stream_) {
+  DYK_REQUIRE(w_oihw && w_packed && O > 0 && I > 0 && kh > 0 && kw > 0 && Opad >= O, "dyk_pack_weights_dgrad: bad arguments");
+  DYK_DISPATCH_DTYPE(dtype, (pack_dgrad_kernel<kBf16><<<grid_for_t((long long)I * kh * kw * Opad, 256), 256, 0,
+                                                      static_cast<cudaStream_t>(stream_)>>>(w_oihw, w_packed, O, I, kh, kw, Opad)));
+  DYK_LAUNCH_OK("pack_dgrad_kernel");
+  return DYK_OK;
+}

@@ -14,6 +14,8 @@ import os as _os
 LIB_PATH = Path(_os.environ.get("DYK_B200_LIB") or PKG_ROOT / "libdyk_b200.so")   # override: the -DDYK_CONV_PROFILE build
 
 DYK_F16, DYK_BF16 = 0, 1
+TRAIN_MAX_SLABS = 128        # DYK_TRAIN_MAX_SLABS
+STEM_WGRAD_STRIPS = 592      # DYK_STEM_WGRAD_STRIPS
 ACT_IDS = {
     "linear": 0, "leaky": 1, "mish": 2, "relu": 3, "relu6": 4, "hard-swish": 5, "hard-sigmoid": 6,
 }
@@ -32,6 +34,7 @@ class ConvParams(C.Structure):
         ("Cout", _i32), ("Cout_store", _i32),
         ("kh", _i32), ("kw", _i32), ("stride", _i32), ("pad", _i32),
         ("act", _i32), ("dtype", _i32), ("upsample2x", _i32), ("out_f32", _i32),
+        ("out_h", _i32), ("out_w", _i32), ("y_plane", _i32),
     ]
 
 
@@ -57,6 +60,25 @@ SIGNATURES = {
     "dyk_nms_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "dyk_nms_batched": (_i32, [_vp, _i32, _i32, _i32, _f32, C.c_double, _i32, C.c_uint64, _i32, _i32, _vp, _vp,
                                _vp, _i64, _vp]),
+    # ---- training path
+    "dyk_bn_train_stats": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dyk_bn_act_apply": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _i32, _vp]),
+    "dyk_bn_act_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _i64, _vp, _vp,
+                              _vp, _vp]),
+    "dyk_chan_sum": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _i32, _vp, _vp]),
+    "dyk_axpby": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
+    "dyk_fusion_weights_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "dyk_maxpool2d_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "dyk_upsample_nearest_bwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dyk_se_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp,
+                          _vp, _vp, _i32, _i32, _vp, _vp]),
+    "dyk_yolo_train_bwd": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp]),
+    "dyk_pack_weights_dgrad": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dyk_conv2d_wgrad_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "dyk_conv2d_wgrad": (_i32, [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                                _vp, _i64, _vp]),
+    "dyk_conv2d_stem_wgrad": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                                     _vp, _vp]),
     "dyk_pack_weights_ohwi": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_nchw_f32_to_nhwc": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_nhwc_to_nchw_f32": (_i32, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),

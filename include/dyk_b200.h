@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DYK_ABI_VERSION 1
+#define DYK_ABI_VERSION 2
 
 enum { DYK_F16 = 0, DYK_BF16 = 1 };
 
@@ -77,6 +77,11 @@ typedef struct dyk_conv_params {
   int32_t dtype;          /* DYK_F16 / DYK_BF16                                  */
   int32_t upsample2x;     /* 1: y is the 2x nearest-upsampled map (models.py:100-101 fused) */
   int32_t out_f32;        /* 1: y is fp32 (y_pix_stride in floats); used by the head convs   */
+  /* ---- ABI v2 additions (zero = previous behaviour) ---- */
+  int32_t out_h, out_w;   /* explicit output size (0 = derive from H, W, pad, k, stride); with pad = 0 this gives
+                             "pad only at the bottom / right", which the strided-conv data gradient needs          */
+  int32_t y_plane;        /* 1 + (row parity*2 + col parity): y is that parity plane of a tensor of size
+                             (2*out_h, 2*out_w) and pixel stride y_pix_stride (0 = dense output)                   */
 } dyk_conv_params;
 int dyk_conv2d_fwd(const dyk_conv_params* p, void* stream);
 
@@ -172,6 +177,83 @@ int dyk_nms_batched(const float* pred, int32_t B, int32_t rows, int32_t nc, floa
                     double iou_thres, int32_t multi_label, uint64_t classes_mask, int32_t agnostic,
                     int32_t max_num, float* out, int32_t* out_count, void* workspace,
                     int64_t workspace_bytes, void* stream);
+
+
+/* =============================== training path ===============================
+ * The reference trains through PyTorch autograd (train_utils/kaist_train_eval_utils.py:74-108:
+ * `pred = model(v, l)` under autocast, `scaler.scale(loss).backward()`).  The entry points below are the native
+ * forward-in-training-mode and backward kernels the Python plan (dyk/train_plan.py) strings together inside one
+ * torch.autograd.Function.  All per-channel reductions use a fixed two-stage order (bit-reproducible, no float atomics).
+ * `workspace` arguments are caller-provided device scratch, sizes in floats given per function.
+ */
+#define DYK_TRAIN_MAX_SLABS 128
+
+/* nn.BatchNorm2d in training mode (models.py:47), statistics part: per-channel batch mean / biased variance of the
+ * 16-bit conv output z -> scale = gamma*invstd, shift = beta - mean*scale (so y = z*scale + shift), saved mean /
+ * invstd for backward, and the in-place running_mean / running_var update (momentum, unbiased variance).
+ * workspace: DYK_TRAIN_MAX_SLABS * 2 * C floats. */
+int dyk_bn_train_stats(const void* z, int64_t z_pix_stride, int64_t npix, int32_t C, int32_t dtype, const float* gamma,
+                       const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                       float* scale, float* shift, float* mean, float* invstd, float* workspace, void* stream);
+/* y = act(z*scale[c] + shift[c])  — BatchNorm normalisation + activation (models.py:47-64) */
+int dyk_bn_act_apply(const void* z, int64_t z_pix_stride, const float* scale, const float* shift, int32_t act, void* y,
+                     int64_t y_pix_stride, int64_t npix, int32_t C, int32_t dtype, void* stream);
+/* backward of activation + train-mode BatchNorm: dz (16-bit) from dy and the saved z / statistics; dgamma, dbeta are
+ * ACCUMULATED into fp32 vectors (may be NULL).  workspace: (DYK_TRAIN_MAX_SLABS * 2 + 3) * C floats. */
+int dyk_bn_act_bwd(const void* dy, int64_t dy_pix_stride, const void* z, int64_t z_pix_stride, const float* scale,
+                   const float* shift, const float* mean, const float* invstd, const float* gamma, int32_t act,
+                   int64_t npix, int32_t C, int32_t dtype, void* dz, int64_t dz_pix_stride, float* dgamma, float* dbeta,
+                   float* workspace, void* stream);
+/* out[c] (+)= sum over pixels of x[pix][c]  (bias gradient of the head convs).  workspace: DYK_TRAIN_MAX_SLABS*2*C floats */
+int dyk_chan_sum(const void* x, int64_t x_pix_stride, int64_t npix, int32_t C, int32_t dtype, float* out,
+                 int32_t accumulate, float* workspace, void* stream);
+/* dst = alpha*src (+ dst when accumulate); alpha read on device (NULL = 1).  Gradient routing of [shortcut] / [route]. */
+int dyk_axpby(const void* src, int64_t src_pix_stride, const float* alpha, void* dst, int64_t dst_pix_stride,
+              int64_t npix, int32_t C, int32_t accumulate, int32_t dtype, void* stream);
+/* WeightedFeatureFusion.w gradient (layers.py:65-73): grad_w[i] += sum(dy*operand_i) * (2/n) * sigmoid'(w_i), n == 2.
+ * workspace: 2 * DYK_TRAIN_MAX_SLABS * 2 * C floats. */
+int dyk_fusion_weights_bwd(const void* dy, int64_t dy_pix_stride, const void* a, int64_t a_pix_stride, const void* b,
+                           int64_t b_pix_stride, int64_t npix, int32_t C, int32_t dtype, const float* w_raw, int32_t n,
+                           float* grad_w, float* workspace, void* stream);
+/* nn.MaxPool2d backward (gradient goes to the first maximum of each window, like PyTorch).
+ * idx_workspace: N*Ho*Wo*C int32. */
+int dyk_maxpool2d_bwd(const void* x, int64_t x_pix_stride, const void* dy, int64_t dy_pix_stride, void* dx,
+                      int64_t dx_pix_stride, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k, int32_t stride,
+                      int32_t accumulate, int32_t dtype, int32_t* idx_workspace, void* stream);
+/* nn.Upsample(nearest, s) backward: dx[h][w] (+)= sum of the s x s block of dy.  H, W are the INPUT (small) sizes. */
+int dyk_upsample_nearest_bwd(const void* dy, int64_t dy_pix_stride, void* dx, int64_t dx_pix_stride, int32_t N, int32_t H,
+                             int32_t W, int32_t C, int32_t s, int32_t accumulate, int32_t dtype, void* stream);
+/* SqueezeExcitation backward (layers.py:184-190): dx (+)= dy*gate + dmean/HW, and the fc1/fc2 weight / bias gradients
+ * ACCUMULATED into gw1 [Csq][C], gb1 [Csq], gw2 [C][Csq], gb2 [C].  pooled / gate: as written by dyk_se_gate in the
+ * forward.  workspace: (64 + 1) * N * C floats. */
+int dyk_se_bwd(const void* x, int64_t x_pix_stride, const void* dy, int64_t dy_pix_stride, void* dx, int64_t dx_pix_stride,
+               int32_t N, int32_t HW, int32_t C, const float* w1, const float* b1, const float* w2, const float* b2,
+               int32_t Csq, const float* pooled, const float* gate, float* gw1, float* gb1, float* gw2, float* gb2,
+               int32_t accumulate, int32_t dtype, float* workspace, void* stream);
+/* inverse of YOLOLayer's view+permute (models.py:229) for the gradient: dp fp32 [N][na][ny][nx][no] -> 16-bit NHWC
+ * [N][ny][nx][Cpad], channels >= na*no zero-filled. */
+int dyk_yolo_train_bwd(const float* dp, int32_t N, int32_t na, int32_t ny, int32_t nx, int32_t no, void* dz, int32_t Cpad,
+                       int32_t dtype, void* stream);
+/* data-gradient weights: OIHW fp32 -> [I][kh][kw][Opad] 16-bit, taps rotated 180 degrees, so that
+ * dx = dyk_conv2d_fwd(dz, W', pad' = k-1-pad) for stride-1 convolutions. */
+int dyk_pack_weights_dgrad(const float* w_oihw, void* w_packed, int32_t O, int32_t I, int32_t kh, int32_t kw, int32_t Opad,
+                           int32_t dtype, void* stream);
+/* weight gradient of a dense convolution (tcgen05, split over pixel ranges, deterministic two-pass reduction):
+ *   grad_w[co][ci][r][s] (+)= sum_{n,ho,wo} dz[n,ho,wo,co] * x[n, ho*stride+r-pad, wo*stride+s-pad, ci]
+ * x: NHWC 16-bit input of the convolution, dz: NHWC 16-bit gradient of its (pre-BN) output, grad_w: fp32 OIHW
+ * (the nn.Conv2d weight layout).  Requirements as dyk_conv2d_fwd; Cout % 8 == 0 (pad dz for the 18-channel heads).
+ * workspace: dyk_conv2d_wgrad_workspace_bytes(...) bytes. */
+int64_t dyk_conv2d_wgrad_workspace_bytes(int32_t Cin, int32_t Cout, int32_t k);
+int dyk_conv2d_wgrad(const void* x, int64_t x_pix_stride, const void* dz, int64_t dz_pix_stride, float* grad_w_oihw,
+                     int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t Cout_real, int32_t k,
+                     int32_t stride, int32_t pad, int32_t accumulate, int32_t dtype, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+/* weight gradient of the stem convolutions (Cin <= 4, NCHW fp32 / uint8 frames as in dyk_conv2d_stem_nchw_fwd).
+ * workspace: DYK_STEM_WGRAD_STRIPS * Cout * k*k*Cin floats. */
+#define DYK_STEM_WGRAD_STRIPS 592
+int dyk_conv2d_stem_wgrad(const void* x_nchw, const void* dz, int64_t dz_pix_stride, float* grad_w_oihw, int32_t N,
+                          int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride, int32_t pad,
+                          int32_t accumulate, int32_t dtype, int32_t x_kind, float* workspace, void* stream);
 
 /* ---- layout / packing helpers ---------------------------------------------------------------------
  * pack: OIHW fp32 (state_dict layout, models.py:35) -> [O][kh][kw][I] dtype.
