@@ -193,19 +193,137 @@ def conv_breakdown(plan, x, y, iters=3):
     return conv_ms, other_ms, flops, n_conv
 
 
+def conv_flops_per_frame(model, Hh, Ww):
+    """2 * sum_conv Cout*Ho*Wo*Cin/groups*k*k for one frame (pair), from the module list."""
+    from dyk import plan as P
+    ops_, _, _, _ = P.build_ops(model, Hh, Ww, "second_index" in model.net_info)
+    fl = 0.0
+    for op in ops_:
+        if isinstance(op, P.ConvOp):
+            c = op.conv
+            fl += 2.0 * op.out.H * op.out.W * c.out_channels * (c.in_channels // c.groups) * c.kernel_size[0] * c.kernel_size[1]
+    return fl
+
+
+def run_train(args, rank, local, world, dev):
+    """BASELINE configs[2]: one optimizer step = forward (batch-statistics BN) + synthetic loss + backward + gradient
+    all-reduce over NCCL + SGD(momentum, nesterov) update, batch 16 per GPU, bf16 storage / fp32 accumulation.
+    The loss (a caller of the path) is a plain torch expression over the three head tensors."""
+    import torch.distributed as dist
+    import models
+    from dyk import _native as nat
+    from dyk import cfg_zoo, dist_utils
+
+    path = cfg_zoo.materialize(args.cfg)
+    torch.manual_seed(0)
+    model = models.YOLO(path, (H, W)).to(dev).train()
+    model.compute_dtype = torch.float16 if args.dtype == "fp16" else torch.bfloat16
+    dual = "second_index" in model.net_info
+    B = args.batch
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=1e-4, momentum=0.937, nesterov=True, foreach=True)   # train.py:85-91
+    ring = 2
+    host = [tuple(t.pin_memory() for t in synthetic_frames(B, seed=1000 * rank + i)) for i in range(ring)]
+    resident = [(v.to(dev), l.to(dev)) for v, l in host]
+
+    def step(v, l):
+        p = model(v, l) if dual else model(v)
+        loss = sum((t.float() ** 2).mean() for t in p)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        dist_utils.allreduce_gradients(params)
+        opt.step()
+        return loss
+
+    def step_resident(i):
+        return step(*resident[i % ring])
+
+    def step_e2e(i):
+        v, l = host[i % ring]
+        loss = step(v.to(dev, non_blocking=True), l.to(dev, non_blocking=True))
+        return float(loss.item())          # the step's result read back
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        return dist_utils.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    for i in range(args.warmup):
+        step_resident(i)
+    step_e2e(0)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = nat.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = nat.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps)
+    if rank == 0:
+        peak_tf, peak_gb, peak_kind = peaks()
+        sustained = peak_tf
+        try:
+            sustained = float(json.loads((REPO / "MEASURED_PEAKS.json").read_text()).get("bf16_tflops_sustained", peak_tf))
+        except Exception:  # noqa: BLE001
+            pass
+        fl_step = 3.0 * conv_flops_per_frame(model, H, W) * B          # fwd + dgrad + wgrad
+        achieved = fl_step / (ms / args.steps / 1e3) / 1e12
+        plan = model._train_plans.last_plan
+        line = {
+            "metric": "paired RGB+LWIR 640x512 frames/sec (training step: forward + backward + all-reduce + SGD)",
+            "value": world * B * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"{args.cfg} {W}x{H} train step, batch {B}/GPU, default-initialised weights, synthetic "
+                                   "squared-logit loss, SGD nesterov", "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"dp{world} (replicas; one flat-bucket gradient all-reduce per step)",
+                       "l2": "activations saved for backward (tens of GB) exceed the 126 MB L2; no explicit flush"},
+            "clocks": clocks,
+            "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": 2 * B * 3 * H * W, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
+                         "frac": achieved / sustained, "traffic": None, "peak_source": peak_kind + " (sustained)",
+                         "kernel": "whole training step (3 x forward conv FLOPs / step time)",
+                         "algorithmic_gflop_per_step": fl_step / 1e9},
+            "train_plan_gb": plan.bytes_allocated / 1e9,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--cfg", default="kaist_dyolov3_add_sl.cfg")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer = BASELINE configs[1] (headline, default); train = configs[2]: dyolov4_fshare bf16 "
+                         "forward + backward + gradient all-reduce + SGD step")
+    ap.add_argument("--cfg", default=None)
     ap.add_argument("--batch", type=int, default=16)
-    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--dtype", default=None, choices=["fp16", "bf16"])
     ap.add_argument("--ref-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
+    if args.cfg is None:
+        args.cfg = "kaist_dyolov3_add_sl.cfg" if args.mode == "infer" else "kaist_dyolov4_fshare_global_concat_se3.cfg"
+    if args.dtype is None:
+        args.dtype = "fp16" if args.mode == "infer" else "bf16"
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -224,6 +342,10 @@ def main():
     import models
     from build_utils.utils import nms_raw
     from dyk import _native as nat
+
+    if args.mode == "train":
+        run_train(args, rank, local, world, dev)
+        return
 
     path, ref, st = oracle_objects(args.cfg)
     model = models.YOLO(path, (H, W))

@@ -570,9 +570,7 @@ class PlanCache:
             raise ValueError("YOLO.forward expects (B, 3, H, W) tensors")
         ops._require_cuda(x, "YOLO.forward")
         if model.training:
-            raise nat.NativeError(
-                "YOLO.forward in training mode: the train-mode (batch-statistics BatchNorm + backward) kernels are "
-                "not built yet; call model.eval() — there is no PyTorch fallback")
+            raise nat.NativeError("PlanCache.run is the eval-mode executor; training goes through dyk.train_plan")
         if y is not None and (y.shape != x.shape or y.device != x.device):
             raise ValueError("visible and LWIR batches must have the same shape and device")
         dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else model.compute_dtype

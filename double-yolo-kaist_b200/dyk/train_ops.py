@@ -169,23 +169,13 @@ def conv_dgrad(dz: View, w_dgrad: torch.Tensor, dx: View, *, k: int, stride: int
         axpby(target, dx, None, True)
 
 
-_sub_cache = {}
-
-
 def _sub_dgrad_weights(w_dgrad, k, pad, ph, pw, offs_h, offs_w):
     """Sub-kernel of the rotated dgrad weights for output parity (ph, pw): taps ordered by increasing dz offset.
-    w_dgrad[ci][r'][s'][co] = W[co][ci][k-1-r'][k-1-s'];  dz offset t_h <-> original tap r = ph + pad - 2*t_h."""
-    key = (w_dgrad.data_ptr(), w_dgrad._version, ph, pw)
-    hit = _sub_cache.get(key)
-    if hit is not None:
-        return hit
+    w_dgrad[ci][r'][s'][co] = W[co][ci][k-1-r'][k-1-s'];  dz offset t_h <-> original tap r = ph + pad - 2*t_h.
+    (Not cached: w_dgrad is re-packed every step, and a pointer-keyed cache would alias recycled allocations.)"""
     rs = [k - 1 - (ph + pad - 2 * t) for t in offs_h]      # index into the rotated tensor
     ss = [k - 1 - (pw + pad - 2 * t) for t in offs_w]
-    sub = w_dgrad[:, rs][:, :, ss].contiguous()            # layout-only gather of parameter taps (host-side packing)
-    if len(_sub_cache) > 4096:
-        _sub_cache.clear()
-    _sub_cache[key] = sub
-    return sub
+    return w_dgrad[:, rs][:, :, ss].contiguous()           # layout-only gather of parameter taps (host-side packing)
 
 
 def conv_wgrad(x: View, dz: View, grad_w: torch.Tensor, *, k: int, stride: int, pad: int, accumulate: bool,

@@ -1,0 +1,385 @@
+"""Training-mode execution plan of ``models.YOLO``: forward with batch-statistics BatchNorm and the full backward,
+as one ``torch.autograd.Function`` whose body is native launches only.
+
+Replaces what autograd does for the reference (reference train_utils/kaist_train_eval_utils.py:
+74-108: ``pred = model(v, l)``, ``scaler.scale(loss).backward()``).  The returned head tensors carry a grad_fn, so the
+reference's ``compute_loss`` / ``GradScaler`` / optimizers / DistributedDataParallel work unchanged on top.
+
+Forward (per cfg block, no cross-layer fusion in this mode — every stored tensor is needed by backward):
+  [convolutional]+BN : conv -> z (16-bit, pre-BN) | batch statistics (two-stage, deterministic) -> scale/shift,
+                       running-stat update | y = act(z*scale + shift)
+  heads (no BN)      : conv + bias -> fp32 logits -> permute (p)
+  shortcut / route / maxpool / upsample / se : the forward kernels of the eval plan (concats are written in place).
+Backward walks the ops in reverse with one gradient buffer per tensor ("first writer overwrites, later writers
+accumulate" is resolved when the plan is built):
+  BN+act backward (reduce, finalize, apply) -> dz ; wgrad (tcgen05, split-K) ; dgrad (forward conv kernels on rotated
+  weights, accumulating through the residual operand) ; axpby routing for shortcut / route ; pool / upsample / SE backward.
+Parameter gradients are produced in one flat fp32 buffer (one view per parameter), zeroed once per backward.
+
+Limits (raise NativeError, never fall back): depthwise / grouped convolutions (MobileNet cfgs), Inception blocks and
+BatchNorm2d(momentum=None) have no training kernels yet; a second forward before the backward of the first overwrites the
+saved activations (the reference never does that).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _native as nat
+from . import ops
+from . import plan as P
+from . import train_ops as T
+from .ops import View
+
+HEAD_PAD = 32   # head logits gradients are padded to 32 channels (K of the dgrad GEMM, 16-byte TMA rows)
+
+
+class _Grad:
+    __slots__ = ("view", "written", "alias_of")
+
+    def __init__(self, view):
+        self.view, self.written, self.alias_of = view, False, None
+
+
+class TrainPlan:
+    def __init__(self, model, B, H, W, dtype, dual, device):
+        self.model, self.B, self.dtype, self.device, self.dual = model, B, dtype, device, dual
+        self.ops, self.layer_vals, self.img0, self.img1 = P.build_ops(model, H, W, dual)
+        for op in self.ops:
+            if isinstance(op, P.ConvOp) and op.flavor == "dw":
+                raise nat.NativeError(f"layer {op.layer}: depthwise convolutions have no training kernels yet")
+            if isinstance(op, P.ConvOp) and op.tag:
+                raise nat.NativeError(f"layer {op.layer}: Inception / separable blocks have no training kernels yet")
+        P.mark_heads(self.ops)
+        P.place_concats(self.ops)
+        self.params = list(model.parameters())
+        self.offsets, off = {}, 0
+        for prm in self.params:
+            self.offsets[id(prm)] = off
+            off += (prm.numel() + 31) // 32 * 32          # padded so vector kernels may write whole 32-float groups
+        self.grad_numel = off
+        self._alloc_forward()
+        self._bind_forward()
+        self._bind_backward()
+
+    # ------------------------------------------------------------------------------------------ storage
+    def _new(self, Cc, H, W, f32=False):
+        dt = torch.float32 if f32 else self.dtype
+        return View(torch.empty((self.B, H, W, Cc), dtype=dt, device=self.device), 0, Cc)
+
+    def _alloc_forward(self):
+        self.bytes_allocated = 0
+        for op in self.ops:
+            v = getattr(op, "out", None)
+            if v is None or v.place:
+                continue
+            v.view = self._new(v.C, v.H, v.W, f32=v.f32)
+            self.bytes_allocated += v.view.buf.numel() * v.view.buf.element_size()
+        for op in self.ops:
+            v = getattr(op, "out", None)
+            if v is not None and v.place:
+                parent, off = v.place
+                v.view = View(parent.view.buf, off, v.C)
+
+    def _vec(self, n):
+        return torch.empty(n, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def _bind_forward(self):
+        self.fwd = []            # callables taking (x, y)
+        self.convs = []          # per ConvOp state (packed weights etc.), refreshed every forward
+        self.bns = []
+        self.p_outs = []
+        self.yolo = []
+        dev = self.device
+        for op in self.ops:
+            if isinstance(op, P.ConvOp):
+                conv, bn = op.conv, op.bn
+                k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+                st = dict(op=op, conv=conv, bn=bn, k=k, s=s, p=p, stem=op.flavor == "stem")
+                if bn is not None:
+                    if bn.momentum is None:
+                        raise nat.NativeError("BatchNorm2d(momentum=None) is not supported by the training kernels")
+                    if not bn.track_running_stats or not bn.affine:
+                        raise nat.NativeError("BatchNorm2d without affine / running stats is not supported")
+                    Cc = conv.out_channels
+                    st.update(z=self._new(Cc, op.out.H, op.out.W), scale=self._vec(Cc), shift=self._vec(Cc),
+                              mean=self._vec(Cc), invstd=self._vec(Cc))
+                    self.bytes_allocated += st["z"].buf.numel() * 2
+                    self.bns.append(bn)
+                elif not op.out.f32:
+                    raise nat.NativeError(f"layer {op.layer}: a convolution without BatchNorm must be a detection head")
+                self.convs.append(st)
+                self.fwd.append(self._conv_fwd(st))
+            elif isinstance(op, P.AddOp):
+                self.fwd.extend(self._add_fwd(op))
+            elif isinstance(op, P.ConcatOp):
+                for s_, off in op.copies:
+                    dst = View(op.out.view.buf, op.out.view.c_off + off, s_.C)
+                    self.fwd.append(lambda x, y, a=s_.view, b=dst: ops.nhwc_copy(a, b))
+            elif isinstance(op, P.PoolOp):
+                self.fwd.append(lambda x, y, o=op: ops.nhwc_maxpool(o.src.view, o.out.view, o.k, o.stride))
+            elif isinstance(op, P.UpOp):
+                self.fwd.append(lambda x, y, o=op: ops.nhwc_upsample(o.src.view, o.out.view, o.s))
+            elif isinstance(op, P.SEOp):
+                op.pooled = torch.empty((self.B, 32, op.src.C), dtype=torch.float32, device=dev)
+                op.gate = torch.empty((self.B, op.src.C), dtype=torch.float32, device=dev)
+                self.fwd.append(lambda x, y, o=op: ops.nhwc_se(o.src.view, o.out.view, *ops.se_weights(o.module.fc1, o.module.fc2),
+                                                                o.pooled, o.gate))
+            elif isinstance(op, P.YoloOp):
+                m = op.module
+                ny, nx = op.src.H, op.src.W
+                if (m.nx, m.ny) != (nx, ny) or m.anchor_vec.device != dev:
+                    m.create_grids((nx, ny), dev)
+                if not op.src.f32:
+                    raise nat.NativeError(f"layer {op.layer}: [yolo] must follow a linear conv without batch norm")
+                p_out = torch.empty((self.B, m.na, ny, nx, m.no), dtype=torch.float32, device=dev)
+                self.p_outs.append(p_out)
+                anchor = m.anchor_vec.to(dev).float().contiguous()
+                self.fwd.append(lambda x, y, o=op, po=p_out, an=anchor, mm=m: ops.yolo_decode(
+                    o.src.view.buf, o.src.view.stride, po, None, N=self.B, ny=o.src.H, nx=o.src.W, na=mm.na, no=mm.no,
+                    anchor_vec=an, stride=mm.stride, v4=mm.bf_type == "yolov4", rows_total=0, row_off=0, in_kind=2))
+
+    def _conv_fwd(self, st):
+        op, conv, bn = st["op"], st["conv"], st["bn"]
+        k, s, p = st["k"], st["s"], st["p"]
+
+        def run(x, y):
+            if st["stem"]:
+                src = x if op.src is self.img0 else y
+                st["x_in"] = src
+                w = conv.weight.detach().float().permute(0, 2, 3, 1).contiguous()
+                ops.nhwc_stem(src, w, None, None, st["z"], k=k, stride=s, pad=p, act="linear")
+            else:
+                st["w"] = ops.pack_conv_weight(conv.weight, self.dtype)
+                if bn is None:
+                    st["bias"] = ops.pad_vec(conv.bias) if conv.bias is not None else None
+                    ops.nhwc_conv(op.src.view, st["w"], None, st["bias"], op.out.view, k=k, stride=s, pad=p, act="linear",
+                                  out_f32=True, cout=conv.out_channels)
+                    return
+                ops.nhwc_conv(op.src.view, st["w"], None, None, st["z"], k=k, stride=s, pad=p, act="linear",
+                              cout=conv.out_channels)
+            T.bn_train_stats(st["z"], bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum, bn.running_mean,
+                             bn.running_var, st["scale"], st["shift"], st["mean"], st["invstd"])
+            T.bn_act_apply(st["z"], st["scale"], st["shift"], op.act, op.out.view)
+        return run
+
+    def _add_fwd(self, op):
+        m = op.module
+        if len(op.others) != 1 or op.others[0].C != op.x.C:
+            raise nat.NativeError(f"layer {op.layer}: only two-operand, equal-width shortcuts have training kernels")
+        steps = []
+        op.wall = None
+        if m.weight:
+            op.wall = torch.empty(2, dtype=torch.float32, device=self.device)
+            steps.append(lambda x, y, o=op, mm=m: ops.fusion_weights(mm.w.detach(), o.wall))
+        steps.append(lambda x, y, o=op: ops.nhwc_add(o.x.view, o.others[0].view, o.out.view, o.wall))
+        return steps
+
+    def forward(self, x, y):
+        for f in self.fwd:
+            f(x, y)
+        if self.bns:
+            torch._foreach_add_([bn.num_batches_tracked for bn in self.bns], 1)   # counters, not arithmetic of the path
+        return tuple(t.clone() for t in self.p_outs)
+
+    # ------------------------------------------------------------------------------------------ backward
+    def _pgrad(self, flat, prm):
+        o = self.offsets[id(prm)]
+        return flat[o:o + prm.numel()].view(prm.shape)
+
+    def _bind_backward(self):
+        """Static schedule of the backward launches.  Each entry is a callable(flat_grads, dps)."""
+        consumers = {}
+        for op in self.ops:
+            for v in op.inputs():
+                consumers.setdefault(id(v), []).append(op)
+        grads = {}
+
+        def gslot(v):
+            g = grads.get(id(v))
+            if g is None:
+                alias = None
+                if v.place is not None:
+                    parent, off = v.place
+                    cons = consumers.get(id(v), [])
+                    if len(cons) == 1 and isinstance(cons[0], P.ConcatOp) and cons[0].out is parent \
+                            and all(s is not v for s, _ in cons[0].copies):
+                        alias = (parent, off)
+                if alias is not None:
+                    pg = gslot(alias[0])
+                    g = _Grad(View(pg.view.buf, pg.view.c_off + alias[1], v.C))
+                    g.alias_of = pg
+                elif v.f32:      # head logits: gradient kept as padded 16-bit NHWC
+                    g = _Grad(self._new(HEAD_PAD, v.H, v.W))
+                else:
+                    g = _Grad(self._new(v.C, v.H, v.W))
+                    self.bytes_allocated += g.view.buf.numel() * 2
+                grads[id(v)] = g
+            return g
+
+        def is_written(g):
+            return g.written or (g.alias_of is not None and is_written(g.alias_of))
+
+        def claim(v):
+            """Returns (grad view of v, accumulate?) and marks it written."""
+            g = gslot(v)
+            acc = is_written(g)
+            g.written = True
+            return g.view, acc
+
+        self.grads, self.consumers = grads, consumers
+        self.bwd = []
+        max_z = max((st["z"].buf.numel() for st in self.convs if "z" in st), default=0)
+        self.dz_scratch = torch.empty(max_z, dtype=self.dtype, device=self.device)
+        conv_state = {id(st["op"]): st for st in self.convs}
+        yolo_i = len(self.p_outs)
+        for op in reversed(self.ops):
+            if isinstance(op, P.YoloOp):
+                yolo_i -= 1
+                gv, acc = claim(op.src)
+                if acc:
+                    raise nat.NativeError("a head convolution feeds more than one consumer")
+                self.bwd.append(lambda flat, dps, i=yolo_i, g=gv: T.yolo_train_bwd(dps[i], g))
+                continue
+            out = getattr(op, "out", None)
+            if out is None:
+                continue
+            gout = grads.get(id(out))
+            if gout is None or not is_written(gout):
+                continue      # nothing downstream depends on this tensor
+            dy = gout.view
+            if isinstance(op, P.ConvOp):
+                st = conv_state[id(op)]
+                self._conv_bwd(st, dy, claim if not st["stem"] else None)
+            elif isinstance(op, P.AddOp):
+                m = op.module
+                for i, operand in enumerate([op.x, op.others[0]]):
+                    gv, acc = claim(operand)
+                    self.bwd.append(lambda flat, dps, d=dy, g=gv, a=acc, o=op, i=i:
+                                    T.axpby(d, g, o.wall[i:i + 1] if o.wall is not None else None, a))
+                if m.weight:
+                    self.bwd.append(lambda flat, dps, d=dy, o=op, mm=m:
+                                    T.fusion_weights_bwd(d, o.x.view, o.others[0].view, mm.w.detach(), self._pgrad(flat, mm.w)))
+            elif isinstance(op, P.ConcatOp):
+                off = 0
+                for s_ in op.srcs:
+                    g = gslot(s_)
+                    if g.alias_of is None or g.alias_of is not grads.get(id(op.out)):
+                        gv, acc = claim(s_)
+                        src = View(dy.buf, dy.c_off + off, s_.C)
+                        self.bwd.append(lambda flat, dps, a=src, b=gv, c=acc: T.axpby(a, b, None, c))
+                    off += s_.C
+            elif isinstance(op, P.PoolOp):
+                gv, acc = claim(op.src)
+                self.bwd.append(lambda flat, dps, o=op, d=dy, g=gv, a=acc: T.maxpool_bwd(o.src.view, d, g, o.k, o.stride, a))
+            elif isinstance(op, P.UpOp):
+                gv, acc = claim(op.src)
+                self.bwd.append(lambda flat, dps, o=op, d=dy, g=gv, a=acc: T.upsample_bwd(d, g, o.s, a))
+            elif isinstance(op, P.SEOp):
+                gv, acc = claim(op.src)
+
+                def se(flat, dps, o=op, d=dy, g=gv, a=acc):
+                    m = o.module
+                    w1, b1, w2, b2 = ops.se_weights(m.fc1, m.fc2)
+                    T.se_bwd(o.src.view, d, g, w1, b1, w2, b2, o.pooled, o.gate,
+                             self._pgrad(flat, m.fc1.weight).view(w1.shape), self._pgrad(flat, m.fc1.bias),
+                             self._pgrad(flat, m.fc2.weight).view(w2.shape), self._pgrad(flat, m.fc2.bias), a)
+                self.bwd.append(se)
+
+    def _conv_bwd(self, st, dy, claim):
+        op, conv, bn = st["op"], st["conv"], st["bn"]
+        k, s, p = st["k"], st["s"], st["p"]
+        gin = claim(op.src) if claim is not None else None
+        st["dy_view"], st["gin"] = dy, gin      # kept for the teacher-forced backward check (oracle/layerwise.py)
+
+        def run(flat, dps):
+            gw = self._pgrad(flat, conv.weight)
+            if bn is not None:
+                z = st["z"]
+                dz = View(self.dz_scratch[:z.buf.numel()].view(z.buf.shape), 0, z.C)
+                T.bn_act_bwd(dy, z, st["scale"], st["shift"], st["mean"], st["invstd"], bn.weight.detach(), op.act, dz,
+                             self._pgrad(flat, bn.weight), self._pgrad(flat, bn.bias))
+                cout_real = None
+            else:
+                dz = dy                                   # padded 16-bit head gradient
+                cout_real = conv.out_channels
+                if conv.bias is not None:
+                    o = self.offsets[id(conv.bias)]
+                    T.chan_sum(dz, flat[o:o + HEAD_PAD], accumulate=True)
+            if st["stem"]:
+                T.stem_wgrad(st["x_in"], dz, gw, k=k, stride=s, pad=p, accumulate=True)
+                return
+            T.conv_wgrad(op.src.view, dz, gw, k=k, stride=s, pad=p, accumulate=True, cout_real=cout_real)
+            gv, acc = gin
+            wd = T.pack_dgrad_weight(conv.weight, self.dtype, opad=dz.C)
+            T.conv_dgrad(dz, wd, gv, k=k, stride=s, pad=p, accumulate=acc)
+        self.bwd.append(run)
+
+    def backward(self, dps):
+        flat = torch.zeros(self.grad_numel, dtype=torch.float32, device=self.device)
+        dps = [d.detach().float().contiguous() if d is not None else torch.zeros_like(po)
+               for d, po in zip(dps, self.p_outs)]
+        for f in self.bwd:
+            f(flat, dps)
+        self.last_flat = flat
+        return [self._pgrad(flat, prm) if prm.requires_grad else None for prm in self.params]
+
+
+class _TrainFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, x, y, *params):
+        ctx.plan = plan
+        ctx.n_params = len(params)
+        outs = plan.forward(x, y)
+        return outs
+
+    @staticmethod
+    def backward(ctx, *dps):
+        with torch.cuda.device(ctx.plan.device):
+            grads = ctx.plan.backward(list(dps))
+        return (None, None, None, *grads)
+
+
+class TrainPlanCache:
+    """At most `keep` training plans are alive (each holds every activation of a step); multi-scale training
+    (reference train.py:143-151) switches shapes every few iterations, so the least recently used plan is dropped."""
+
+    def __init__(self, model, keep=2):
+        self.model, self.keep = model, keep
+        self.plans = {}
+        self.last_plan = None
+
+    def invalidate(self):
+        self.plans.clear()
+        self.last_plan = None
+
+    def run(self, x, y):
+        model = self.model
+        ops._require_cuda(x, "YOLO.forward (training)")
+        dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else model.compute_dtype
+        if dtype not in (torch.float16, torch.bfloat16):
+            raise nat.NativeError(f"compute dtype {dtype} is not supported (float16 / bfloat16)")
+        if y is not None and (y.shape != x.shape or y.device != x.device):
+            raise ValueError("visible and LWIR batches must have the same shape and device")
+
+        def prep(t):
+            if t is None:
+                return None
+            if t.dtype not in (torch.float32, torch.uint8):
+                t = t.float()
+            return t.detach().contiguous()
+
+        x, y = prep(x), prep(y)
+        B, _, H, W = x.shape
+        key = (B, H, W, dtype, y is not None, x.device)
+        plan = self.plans.pop(key, None)
+        with torch.cuda.device(x.device):
+            if plan is None:
+                while len(self.plans) >= self.keep:
+                    self.plans.pop(next(iter(self.plans)))
+                plan = TrainPlan(model, B, H, W, dtype, y is not None, x.device)
+            self.plans[key] = plan           # re-insert = most recently used
+            self.last_plan = plan
+            outs = _TrainFunction.apply(plan, x, y, *plan.params)
+        return list(outs)

@@ -25,6 +25,7 @@ from build_utils.parse_config import parse_model_cfg
 from build_utils.utils import get_yolo_layers
 from dyk import ops as _ops
 from dyk import plan as _plan
+from dyk import train_plan as _train_plan
 
 
 def create_modules(modules_defs: list, img_size, cfg):
@@ -182,7 +183,9 @@ class YOLO(nn.Module):
 
     ``forward(x, y=None)``: x = visible frames, y = LWIR frames, NCHW float (values in [0,1]) or uint8
     (raw pixels; the /255 of the reference's callers is then fused into the stem kernel) CUDA tensors.
-    Training mode returns the list of raw head tensors, eval mode ``(cat(io, 1), tuple(p))``.
+    Training mode returns the list of raw head tensors (differentiable: forward with batch-statistics BatchNorm and
+    the whole backward run as native kernels inside one autograd node, dyk/train_plan.py), eval mode
+    ``(cat(io, 1), tuple(p))``.
 
     Extra knobs (not in the reference): ``compute_dtype`` (torch.float16 | torch.bfloat16; under
     ``torch.autocast`` the autocast dtype wins) and ``use_cuda_graph``.
@@ -197,6 +200,7 @@ class YOLO(nn.Module):
         self.compute_dtype = torch.float16
         self.use_cuda_graph = True
         self._plans = _plan.PlanCache(self)
+        self._train_plans = _train_plan.TrainPlanCache(self)
         self.info(verbose)
 
     def get_yolo_layers(self):
@@ -209,10 +213,16 @@ class YOLO(nn.Module):
         out = super()._apply(fn, *args, **kwargs)
         if '_plans' in self.__dict__:
             self._plans.invalidate()  # parameter storage may have moved
+        if '_train_plans' in self.__dict__:
+            self._train_plans.invalidate()
         return out
 
     def forward(self, x, y=None):
         di = "second_index" in self.net_info and y is not None
+        if self.training:
+            if "second_index" in self.net_info and y is None:
+                raise ValueError("this cfg defines second_index: call model(visible, lwir) with both modalities")
+            return self._train_plans.run(x, y if di else None)   # list of raw head tensors with a grad_fn
         io, p = self._plans.run(x, y if di else None)
         return io, p
 

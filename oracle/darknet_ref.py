@@ -201,6 +201,8 @@ class DarknetRef:
         if self._round is not None and groups == 1 and w.shape[1] > 4:
             w = w.to(self._round).float()   # dense tensor-core convs hold their weights in the 16-bit dtype
         x = F.conv2d(x, w, st.get(pconv + ".bias"), stride, pad, 1, groups)
+        if pbn is not None and training and self._round is not None:
+            x = x.to(self._round).float()   # the training plan stores the pre-BN conv output in 16 bits
         if pbn is not None:
             x = self._bn(x, st, pbn, training, mom)
         return activation(x, act)

@@ -68,3 +68,65 @@ def assert_layerwise(rows, n_layers, what=""):
         assert r["frac_diff"] < 0.05, (what, "too many elements differ", r)
         checked += 1
     assert checked > n_layers // 3, (what, "too few layers were compared", checked)
+
+
+def _nchw(view):
+    return view.buf[..., view.c_off:view.c_off + view.C].permute(0, 3, 1, 2).float().cpu().contiguous()
+
+
+def compare_backward(plan, frames):
+    """Teacher-forced check of the training backward, convolution block by convolution block.
+
+    After one native forward + backward (plan = model._train_plans.last_plan) every block's *native* input x, the native
+    gradient dy of its output and the native parameter gradients are still in the plan's buffers.  For each
+    [convolutional] block the oracle recomputes y = act(BN_train(conv(x, W))) in fp32 torch from the native x (weights
+    rounded to the 16-bit type like the tensor-core kernel sees them), back-propagates the native dy through it with
+    autograd and compares dW, dgamma, dbeta (and dx where this block is the only writer of the input gradient).
+    Evaluating every block on the native tensors keeps the activation kinks on the same side, which an end-to-end
+    comparison of a 16-bit run with an fp32 run cannot (see tools/train_parity.py).
+    frames: (visible, lwir) NCHW fp32 CPU tensors as given to the model (for the stem blocks).
+    Returns a list of dict(layer, dW, dgamma, dbeta, dx) with relative L2 errors (None where not applicable)."""
+    import torch.nn.functional as F
+    from oracle.darknet_ref import activation
+    flat = plan.last_flat
+    rows = []
+    for st in plan.convs:
+        op, conv, bn = st["op"], st["conv"], st["bn"]
+        k, s, p = st["k"], st["s"], st["p"]
+        if st["stem"]:
+            x = (frames[0] if op.src is plan.img0 else frames[1]).clone()
+            w = conv.weight.detach().float().cpu().clone()
+        else:
+            x = _nchw(op.src.view)
+            w = conv.weight.detach().to(plan.dtype).float().cpu().clone()
+        dy_full = _nchw(st["dy_view"])
+        if bn is not None:
+            # BN + activation on the *native* pre-BN tensor z (so every activation kink sits where the native run had it),
+            # then the convolution gradients from the 16-bit-rounded dz, as the native wgrad / dgrad kernels see it
+            g = bn.weight.detach().float().cpu().clone().requires_grad_(True)
+            b = bn.bias.detach().float().cpu().clone().requires_grad_(True)
+            z = _nchw(st["z"]).requires_grad_(True)
+            activation(F.batch_norm(z, None, None, g, b, True, 0.0, bn.eps), op.act).backward(dy_full)
+            dz = z.grad.to(plan.dtype).float()
+            bias = None
+        else:
+            g = b = None
+            bias = conv.bias.detach().float().cpu().clone().requires_grad_(True)
+            dz = dy_full[:, :conv.out_channels]
+        w_grad = torch.nn.grad.conv2d_weight(x, w.shape, dz, stride=s, padding=p)
+        x_grad = None if st["stem"] else torch.nn.grad.conv2d_input(x.shape, w, dz, stride=s, padding=p)
+        bias_grad = None if bias is None else dz.sum((0, 2, 3))
+
+        def rel(got, want):
+            return float((got.cpu() - want).norm() / (want.norm() + 1e-20))
+
+        row = dict(layer=op.layer, dW=rel(plan._pgrad(flat, conv.weight), w_grad))
+        if bn is not None:
+            row["dgamma"] = rel(plan._pgrad(flat, bn.weight), g.grad)
+            row["dbeta"] = rel(plan._pgrad(flat, bn.bias), b.grad)
+        else:
+            row["dbias"] = rel(plan._pgrad(flat, conv.bias), bias_grad)
+        if not st["stem"] and len(plan.consumers.get(id(op.src), [])) == 1 and st["gin"] is not None and not st["gin"][1]:
+            row["dx"] = rel(_nchw(st["gin"][0]), x_grad)
+        rows.append(row)
+    return rows
