@@ -1,0 +1,387 @@
+// CTA-pair (tcgen05 cta_group::2) version of the 3x3 stride-1 halo convolution (conv_halo.cu): two SMs of one TPC
+// compute a 256-pixel x 256-channel tile together.
+//
+// Why pairs: an SS-mode tcgen05.mma re-reads its operands from shared memory for every K = 16 step, and the measured
+// ceiling of that path is ~100 B/clk/SM for MMA operand reads + TMA writes together (profiles/README.md).  A single CTA
+// at 128 x 256 needs 96 B/clk for operand reads alone plus 68 B/clk of TMA writes -> ~60 % tensor pipe.  In a pair each
+// CTA holds its own 128 pixel rows (A, as a halo window: loaded once per 64-channel chunk for all nine taps) and HALF of
+// the 256-row weight tile (B); the pair's MMA (M = 256) reads A locally and each B half once, so per CTA and tap
+// (512 MMA cycles) shared memory moves 32 KB of operand reads + 18.6 KB of TMA writes = 99 B/clk.
+//
+// Protocol (as in CUTLASS' 2-SM kernels): both CTAs run a TMA producer for their own halves, crediting the bytes to the
+// LEADER CTA's "full" barriers; only the leader issues tcgen05.mma.cta_group::2; tcgen05.commit multicasts the "empty"
+// and "accumulator full" arrivals to both CTAs; the epilogue warps of both CTAs arrive on the leader's "accumulator
+// empty" barrier.  Accumulators: 128 lanes x 256 fp32 columns per CTA, double buffered (all 512 TMEM columns).
+//
+// Warp roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner (+ MMA issuer in the leader),
+// warps 2..9 = epilogue.
+#include "common.h"
+#include "ptx.cuh"
+#include "act.cuh"
+#include "conv_common.cuh"
+#include <cstdlib>
+#include <cstring>
+
+namespace dyk {
+
+int encode_map_generic(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+                       const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle_bytes, const char* what);
+
+struct Halo2Tmaps {
+  CUtensorMap a;  // input  (Cin, W, H, N), box {64, 10, 18, 1}
+  CUtensorMap b;  // packed weights (Cin, 9, Cout), box {64, 1, 128}
+  CUtensorMap y;  // output (Cout_store, W, H, N), box {32, 8, 4, 1}
+};
+
+struct Halo2KArgs {
+  int H, W, N;
+  int num_subs;
+  int n_blocks, num_tiles;      // pair tiles = ceil(num_subs / 2) * n_blocks, n-block fastest
+  int k_chunks;
+  int Cout_store;
+  int act;
+  FastDiv fd_nblocks, fd_subs_w, fd_subs_h;
+  const float* scale;
+  const float* bias;
+  const void* res;
+  long long res_pix_stride;
+};
+
+constexpr int kH2EpiWarps = 8;
+constexpr int kH2Threads = 64 + kH2EpiWarps * 32;
+constexpr int kH2SubW = 8, kH2SubH = 16, kH2HaloW = 10, kH2HaloH = 18;
+constexpr int kH2HaloBytes = kH2HaloW * kH2HaloH * 128;   // 23040
+constexpr int kH2ASlot = 23552;
+constexpr int kH2BSlot = 128 * 128;                       // half of the 256-row weight tile
+constexpr int kH2AStages = 2, kH2BStages = 8;
+constexpr int kH2BlockN = 256;
+constexpr int kH2StagingBytes = kH2EpiWarps * 2 * 2048;
+constexpr int kH2VecFloats = 2 * kH2BlockN;
+constexpr int kH2VecBytes = kH2EpiWarps * kH2VecFloats * 4;
+constexpr int kH2Total = kH2AStages * kH2ASlot + kH2BStages * kH2BSlot + kH2StagingBytes + kH2VecBytes + 1024 + 1024;
+static_assert(kH2Total <= 227 * 1024, "halo2 shared memory budget");
+
+struct Sub2 {
+  int w0, h0, n;
+};
+__device__ __forceinline__ Sub2 sub2_coord(const Halo2KArgs& p, unsigned sub) {
+  Sub2 c;
+  const unsigned rowt = fd_div(sub, p.fd_subs_w);
+  const unsigned sw = sub - rowt * p.fd_subs_w.div;
+  const unsigned n = fd_div(rowt, p.fd_subs_h);
+  const unsigned sh = rowt - n * p.fd_subs_h.div;
+  c.w0 = sw * kH2SubW;
+  c.h0 = sh * kH2SubH;
+  c.n = sub < (unsigned)p.num_subs ? (int)n : p.N;
+  return c;
+}
+
+template <bool kBf16, int kAct>
+__device__ __forceinline__ void halo2_epilogue(const Halo2Tmaps& tm, const Halo2KArgs& p, const Sub2& sc, int n_base,
+                                               uint32_t t_row, uint8_t* wstage, float* wvec, int& sbuf,
+                                               uint32_t tempty_leader, int q, int lane, int half) {
+  constexpr int kCols = 32;
+  constexpr int kChunks = kH2BlockN / kCols;   // 8; this warp handles chunks half, half+2, ...
+  const int row = q * 32 + lane;
+  const int wo = sc.w0 + (row & 7), ho = sc.h0 + (row >> 3);
+  const bool sub_ok = sc.n < p.N;
+  const bool pix_ok = sub_ok && (wo < p.W) && (ho < p.H);
+  const long long pix = (static_cast<long long>(sc.n) * p.H + ho) * p.W + wo;
+  const bool has_res = p.res != nullptr;
+
+  uint4 rres[kCols / 8];
+  auto load_res = [&](int c) {
+    const int c0 = n_base + c * kCols;
+    const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (pix * p.res_pix_stride + c0) * 2;
+#pragma unroll
+    for (int j = 0; j < kCols / 8; ++j) {
+      rres[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (pix_ok && c0 + j * 8 < p.Cout_store) rres[j] = __ldg(reinterpret_cast<const uint4*>(rp) + j);
+    }
+  };
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < kH2BlockN / 32; ++j) {
+    const int col = n_base + j * 32 + lane;
+    wvec[j * 32 + lane] = p.scale ? __ldg(p.scale + col) : 1.f;
+    wvec[kH2BlockN + j * 32 + lane] = p.bias ? __ldg(p.bias + col) : 0.f;
+  }
+  __syncwarp();
+
+#pragma unroll 1
+  for (int c = half; c < kChunks; c += 2) {
+    const int cl = c * kCols;
+    const int cg0 = n_base + cl;
+    const bool beyond = cg0 >= p.Cout_store || !sub_ok;
+    const bool last = (c + 2 >= kChunks) || (cg0 + 2 * kCols >= p.Cout_store);
+    if (beyond) {
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader);
+      break;
+    }
+    if (has_res) load_res(c);
+    uint32_t v[kCols];
+    tmem_ld_32x32b_x32(t_row + cl, v);
+    tmem_ld_wait();
+    if (last) {
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader);
+    }
+    uint8_t* sbase = wstage + sbuf * 2048;
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
+#pragma unroll
+    for (int ch = 0; ch < kCols / 8; ++ch) {
+      float o[8];
+      const float4 sc0 = *reinterpret_cast<const float4*>(wvec + cl + ch * 8);
+      const float4 sc1 = *reinterpret_cast<const float4*>(wvec + cl + ch * 8 + 4);
+      const float4 bi0 = *reinterpret_cast<const float4*>(wvec + kH2BlockN + cl + ch * 8);
+      const float4 bi1 = *reinterpret_cast<const float4*>(wvec + kH2BlockN + cl + ch * 8 + 4);
+      o[0] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 0]), sc0.x, bi0.x));
+      o[1] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 1]), sc0.y, bi0.y));
+      o[2] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 2]), sc0.z, bi0.z));
+      o[3] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 3]), sc0.w, bi0.w));
+      o[4] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 4]), sc1.x, bi1.x));
+      o[5] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 5]), sc1.y, bi1.y));
+      o[6] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 6]), sc1.z, bi1.z));
+      o[7] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 7]), sc1.w, bi1.w));
+      if (has_res) {
+        const uint32_t rr[4] = {rres[ch].x, rres[ch].y, rres[ch].z, rres[ch].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack2<kBf16>(rr[e]);
+          o[e * 2 + 0] += f.x;
+          o[e * 2 + 1] += f.y;
+        }
+      }
+      const int phys = ch ^ ((lane >> 1) & 3);
+      const uint4 val = make_uint4(pack2<kBf16>(o[0], o[1]), pack2<kBf16>(o[2], o[3]), pack2<kBf16>(o[4], o[5]),
+                                   pack2<kBf16>(o[6], o[7]));
+      *reinterpret_cast<uint4*>(sbase + lane * 64 + phys * 16) = val;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(&tm.y, sbase, cg0, sc.w0, sc.h0 + 4 * q, sc.n);
+      tma_store_commit();
+    }
+    sbuf ^= 1;
+    if (last) break;
+  }
+}
+
+template <bool kBf16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kH2Threads, 1)
+conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_base = smem;
+  uint8_t* b_base = a_base + kH2AStages * kH2ASlot;
+  uint8_t* staging = b_base + kH2BStages * kH2BSlot;
+  float* vecs = reinterpret_cast<float*>(staging + kH2StagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(vecs) + kH2VecBytes);
+  uint64_t* a_full = bars;                          // [2]  (used in the leader)
+  uint64_t* a_empty = a_full + kH2AStages;          // [2]  (per CTA, multicast arrivals)
+  uint64_t* b_full = a_empty + kH2AStages;          // [8]  (leader)
+  uint64_t* b_empty = b_full + kH2BStages;          // [8]  (per CTA)
+  uint64_t* tfull = b_empty + kH2BStages;           // [2]  (per CTA, multicast arrivals)
+  uint64_t* tempty = tfull + 2;                     // [2]  (leader; 16 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.a);
+    tma_prefetch_desc(&tm.b);
+    tma_prefetch_desc(&tm.y);
+    for (int i = 0; i < kH2AStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kH2BStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * kH2EpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp_idx == 1) tmem_alloc_2sm<512>(tmem_slot);
+  tc_fence_before_sync();
+  cluster_sync_all();      // barriers of both CTAs initialised before any remote arrive / TMA credit
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp_idx == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs, own halves)
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+        const unsigned mt = fd_div((unsigned)tile, p.fd_nblocks);
+        const int nblk = tile - (int)(mt * p.fd_nblocks.div);
+        const Sub2 sc = sub2_coord(p, mt * 2 + rank);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(&a_empty[as], aph ^ 1);
+          if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * kH2HaloBytes);
+          tma_load_4d_2sm(a_base + as * kH2ASlot, &tm.a, leader_smem_addr(&a_full[as]), kc * 64, sc.w0 - 1, sc.h0 - 1, sc.n);
+          if (++as == kH2AStages) { as = 0; aph ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            if (leader) mbar_arrive_expect_tx(&b_full[bs], 2 * kH2BSlot);
+            tma_load_3d_2sm(b_base + bs * kH2BSlot, &tm.b, leader_smem_addr(&b_full[bs]), kc * 64, tap,
+                            nblk * kH2BlockN + rank * 128);
+            if (++bs == kH2BStages) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(256, kH2BlockN, kBf16 ? 1 : 0);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int tl = 0;
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++tl) {
+        const int acc = tl & 1;
+        mbar_wait(&tempty[acc], ((tl >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * kH2BlockN;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(a_base + as * kH2ASlot);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after_sync();
+            const uint64_t bdesc = umma_desc_kmajor<128>(smem_u32(b_base + bs * kH2BSlot));
+            const int r = tap / 3, s = tap - 3 * r;
+            uint64_t adesc = 0;
+            adesc |= static_cast<uint64_t>(((sa + (r * kH2HaloW + s) * 128) & 0x3FFFF) >> 4);
+            adesc |= static_cast<uint64_t>(1) << 16;
+            adesc |= static_cast<uint64_t>((kH2HaloW * 128) >> 4) << 32;
+            adesc |= static_cast<uint64_t>(1) << 46;
+            adesc |= static_cast<uint64_t>(2) << 61;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&b_empty[bs]);
+            if (++bs == kH2BStages) { bs = 0; bph ^= 1; }
+          }
+          umma_commit_2sm(&a_empty[as]);
+          if (++as == kH2AStages) { as = 0; aph ^= 1; }
+        }
+        umma_commit_2sm(&tfull[acc]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps per CTA, own 128 rows)
+    const int ew = warp_idx - 2;
+    const int q = warp_idx & 3;
+    const int half = ew >> 2;
+    uint8_t* wstage = staging + ew * 4096;
+    float* wvec = vecs + ew * kH2VecFloats;
+    int tl = 0, sbuf = 0;
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++tl) {
+      const int acc = tl & 1;
+      const unsigned mt = fd_div((unsigned)tile, p.fd_nblocks);
+      const int nblk = tile - (int)(mt * p.fd_nblocks.div);
+      const Sub2 sc = sub2_coord(p, mt * 2 + rank);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kH2BlockN;
+      const uint32_t tempty_leader = leader_smem_addr(&tempty[acc]);
+      mbar_wait(&tfull[acc], (tl >> 1) & 1);
+      tc_fence_after_sync();
+#define DYK_H2EPI(ACT) \
+  halo2_epilogue<kBf16, ACT>(tm, p, sc, nblk * kH2BlockN, t_row, wstage, wvec, sbuf, tempty_leader, q, lane, half)
+      switch (p.act) {
+        case DYK_ACT_LEAKY: DYK_H2EPI(DYK_ACT_LEAKY); break;
+        case DYK_ACT_MISH: DYK_H2EPI(DYK_ACT_MISH); break;
+        case DYK_ACT_RELU: DYK_H2EPI(DYK_ACT_RELU); break;
+        case DYK_ACT_RELU6: DYK_H2EPI(DYK_ACT_RELU6); break;
+        case DYK_ACT_HARDSWISH: DYK_H2EPI(DYK_ACT_HARDSWISH); break;
+        case DYK_ACT_HARDSIGMOID: DYK_H2EPI(DYK_ACT_HARDSIGMOID); break;
+        default: DYK_H2EPI(DYK_ACT_LINEAR); break;
+      }
+#undef DYK_H2EPI
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();      // the peer's barriers / smem stay valid until the leader's last multicast commit landed
+  if (warp_idx == 1) tmem_dealloc_2sm<512>(tmem_base);
+}
+
+template <bool kBf16>
+static int launch_halo2(const Halo2Tmaps& tm, const Halo2KArgs& ka, cudaStream_t stream) {
+  auto kern = conv3x3_halo2_kernel<kBf16>;
+  static bool configured = false;
+  if (!configured) {
+    DYK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kH2Total));
+    configured = true;
+  }
+  int clusters = num_sms() / 2;
+  if (ka.num_tiles < clusters) clusters = ka.num_tiles;
+  kern<<<2 * clusters, kH2Threads, kH2Total, stream>>>(tm, ka);
+  DYK_LAUNCH_OK("conv3x3_halo2_kernel");
+  return DYK_OK;
+}
+
+// Returns DYK_OK after launching, 1 when the layer is not eligible, < 0 on error.
+int conv3x3_halo2_try(const dyk_conv_params* p, cudaStream_t stream) {
+  static const bool off = getenv("DYK_HALO2") != nullptr && getenv("DYK_HALO2")[0] == '0';
+  if (off) return 1;
+  if (!(p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && !p->upsample2x && !p->out_f32 && !p->y_plane &&
+        p->out_h == 0 && p->out_w == 0))
+    return 1;
+  if (p->Cout_store < 256 || p->Cin < 64) return 1;
+  const int H = p->H, W = p->W, N = p->N;
+  const int subs_w = ceil_div(W, kH2SubW), subs_h = ceil_div(H, kH2SubH);
+  const long long num_subs = (long long)subs_w * subs_h * N;
+  if (num_subs >= (1ll << 30)) return 1;
+  const double eff = (double)W * H / ((double)subs_w * kH2SubW * subs_h * kH2SubH);
+  if (eff < 0.6) return 1;
+  const int n_blocks = ceil_div(p->Cout_store, kH2BlockN);
+
+  Halo2Tmaps tm;
+  Halo2KArgs ka;
+  memset(&tm, 0, sizeof(tm));
+  memset(&ka, 0, sizeof(ka));
+  int rc;
+  {
+    const long long xs = p->x_pix_stride * 2;
+    const cuuint64_t dims[4] = {(cuuint64_t)p->Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t str[3] = {(cuuint64_t)xs, (cuuint64_t)xs * W, (cuuint64_t)xs * W * H};
+    const cuuint32_t box[4] = {64, kH2HaloW, kH2HaloH, 1};
+    if ((rc = encode_map_generic(&tm.a, p->x, 4, dims, str, box, 128, "halo2 A"))) return rc;
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)p->Cin, 9, (cuuint64_t)p->Cout};
+    const cuuint64_t str[2] = {(cuuint64_t)p->Cin * 2, (cuuint64_t)p->Cin * 2 * 9};
+    const cuuint32_t box[3] = {64, 1, 128};
+    if ((rc = encode_map_generic(&tm.b, p->w, 3, dims, str, box, 128, "halo2 B"))) return rc;
+  }
+  {
+    const long long ys = p->y_pix_stride * 2;
+    const cuuint64_t dims[4] = {(cuuint64_t)p->Cout_store, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t str[3] = {(cuuint64_t)ys, (cuuint64_t)ys * W, (cuuint64_t)ys * W * H};
+    const cuuint32_t box[4] = {32, kH2SubW, 4, 1};
+    if ((rc = encode_map_generic(&tm.y, p->y, 4, dims, str, box, 64, "halo2 Y"))) return rc;
+  }
+  ka.H = H; ka.W = W; ka.N = N;
+  ka.num_subs = (int)num_subs;
+  ka.n_blocks = n_blocks;
+  ka.num_tiles = (int)(ceil_div64(num_subs, 2) * n_blocks);
+  ka.k_chunks = ceil_div(p->Cin, 64);
+  ka.Cout_store = p->Cout_store;
+  ka.act = p->act;
+  ka.fd_nblocks = make_fastdiv((unsigned)n_blocks);
+  ka.fd_subs_w = make_fastdiv((unsigned)subs_w);
+  ka.fd_subs_h = make_fastdiv((unsigned)subs_h);
+  ka.scale = p->scale; ka.bias = p->bias;
+  ka.res = p->res; ka.res_pix_stride = p->res_pix_stride;
+  return p->dtype == DYK_BF16 ? launch_halo2<true>(tm, ka, stream) : launch_halo2<false>(tm, ka, stream);
+}
+
+}  // namespace dyk

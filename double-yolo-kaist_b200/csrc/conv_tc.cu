@@ -473,6 +473,7 @@ static inline int encode_map(CUtensorMap* map, const void* base, int rank, const
 }
 
 int conv3x3_halo_try(const dyk_conv_params* p, cudaStream_t stream);   // conv_halo.cu
+int conv3x3_halo2_try(const dyk_conv_params* p, cudaStream_t stream);  // conv_halo2.cu (CTA pairs)
 
 // Spatial box (tw, th, tn) with tw*th*tn == 128 that wastes the fewest output pixels.
 static void pick_tile(int Wo, int Ho, int N, int* tw, int* th, int* tn) {
@@ -584,6 +585,8 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   // 3x3 stride-1 layers: halo kernel (every input pixel loaded once per tile instead of once per tap)
   static const bool no_halo = getenv("DYK_NO_HALO") != nullptr && getenv("DYK_NO_HALO")[0] == '1';
   if (!no_halo) {
+    const int h2 = conv3x3_halo2_try(p, stream);
+    if (h2 <= 0) return h2;
     const int hr = conv3x3_halo_try(p, stream);
     if (hr <= 0) return hr;   // launched (0) or failed (< 0); 1 = not eligible
   }

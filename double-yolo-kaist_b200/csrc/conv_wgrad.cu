@@ -203,7 +203,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradTmaps tm, const WgradKArgs p) {
 
 // grad_w[co][ci][r][s] (+)= sum over splits (fixed order) of part[split][tap][co][ci]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int taps, int Cout_pad, int Cin_pad, int Cout,
-                                    int Cin, float* __restrict__ grad, int accumulate) {
+                                    int Cin, float* __restrict__ grad, int accumulate) {   // Cin = real input channels
   const long long total = (long long)Cout * taps * Cin;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -336,14 +336,15 @@ extern "C" __attribute__((visibility("default"))) int64_t dyk_conv2d_wgrad_works
 
 extern "C" __attribute__((visibility("default"))) int dyk_conv2d_wgrad(
     const void* x, int64_t xs, const void* dz, int64_t dzs, float* grad, int32_t N, int32_t H, int32_t W, int32_t Cin,
-    int32_t Cout, int32_t Cout_real, int32_t k, int32_t stride, int32_t pad, int32_t accumulate, int32_t dtype,
-    void* workspace, int64_t workspace_bytes, void* stream_) {
+    int32_t Cin_real, int32_t Cout, int32_t Cout_real, int32_t k, int32_t stride, int32_t pad, int32_t accumulate,
+    int32_t dtype, void* workspace, int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DYK_REQUIRE(x && dz && grad && workspace, "dyk_conv2d_wgrad: null pointer");
   DYK_REQUIRE(dtype == DYK_F16 || dtype == DYK_BF16, "dyk_conv2d_wgrad: dtype %d", dtype);
   DYK_REQUIRE(stride == 1 || stride == 2, "dyk_conv2d_wgrad: stride %d", stride);
   DYK_REQUIRE(k >= 1 && k <= 7, "dyk_conv2d_wgrad: kernel %d", k);
-  DYK_REQUIRE(Cin > 0 && Cin % 8 == 0 && Cout > 0 && Cout % 8 == 0 && Cout_real > 0 && Cout_real <= Cout,
+  DYK_REQUIRE(Cin > 0 && Cin % 8 == 0 && Cout > 0 && Cout % 8 == 0 && Cout_real > 0 && Cout_real <= Cout &&
+                  Cin_real > 0 && Cin_real <= Cin,
               "dyk_conv2d_wgrad: Cin=%d Cout=%d must be positive multiples of 8", Cin, Cout);
   DYK_REQUIRE(xs % 8 == 0 && dzs % 8 == 0 && xs >= Cin && dzs >= Cout, "dyk_conv2d_wgrad: pixel strides");
   DYK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dz) & 15) == 0,
@@ -412,11 +413,11 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_wgrad(
   else rc = wp.BN == 64 ? DYK_WG(64, 1) : (wp.BN == 128 ? DYK_WG(128, 1) : DYK_WG(256, 1));
 #undef DYK_WG
   if (rc) return rc;
-  const long long total = (long long)Cout_real * ka.taps_total * Cin;
+  const long long total = (long long)Cout_real * ka.taps_total * Cin_real;
   long long g = (total + 255) / 256;
   if (g > num_sms() * 16) g = num_sms() * 16;
-  wgrad_reduce_kernel<<<(int)g, 256, 0, stream>>>(ka.part, splits, ka.taps_total, ka.Cout_pad, ka.Cin_pad, Cout_real, Cin, grad,
-                                                  accumulate);
+  wgrad_reduce_kernel<<<(int)g, 256, 0, stream>>>(ka.part, splits, ka.taps_total, ka.Cout_pad, ka.Cin_pad, Cout_real, Cin_real,
+                                                  grad, accumulate);
   DYK_LAUNCH_OK("wgrad_reduce_kernel");
   return DYK_OK;
 }

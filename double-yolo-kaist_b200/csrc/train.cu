@@ -377,76 +377,99 @@ __global__ void upsample_bwd_kernel(const uint8_t* __restrict__ dy, long long dy
 }
 
 // ------------------------------------------------------------------ SqueezeExcitation backward (layers.py:184-190)
-// One block: recomputes the tiny MLP per image, then
-//   dv2 = dgate * [ -3 < v2 < 3 ] / 6, dW2 += dv2 (x) hid, db2 += dv2, dhid = W2^T dv2, dv1 = dhid * [v1 > 0],
-//   dW1 += dv1 (x) mean, db1 += dv1, dmean = W1^T dv1;   dmean_out[n][c] = dmean / HW   (added to every pixel of dx).
-// Images are processed sequentially so the weight gradients are accumulated in a fixed order.
+// (1) one block per image: recompute the tiny MLP and back-propagate the gate gradient through it
+//       dv2 = dgate * [ -3 < v2 < 3 ] / 6, dhid = W2^T dv2, dv1 = dhid * [v1 > 0], dmean = W1^T dv1
+//     keeps mean / relu(hid) / dv2 / dv1 per image for (2);  dmean_out[n][c] = dmean / HW (added to every pixel of dx)
 __global__ void __launch_bounds__(1024)
 se_mlp_bwd_kernel(const float* __restrict__ pooled, int slabs, float inv_hw, const float* __restrict__ dgate_part,
-                  int dslabs, int N, int C, int Csq, const float* __restrict__ w1, const float* __restrict__ b1,
-                  const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ gw1,
-                  float* __restrict__ gb1, float* __restrict__ gw2, float* __restrict__ gb2, float* __restrict__ dmean_out) {
+                  int dslabs, int C, int Csq, const float* __restrict__ w1, const float* __restrict__ b1,
+                  const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ keep,
+                  float* __restrict__ dmean_out) {
   extern __shared__ float sm[];
   float* mean = sm;            // [C]
   float* dv2 = mean + C;       // [C]
-  float* hid = dv2 + C;        // [Csq]
+  float* hid = dv2 + C;        // [Csq]  pre-activation v1
   float* dv1 = hid + Csq;      // [Csq]
+  const int n = blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
-  for (int n = 0; n < N; ++n) {
-    for (int c = tid; c < C; c += nt) {
-      float s = 0.f;
-      for (int sl = 0; sl < slabs; ++sl) s += pooled[((long long)n * slabs + sl) * C + c];
-      mean[c] = s * inv_hw;
-    }
-    __syncthreads();
-    for (int j = warp; j < Csq; j += nwarps) {
-      float s = 0.f;
-      for (int c = lane; c < C; c += 32) s += w1[(long long)j * C + c] * mean[c];
+  for (int c = tid; c < C; c += nt) {
+    float s = 0.f;
+    for (int sl = 0; sl < slabs; ++sl) s += pooled[((long long)n * slabs + sl) * C + c];
+    mean[c] = s * inv_hw;
+  }
+  __syncthreads();
+  for (int j = warp; j < Csq; j += nwarps) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += w1[(long long)j * C + c] * mean[c];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) hid[j] = s + b1[j];          // pre-activation v1 (relu applied on use)
-    }
-    __syncthreads();
-    for (int c = warp; c < C; c += nwarps) {
-      float s = 0.f;
-      for (int j = lane; j < Csq; j += 32) s += w2[(long long)c * Csq + j] * fmaxf(hid[j], 0.f);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) hid[j] = s + b1[j];
+  }
+  __syncthreads();
+  for (int c = warp; c < C; c += nwarps) {
+    float s = 0.f;
+    for (int j = lane; j < Csq; j += 32) s += w2[(long long)c * Csq + j] * fmaxf(hid[j], 0.f);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) {
-        const float v2 = s + b2[c];
-        float dg = 0.f;
-        for (int sl = 0; sl < dslabs; ++sl) dg += dgate_part[(((long long)n * dslabs + sl) * 2) * C + c];
-        dv2[c] = (v2 > -3.f && v2 < 3.f) ? dg * (1.f / 6.f) : 0.f;
-      }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      const float v2 = s + b2[c];
+      float dg = 0.f;
+      for (int sl = 0; sl < dslabs; ++sl) dg += dgate_part[(((long long)n * dslabs + sl) * 2) * C + c];
+      dv2[c] = (v2 > -3.f && v2 < 3.f) ? dg * (1.f / 6.f) : 0.f;
     }
-    __syncthreads();
-    // dW2, db2
-    for (long long i = tid; i < (long long)C * Csq; i += nt) {
-      const int c = (int)(i / Csq), j = (int)(i - (long long)c * Csq);
-      gw2[i] += dv2[c] * fmaxf(hid[j], 0.f);
-    }
-    for (int c = tid; c < C; c += nt) gb2[c] += dv2[c];
-    // dhid -> dv1
-    for (int j = warp; j < Csq; j += nwarps) {
-      float s = 0.f;
-      for (int c = lane; c < C; c += 32) s += w2[(long long)c * Csq + j] * dv2[c];
+  }
+  __syncthreads();
+  for (int j = warp; j < Csq; j += nwarps) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += w2[(long long)c * Csq + j] * dv2[c];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) dv1[j] = hid[j] > 0.f ? s : 0.f;
-    }
-    __syncthreads();
-    for (long long i = tid; i < (long long)Csq * C; i += nt) {
-      const int j = (int)(i / C), c = (int)(i - (long long)j * C);
-      gw1[i] += dv1[j] * mean[c];
-    }
-    for (int j = tid; j < Csq; j += nt) gb1[j] += dv1[j];
-    for (int c = tid; c < C; c += nt) {
-      float s = 0.f;
-      for (int j = 0; j < Csq; ++j) s += w1[(long long)j * C + c] * dv1[j];
-      dmean_out[(long long)n * C + c] = s * inv_hw;
-    }
-    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) dv1[j] = hid[j] > 0.f ? s : 0.f;
+  }
+  __syncthreads();
+  float* kn = keep + (long long)n * (2 * C + 2 * Csq);     // [mean C | dv2 C | relu(hid) Csq | dv1 Csq]
+  for (int c = tid; c < C; c += nt) {
+    kn[c] = mean[c];
+    kn[C + c] = dv2[c];
+    float s = 0.f;
+    for (int j = 0; j < Csq; ++j) s += w1[(long long)j * C + c] * dv1[j];
+    dmean_out[(long long)n * C + c] = s * inv_hw;
+  }
+  for (int j = tid; j < Csq; j += nt) {
+    kn[2 * C + j] = fmaxf(hid[j], 0.f);
+    kn[2 * C + Csq + j] = dv1[j];
+  }
+}
+// (2) weight / bias gradients, one thread per element, images summed in a fixed order:
+//       gw2[c][j] += sum_n dv2[n][c] * relu(hid)[n][j]     gb2[c] += sum_n dv2[n][c]
+//       gw1[j][c] += sum_n dv1[n][j] * mean[n][c]          gb1[j] += sum_n dv1[n][j]
+__global__ void se_wgrad_kernel(const float* __restrict__ keep, int N, int C, int Csq, float* __restrict__ gw1,
+                                float* __restrict__ gb1, float* __restrict__ gw2, float* __restrict__ gb2) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long nw = (long long)C * Csq;
+  const int stride = 2 * C + 2 * Csq;
+  if (i < nw) {
+    const int c = (int)(i / Csq), j = (int)(i - (long long)c * Csq);       // gw2 [C][Csq]
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += keep[(long long)n * stride + C + c] * keep[(long long)n * stride + 2 * C + j];
+    gw2[i] += s;
+  } else if (i < 2 * nw) {
+    const long long e = i - nw;
+    const int j = (int)(e / C), c = (int)(e - (long long)j * C);           // gw1 [Csq][C]
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += keep[(long long)n * stride + 2 * C + Csq + j] * keep[(long long)n * stride + c];
+    gw1[e] += s;
+  } else if (i < 2 * nw + C) {
+    const int c = (int)(i - 2 * nw);
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += keep[(long long)n * stride + C + c];
+    gb2[c] += s;
+  } else if (i < 2 * nw + C + Csq) {
+    const int j = (int)(i - 2 * nw - C);
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += keep[(long long)n * stride + 2 * C + Csq + j];
+    gb1[j] += s;
   }
 }
 // dx (+)= dy * gate[n][c] + dmean[n][c]
@@ -495,6 +518,23 @@ __global__ void yolo_train_bwd_kernel(const float* __restrict__ dp, int N, int n
       v = dp[((((long long)n * na + a) * ny + y) * nx + x) * no + o];
     }
     store1<kBf16>(dz, i, v);
+  }
+}
+
+// ------------------------------------------------------------------ stem frames -> NHWC, 8 channels (zero padded)
+template <bool kBf16, typename TIn>
+__global__ void frames_to_nhwc8_kernel(const TIn* __restrict__ x, uint8_t* __restrict__ y, int N, int Cin, int HW) {
+  const long long total = (long long)N * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, p = i - n * HW;
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < Cin; ++c) {
+      const TIn v = x[(n * Cin + c) * HW + p];
+      if constexpr (sizeof(TIn) == 1) f[c] = (float)v / 255.0f;
+      else f[c] = (float)v;
+    }
+    *reinterpret_cast<uint4*>(y + i * 16) = pack8<kBf16>(f);
   }
 }
 
@@ -676,6 +716,7 @@ DYK_EXPORT int dyk_se_bwd(const void* x, int64_t xs, const void* dy, int64_t dys
   int dslabs = slabs_for(HW); if (dslabs > 32) dslabs = 32;
   float* dgate_part = workspace;                                   // [N][dslabs][2][C]
   float* dmean = workspace + (size_t)N * 32 * 2 * C;               // [N][C]
+  float* keep = dmean + (size_t)N * C;                             // [N][2C + 2Csq]  (<= 4 N C floats)
   const dim3 grid((C + 63) / 64, dslabs);
   for (int n = 0; n < N; ++n) {   // dgate[n][c] = sum_hw dy * x
     DYK_DISPATCH_DTYPE(dtype, (chan_reduce_kernel<kBf16, 3><<<grid, 256, 0, stream>>>(
@@ -683,9 +724,13 @@ DYK_EXPORT int dyk_se_bwd(const void* x, int64_t xs, const void* dy, int64_t dys
                                   nullptr, nullptr, nullptr, 0, dgate_part + (size_t)n * dslabs * 2 * C)));
     DYK_LAUNCH_OK("chan_reduce_kernel<3> (se)");
   }
-  se_mlp_bwd_kernel<<<1, 1024, (2 * C + 2 * Csq) * sizeof(float), stream>>>(pooled, fslabs, 1.f / (float)HW, dgate_part, dslabs, N,
-                                                                          C, Csq, w1, b1, w2, b2, gw1, gb1, gw2, gb2, dmean);
+  DYK_REQUIRE(Csq <= C, "dyk_se_bwd: Csq > C");
+  se_mlp_bwd_kernel<<<N, 1024, (2 * C + 2 * Csq) * sizeof(float), stream>>>(pooled, fslabs, 1.f / (float)HW, dgate_part, dslabs, C,
+                                                                          Csq, w1, b1, w2, b2, keep, dmean);
   DYK_LAUNCH_OK("se_mlp_bwd_kernel");
+  const long long nel = 2ll * C * Csq + C + Csq;
+  se_wgrad_kernel<<<(int)((nel + 255) / 256), 256, 0, stream>>>(keep, N, C, Csq, gw1, gb1, gw2, gb2);
+  DYK_LAUNCH_OK("se_wgrad_kernel");
   DYK_DISPATCH_DTYPE(dtype, (se_bwd_apply_kernel<kBf16><<<grid_for_t((long long)N * HW * (C / 8), 256), 256, 0, stream>>>(
                                 (const uint8_t*)dy, dys, gate, dmean, (uint8_t*)dx, dxs, N, HW, C, accumulate)));
   DYK_LAUNCH_OK("se_bwd_apply_kernel");
@@ -707,5 +752,19 @@ DYK_EXPORT int dyk_pack_weights_dgrad(const float* w_oihw, void* w_packed, int32
   DYK_DISPATCH_DTYPE(dtype, (pack_dgrad_kernel<kBf16><<<grid_for_t((long long)I * kh * kw * Opad, 256), 256, 0,
                                                       static_cast<cudaStream_t>(stream_)>>>(w_oihw, w_packed, O, I, kh, kw, Opad)));
   DYK_LAUNCH_OK("pack_dgrad_kernel");
+  return DYK_OK;
+}
+
+DYK_EXPORT int dyk_frames_to_nhwc8(const void* x_nchw, void* y, int32_t N, int32_t Cin, int32_t H, int32_t W, int32_t dtype,
+                                   int32_t x_kind, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYK_REQUIRE(x_nchw && y && N > 0 && Cin >= 1 && Cin <= 8 && H > 0 && W > 0 && DYK_AL16(y), "dyk_frames_to_nhwc8: bad arguments");
+  const int grid = grid_for_t((long long)N * H * W, 256);
+  if (x_kind == 1) {
+    DYK_DISPATCH_DTYPE(dtype, (frames_to_nhwc8_kernel<kBf16, uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)x_nchw, (uint8_t*)y, N, Cin, H * W)));
+  } else {
+    DYK_DISPATCH_DTYPE(dtype, (frames_to_nhwc8_kernel<kBf16, float><<<grid, 256, 0, stream>>>((const float*)x_nchw, (uint8_t*)y, N, Cin, H * W)));
+  }
+  DYK_LAUNCH_OK("frames_to_nhwc8_kernel");
   return DYK_OK;
 }

@@ -76,7 +76,8 @@ SIGNATURES = {
     "dyk_pack_weights_dgrad": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_conv2d_wgrad_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "dyk_conv2d_wgrad": (_i32, [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
-                                _vp, _i64, _vp]),
+                                _i32, _vp, _i64, _vp]),
+    "dyk_frames_to_nhwc8": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_conv2d_stem_wgrad": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                      _vp, _vp]),
     "dyk_pack_weights_ohwi": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),

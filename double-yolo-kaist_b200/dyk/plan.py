@@ -314,6 +314,49 @@ def liveness(ops_):
                 v.first = 0
 
 
+def assign_lanes(ops_):
+    """Two-lane schedule of the op list.  The dual-stream models are two independent backbones between fusion points
+    (SURVEY.md Appendix A), and at batch 16 the late layers have too few tiles to fill 148 SMs for whole waves; running
+    the visible and the LWIR branch on two CUDA streams lets the CTAs of one branch fill the tail of the other.
+
+    Greedy rule over the (already topologically ordered) ops, using transitive-ancestor bitsets: an op goes to the lane
+    whose most recent op it depends on; if it depends on both it joins on lane 0; if on neither it stays with its most
+    recent ancestor (short CSP side branches), and an op without any ancestor in the body (the first layer after the
+    LWIR stem) opens lane 1.  Returns (lane per op, producer-op index per Value id)."""
+    producer = {}
+    anc = []
+    lanes = []
+    last = [None, None]
+    for k, op in enumerate(ops_):
+        a = 0
+        for v in op.inputs():
+            p = producer.get(id(v))
+            if p is not None and lanes[p] >= 0:           # stems are sources: they run before the body
+                a |= (1 << p) | anc[p]
+        anc.append(a)
+        out = getattr(op, "out", None)
+        if out is not None:
+            producer[id(out)] = k
+        if isinstance(op, ConvOp) and op.flavor == "stem":
+            lanes.append(-1)                      # runs eagerly before the body, on the caller's stream
+            continue
+        d0 = last[0] is not None and (a >> last[0]) & 1
+        d1 = last[1] is not None and (a >> last[1]) & 1
+        if d0 and not d1:
+            lane = 0
+        elif d1 and not d0:
+            lane = 1
+        elif d0 and d1:
+            lane = 0
+        elif a:
+            lane = max(lanes[a.bit_length() - 1], 0)      # most recent ancestor's lane
+        else:
+            lane = 0 if last[0] is None else 1
+        lanes.append(lane)
+        last[lane] = k
+    return lanes, producer
+
+
 class WeightBank:
     """Packed weights / folded BN vectors per conv module, refreshed in place when parameters change."""
 
@@ -367,6 +410,10 @@ class Plan:
         mark_heads(self.ops)
         place_concats(self.ops)
         liveness(self.ops)
+        self.two_lanes = os.environ.get("DYK_LANES", "2") != "1"
+        self.lanes, self.producer = assign_lanes(self.ops)
+        if not self.two_lanes:
+            self.lanes = [min(l, 0) for l in self.lanes]
         self._allocate()
         self._bind(model, bank)
         self.graph = None
@@ -377,28 +424,40 @@ class Plan:
         reuse = os.environ.get("DYK_NO_REUSE", "0") != "1"
         roots = {}
         order = []
-        for op in self.ops:
+        for k, op in enumerate(self.ops):
             v = getattr(op, "out", None)
             if v is None:
                 continue
             root = v.place[0] if v.place else v
             if id(root) not in roots:
-                roots[id(root)] = [root, v.first, v.last]
+                roots[id(root)] = [root, v.first, v.last, set()]
                 order.append(id(root))
             r = roots[id(root)]
             r[1] = min(r[1], v.first)
             r[2] = max(r[2], v.last if v.last is not None else v.first)
+        # lanes that touch each root (writers and readers); stems (-1) run before the body on the caller's stream
+        def root_of(v):
+            return v.place[0] if v.place else v
+        for k, op in enumerate(self.ops):
+            lane = self.lanes[k]
+            for v in ([getattr(op, "out", None)] if getattr(op, "out", None) is not None else []) + list(op.inputs()):
+                r = roots.get(id(root_of(v)))
+                if r is not None and lane >= 0:
+                    r[3].add(lane)
         # a concat root's own first/last (its ConcatOp index and its consumers) were merged above through
         # the ConcatOp's `out`; members extend the interval backwards to their producers.
-        free = {}     # (shape, dtype) -> list of (tensor, free_after_op)
+        # Buffers are recycled only within one lane (stream order then guarantees that every access of the previous
+        # owner has completed); tensors touched by both lanes are never recycled.
+        free = {}     # (shape, dtype, lane) -> list of (tensor, free_after_op)
         self.bytes_allocated = 0
         for rid in sorted(order, key=lambda r: roots[r][1]):
-            root, first, last = roots[rid]
+            root, first, last, lanes = roots[rid]
             dt = torch.float32 if root.f32 else self.dtype
             shape = (self.B, root.H, root.W, root.C)
+            lane = next(iter(lanes)) if len(lanes) == 1 else None
             buf = None
-            if reuse:
-                lst = free.get((shape, dt), [])
+            if reuse and lane is not None:
+                lst = free.get((shape, dt, lane), [])
                 for j, (t, free_after) in enumerate(lst):
                     if free_after < first:
                         buf = t
@@ -407,7 +466,8 @@ class Plan:
             if buf is None:
                 buf = torch.empty(shape, dtype=dt, device=self.device)
                 self.bytes_allocated += buf.numel() * buf.element_size()
-            free.setdefault((shape, dt), []).append((buf, last))
+            if lane is not None:
+                free.setdefault((shape, dt, lane), []).append((buf, last))
             root.view = View(buf, 0, root.C)
         for op in self.ops:
             v = getattr(op, "out", None)
@@ -426,7 +486,50 @@ class Plan:
         self.p_outs = []
         row_off = 0
         dev = self.device
-        for op in self.ops:
+        self.side_stream = torch.cuda.Stream(device=dev) if (self.two_lanes and dev.type == "cuda" and 1 in self.lanes) else None
+        events = {}           # producer op index -> event recorded right after its last launch
+        synced = {0: -1, 1: -1}   # per consuming lane: newest producer index of the other lane already waited for
+        for k, op in enumerate(self.ops):
+            lane = self.lanes[k]
+            n_before = len(self.steps)
+            if lane >= 0 and self.side_stream is not None:
+                need = -1
+                for v in op.inputs():
+                    p = self.producer.get(id(v))
+                    if p is not None and self.lanes[p] >= 0 and self.lanes[p] != lane:
+                        need = max(need, p)
+                if need > synced[lane]:
+                    # wait for everything the other lane has launched up to (and including) op `need`
+                    ev = events.get(need)
+                    if ev is None:
+                        raise nat.NativeError("internal: cross-lane producer without an event")
+                    self.steps.append(_Sync("wait", ev, lane))
+                    synced[lane] = need
+            self._bind_op(op, k, bank, rows_total, row_off_ref := [row_off])
+            row_off = row_off_ref[0]
+            for st in self.steps[n_before:]:
+                if not isinstance(st, _Sync):
+                    st.lane = max(lane, 0)
+            if lane >= 0 and self.side_stream is not None and self._has_cross_lane_consumer(k):
+                ev = torch.cuda.Event()
+                events[k] = ev
+                self.steps.append(_Sync("record", ev, lane))
+        self.launches_per_forward = len(self.stem_steps) + sum(s.launches for s in self.steps)
+
+    def _has_cross_lane_consumer(self, k):
+        if not hasattr(self, "_cross"):
+            self._cross = set()
+            for j, op in enumerate(self.ops):
+                for v in op.inputs():
+                    p = self.producer.get(id(v))
+                    if p is not None and self.lanes[p] >= 0 and self.lanes[j] >= 0 and self.lanes[p] != self.lanes[j]:
+                        self._cross.add(p)
+        return k in self._cross
+
+    def _bind_op(self, op, k, bank, rows_total, row_off_ref):
+        dev = self.device
+        row_off = row_off_ref[0]
+        if True:
             if isinstance(op, ConvOp):
                 fl = op.flavor
                 e = bank.get(op.conv, op.bn, self.dtype, fl)
@@ -475,7 +578,7 @@ class Plan:
                 if m.bf_type not in ("yolov3", "yolov4"):
                     raise TypeError("bounding box predication error")
                 row_off += m.na * ny * nx
-        self.launches_per_forward = len(self.stem_steps) + sum(s.launches for s in self.steps)
+        row_off_ref[0] = row_off
 
     def _bind_add(self, op):
         m = op.module
@@ -507,8 +610,27 @@ class Plan:
             ops.nhwc_stem(x if which == 0 else y, e["w"], e["scale"], e["bias"], out, **kw)
 
     def run_body(self):
+        side = self.side_stream
+        if side is None:
+            for s in self.steps:
+                if not isinstance(s, _Sync):
+                    s()
+            return
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)                      # fork: the stems (caller's stream) precede both lanes
+        streams = (main, side)
         for s in self.steps:
-            s()
+            if isinstance(s, _Sync):
+                if s.kind == "record":
+                    s.event.record(streams[s.lane])
+                else:
+                    streams[s.lane].wait_event(s.event)
+            elif s.lane == 0:
+                s()
+            else:
+                with torch.cuda.stream(side):
+                    s()
+        main.wait_stream(side)                      # join
 
     def capture(self):
         g = torch.cuda.CUDAGraph()
@@ -525,8 +647,21 @@ class Plan:
             torch.cuda.synchronize()
 
 
+class _Sync:
+    """Cross-lane ordering marker in Plan.steps: record an event on a lane / make a lane wait for it."""
+    launches = 0
+    lane = 0
+
+    def __init__(self, kind, event, lane):
+        self.kind, self.event, self.lane = kind, event, lane
+
+    def __call__(self):
+        pass
+
+
 class _Call:
     launches = 1
+    lane = 0
 
     def __init__(self, fn, *args, **kw):
         self.fn, self.args, self.kw = fn, args, kw
@@ -539,6 +674,7 @@ class _Call:
 
 class _ConvStep:
     launches = 1
+    lane = 0
 
     def __init__(self, x, e, y, kw):
         self.x, self.e, self.y, self.kw = x, e, y, kw

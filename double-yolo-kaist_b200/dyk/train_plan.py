@@ -308,7 +308,7 @@ class TrainPlan:
                     o = self.offsets[id(conv.bias)]
                     T.chan_sum(dz, flat[o:o + HEAD_PAD], accumulate=True)
             if st["stem"]:
-                T.stem_wgrad(st["x_in"], dz, gw, k=k, stride=s, pad=p, accumulate=True)
+                T.stem_wgrad_tc(st["x_in"], dz, gw, k=k, stride=s, pad=p, accumulate=True)
                 return
             T.conv_wgrad(op.src.view, dz, gw, k=k, stride=s, pad=p, accumulate=True, cout_real=cout_real)
             gv, acc = gin

@@ -225,7 +225,7 @@ int dyk_upsample_nearest_bwd(const void* dy, int64_t dy_pix_stride, void* dx, in
                              int32_t W, int32_t C, int32_t s, int32_t accumulate, int32_t dtype, void* stream);
 /* SqueezeExcitation backward (layers.py:184-190): dx (+)= dy*gate + dmean/HW, and the fc1/fc2 weight / bias gradients
  * ACCUMULATED into gw1 [Csq][C], gb1 [Csq], gw2 [C][Csq], gb2 [C].  pooled / gate: as written by dyk_se_gate in the
- * forward.  workspace: (64 + 1) * N * C floats. */
+ * forward.  workspace: 72 * N * C floats. */
 int dyk_se_bwd(const void* x, int64_t x_pix_stride, const void* dy, int64_t dy_pix_stride, void* dx, int64_t dx_pix_stride,
                int32_t N, int32_t HW, int32_t C, const float* w1, const float* b1, const float* w2, const float* b2,
                int32_t Csq, const float* pooled, const float* gate, float* gw1, float* gb1, float* gw2, float* gb2,
@@ -245,9 +245,15 @@ int dyk_pack_weights_dgrad(const float* w_oihw, void* w_packed, int32_t O, int32
  * workspace: dyk_conv2d_wgrad_workspace_bytes(...) bytes. */
 int64_t dyk_conv2d_wgrad_workspace_bytes(int32_t Cin, int32_t Cout, int32_t k);
 int dyk_conv2d_wgrad(const void* x, int64_t x_pix_stride, const void* dz, int64_t dz_pix_stride, float* grad_w_oihw,
-                     int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t Cout_real, int32_t k,
-                     int32_t stride, int32_t pad, int32_t accumulate, int32_t dtype, void* workspace,
+                     int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cin_real, int32_t Cout, int32_t Cout_real,
+                     int32_t k, int32_t stride, int32_t pad, int32_t accumulate, int32_t dtype, void* workspace,
                      int64_t workspace_bytes, void* stream);
+/* Cin_real / Cout_real: channels of the OIHW gradient actually written when x / dz carry zero-padded channels
+ * (stem frames padded 3 -> 8, head logits padded 18 -> 32). */
+/* caller's NCHW fp32 / uint8 frames (as dyk_conv2d_stem_nchw_fwd, uint8 divided by 255) -> NHWC 16-bit with the channel
+ * dimension zero-padded to 8, the operand layout the tensor-core wgrad kernel needs for the stem convolutions. */
+int dyk_frames_to_nhwc8(const void* x_nchw, void* y, int32_t N, int32_t Cin, int32_t H, int32_t W, int32_t dtype,
+                        int32_t x_kind, void* stream);
 /* weight gradient of the stem convolutions (Cin <= 4, NCHW fp32 / uint8 frames as in dyk_conv2d_stem_nchw_fwd).
  * workspace: DYK_STEM_WGRAD_STRIPS * Cout * k*k*Cin floats. */
 #define DYK_STEM_WGRAD_STRIPS 592

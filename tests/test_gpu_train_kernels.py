@@ -173,6 +173,10 @@ def test_stem_wgrad(dtype):
         grad = torch.empty((Cout, 3, 3, 3), device=DEV)
         T.stem_wgrad(xin, dzv, grad, k=3, stride=1, pad=1, accumulate=False)
         _assert_close(grad.cpu(), want, 2e-4, "stem wgrad", floor=float(want.pow(2).mean().sqrt()))
+        # tensor-core variant: the frames are rounded to the 16-bit type first (one rounding per pixel, averaged out)
+        grad2 = torch.empty((Cout, 3, 3, 3), device=DEV)
+        T.stem_wgrad_tc(xin, dzv, grad2, k=3, stride=1, pad=1, accumulate=False)
+        _assert_close(grad2.cpu(), want, 4 * EPS16[dtype], "stem wgrad (tensor core)", floor=float(want.pow(2).mean().sqrt()))
 
 
 @pytest.mark.parametrize("dtype", DT)
