@@ -24,8 +24,9 @@ static inline int grid_for_t(long long work, int block) {
   if (g < 1) g = 1;
   return (int)g;
 }
+// enough slabs that (C / 64) x slabs blocks fill the GPU a few times over, capped by the workspace contract
 static inline int slabs_for(long long npix) {
-  long long s = npix / 1024;
+  long long s = npix / 512;
   if (s < 1) s = 1;
   if (s > kMaxSlabs) s = kMaxSlabs;
   return (int)s;
@@ -209,13 +210,21 @@ __global__ void bn_act_bwd_apply_kernel(const uint8_t* __restrict__ dy, long lon
     float g[8], fz[8], o[8];
     unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dy + pix * dys * 2) + c), g);
     unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(z + pix * zs * 2) + c), fz);
+    float ps[7][8];   // scale, shift, mean, invstd, cA, cB, cC of these 8 channels (two 16-byte loads each)
+    const float* srcs[7] = {scale, shift, mean, invstd, coef, coef + C, coef + 2 * C};
+#pragma unroll
+    for (int v = 0; v < 7; ++v) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(srcs[v] + c * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(srcs[v] + c * 8) + 1);
+      ps[v][0] = a.x; ps[v][1] = a.y; ps[v][2] = a.z; ps[v][3] = a.w;
+      ps[v][4] = b.x; ps[v][5] = b.y; ps[v][6] = b.z; ps[v][7] = b.w;
+    }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int ch = c * 8 + q;
-      const float zhat = fmaf(fz[q], __ldg(scale + ch), __ldg(shift + ch));
+      const float zhat = fmaf(fz[q], ps[0][q], ps[1][q]);
       const float gg = g[q] * act_grad(zhat, act);
-      const float xhat = (fz[q] - __ldg(mean + ch)) * __ldg(invstd + ch);
-      o[q] = __ldg(coef + ch) * gg + __ldg(coef + C + ch) + __ldg(coef + 2 * C + ch) * xhat;
+      const float xhat = (fz[q] - ps[2][q]) * ps[3][q];
+      o[q] = ps[4][q] * gg + ps[5][q] + ps[6][q] * xhat;
     }
     *(reinterpret_cast<uint4*>(dz + pix * dzs * 2) + c) = pack8<kBf16>(o);
   }

@@ -14,7 +14,7 @@ import os as _os
 LIB_PATH = Path(_os.environ.get("DYK_B200_LIB") or PKG_ROOT / "libdyk_b200.so")   # override: the -DDYK_CONV_PROFILE build
 
 DYK_F16, DYK_BF16 = 0, 1
-TRAIN_MAX_SLABS = 128        # DYK_TRAIN_MAX_SLABS
+TRAIN_MAX_SLABS = 1024       # DYK_TRAIN_MAX_SLABS
 STEM_WGRAD_STRIPS = 592      # DYK_STEM_WGRAD_STRIPS
 ACT_IDS = {
     "linear": 0, "leaky": 1, "mish": 2, "relu": 3, "relu6": 4, "hard-swish": 5, "hard-sigmoid": 6,

@@ -186,7 +186,7 @@ int dyk_nms_batched(const float* pred, int32_t B, int32_t rows, int32_t nc, floa
  * torch.autograd.Function.  All per-channel reductions use a fixed two-stage order (bit-reproducible, no float atomics).
  * `workspace` arguments are caller-provided device scratch, sizes in floats given per function.
  */
-#define DYK_TRAIN_MAX_SLABS 128
+#define DYK_TRAIN_MAX_SLABS 1024
 
 /* nn.BatchNorm2d in training mode (models.py:47), statistics part: per-channel batch mean / biased variance of the
  * 16-bit conv output z -> scale = gamma*invstd, shift = beta - mean*scale (so y = z*scale + shift), saved mean /

@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""BASELINE config 5: batched-NMS throughput sweep, bs = 1..128, 3 scales (20160 rows = 15360 + 3840 + 960),
+conf_thres 0.001, iou_thres 0.6, nc = 1, against the reference's algorithm run on the same GPU
+(build_utils/utils.py:387-464 restated with torchvision.ops.nms: per-image Python loop, boolean-mask compaction,
+xywh2xyxy, torchvision CUDA nms, [:100]).  Regimes: dense = every row survives the confidence filter
+(conf ~ 0.011, many near-ties), sparse = obj logit ~ N(-7, 2), 8 box clusters per frame.
+    python tools/nms_sweep.py [out.json]"""
+import json, sys
+from pathlib import Path
+REPO = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(REPO), str(REPO / "double-yolo-kaist_b200")]
+import torch
+import torchvision
+from build_utils.utils import nms_raw
+
+ROWS, CONF, IOU = 20160, 0.001, 0.6
+
+
+def make(B, regime, seed=2):
+    g = torch.Generator().manual_seed(seed)
+    p = torch.empty((B, ROWS, 6))
+    if regime == "dense":
+        p[..., 0] = torch.rand((B, ROWS), generator=g) * 640
+        p[..., 1] = torch.rand((B, ROWS), generator=g) * 512
+        p[..., 2:4] = 8 + torch.rand((B, ROWS, 2), generator=g) * 120
+        p[..., 4] = 0.0105 + torch.rand((B, ROWS), generator=g) * 0.0011
+        p[..., 5] = 0.98
+    else:
+        centres = torch.rand((B, 8, 2), generator=g) * torch.tensor([640.0, 512.0])
+        which = torch.randint(0, 8, (B, ROWS), generator=g)
+        xy = torch.gather(centres, 1, which.unsqueeze(-1).expand(-1, -1, 2)) + torch.randn((B, ROWS, 2), generator=g) * 4
+        p[..., :2] = xy
+        p[..., 2:4] = 30 + torch.rand((B, ROWS, 2), generator=g) * 60
+        p[..., 4] = torch.sigmoid(torch.randn((B, ROWS), generator=g) * 2 - 7)
+        p[..., 5] = 0.9 + torch.rand((B, ROWS), generator=g) * 0.1
+    return p.cuda()
+
+
+def reference_gpu(prediction):
+    out = [None] * prediction.shape[0]
+    for xi, x in enumerate(prediction):
+        x = x[x[:, 4] > CONF]
+        x = x[((x[:, 2:4] > 2) & (x[:, 2:4] < 4096)).all(1)]
+        if not x.shape[0]:
+            continue
+        x = x.clone()
+        x[..., 5:] *= x[..., 4:5]
+        box = torch.stack((x[:, 0] - x[:, 2] / 2, x[:, 1] - x[:, 3] / 2, x[:, 0] + x[:, 2] / 2, x[:, 1] + x[:, 3] / 2), 1)
+        conf, j = x[:, 5:].max(1)
+        x = torch.cat((box, conf.unsqueeze(1), j.float().unsqueeze(1)), 1)[conf > CONF]
+        if not x.shape[0]:
+            continue
+        boxes, scores = x[:, :4] + x[:, 5:6] * 4096, x[:, 4]
+        i = torchvision.ops.nms(boxes, scores, IOU)[:100]
+        out[xi] = x[i]
+    return out
+
+
+def timeit(fn, iters):
+    fn(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+rows = []
+for regime in ("dense", "sparse"):
+    for B in (1, 2, 4, 8, 16, 32, 64, 128):
+        pred = make(B, regime)
+        ms = timeit(lambda: nms_raw(pred, CONF, IOU, False, None, False, 100), 10 if B <= 16 else 4)
+        ms_ref = timeit(lambda: reference_gpu(pred), 3 if B <= 16 else 1)
+        out, cnt = nms_raw(pred, CONF, IOU, False, None, False, 100)
+        ref = reference_gpu(pred)
+        same = all((r is None and int(c) == 0) or (r is not None and int(c) == r.shape[0] and torch.equal(out[i, :int(c)], r))
+                   for i, (r, c) in enumerate(zip(ref, cnt.tolist())))
+        rows.append(dict(regime=regime, batch=B, native_ms=ms, reference_gpu_ms=ms_ref, native_fps=B / ms * 1e3,
+                         reference_fps=B / ms_ref * 1e3, speedup=ms_ref / ms, identical_to_torchvision_gpu=bool(same),
+                         hbm_floor_us=B * ROWS * 24 / 6.458e6))
+        print(f"{regime:6s} B={B:3d}: native {ms:8.3f} ms ({B / ms * 1e3:9.0f} frames/s)  reference-on-GPU {ms_ref:9.3f} ms "
+              f"({B / ms_ref * 1e3:8.0f} frames/s)  x{ms_ref / ms:6.1f}  identical={same}", flush=True)
+if len(sys.argv) > 1:
+    json.dump(rows, open(sys.argv[1], "w"), indent=1)
