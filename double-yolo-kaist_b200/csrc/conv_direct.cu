@@ -3,6 +3,7 @@
 //    layout/precision conversion costs no extra pass over the images;
 //  * depthwise convolutions (groups == C; models.py:41, build_utils/layers.py:224), which are HBM-bound.
 #include "common.h"
+#include <cstdlib>
 #include "act.cuh"
 #include "vec.cuh"
 
@@ -126,6 +127,10 @@ dwconv_kernel(const uint8_t* __restrict__ x, long long xs, const float* __restri
 
 }  // namespace dyk
 
+namespace dyk {
+int stem_tc_try(const void* x, const float* w, const float* scale, const float* bias, void* y, int64_t ys, int N, int H,
+                int W, int Cin, int Cout, int k, int stride, int pad, int act, int dtype, int x_kind, cudaStream_t stream);
+}
 using namespace dyk;
 
 extern "C" __attribute__((visibility("default"))) int dyk_conv2d_stem_nchw_fwd(const void* x, const float* w, const float* scale, const float* bias,
@@ -142,6 +147,13 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_stem_nchw_fwd(c
   DYK_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, "dyk_conv2d_stem_nchw_fwd: y must be 16-byte aligned");
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   DYK_REQUIRE(Ho > 0 && Wo > 0, "dyk_conv2d_stem_nchw_fwd: empty output");
+  // 3x3 / stride 1 / 3 -> 32 channels (every shipped cfg): tensor-core kernel (conv_stem_tc.cu); DYK_STEM_TC=0 keeps the
+  // CUDA-core kernel below, which also serves all other stem shapes
+  static const bool stem_tc_off = getenv("DYK_STEM_TC") != nullptr && getenv("DYK_STEM_TC")[0] == '0';
+  if (!stem_tc_off && (dtype == DYK_F16 || dtype == DYK_BF16)) {
+    const int rc = stem_tc_try(x, w, scale, bias, y, ys, N, H, W, Cin, Cout, k, stride, pad, act, dtype, x_kind, stream);
+    if (rc <= 0) return rc;
+  }
   const long long total = (long long)N * Ho * Wo;
   const int ct = (Cout % 32 == 0) ? 32 : 16;
   long long gx = (total + 127) / 128;

@@ -200,6 +200,11 @@ class DarknetRef:
         w = st[pconv + ".weight"]
         if self._round is not None and groups == 1 and w.shape[1] > 4:
             w = w.to(self._round).float()   # dense tensor-core convs hold their weights in the 16-bit dtype
+        elif (self._round is not None and groups == 1 and tuple(w.shape) == (32, 3, 3, 3) and stride == 1 and pad == 1):
+            # the 3 -> 32 stem runs on the tensor cores too (csrc/conv_stem_tc.cu): frames and weights are rounded to the
+            # 16-bit type when the im2col rows are built; other stem shapes stay on the fp32 CUDA-core kernel
+            w = w.to(self._round).float()
+            x = x.to(self._round).float()
         x = F.conv2d(x, w, st.get(pconv + ".bias"), stride, pad, 1, groups)
         if pbn is not None and training and self._round is not None:
             x = x.to(self._round).float()   # the training plan stores the pre-BN conv output in 16 bits
