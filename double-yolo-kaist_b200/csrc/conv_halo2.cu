@@ -26,6 +26,7 @@ namespace dyk {
 
 int encode_map_generic(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
                        const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle_bytes, const char* what);
+extern unsigned long long* g_conv_prof;   // conv_tc.cu (dyk_conv_set_profile)
 
 struct Halo2Tmaps {
   CUtensorMap a;  // input  (Cin, W, H, N), box {64, 10, 18, 1}
@@ -33,7 +34,16 @@ struct Halo2Tmaps {
   CUtensorMap y;  // output (Cout_store, W, H, N), box {32, 8, 4, 1}
 };
 
+#ifdef DYK_CONV_PROFILE
+constexpr bool kH2Prof = true;
+#else
+constexpr bool kH2Prof = false;
+#endif
+// counters (dyk_conv_set_profile): 0 MMA wait data, 1 MMA wait accumulator, 2 MMA issue-loop total, 3 epilogue (warp 2,
+// leader) wait accumulator, 4 epilogue total, 5 epilogue cycles inside tcgen05.ld + wait, 6 epilogue cycles waiting for a
+// staging buffer (TMA store read), 7 clusters
 struct Halo2KArgs {
+  unsigned long long* prof;
   int H, W, N;
   int num_subs;
   int n_blocks, num_tiles;      // pair tiles = ceil(num_subs / 2) * n_blocks, n-block fastest
@@ -79,26 +89,14 @@ __device__ __forceinline__ Sub2 sub2_coord(const Halo2KArgs& p, unsigned sub) {
 template <bool kBf16, int kAct>
 __device__ __forceinline__ void halo2_epilogue(const Halo2Tmaps& tm, const Halo2KArgs& p, const Sub2& sc, int n_base,
                                                uint32_t t_row, uint8_t* wstage, float* wvec, int& sbuf,
-                                               uint32_t tempty_leader, int q, int lane, int half) {
+                                               uint32_t tempty_leader, int q, int lane, int half, bool prof_warp,
+                                               long long& prof_ld, long long& prof_st, const uint4 (&rres_all)[4][4]) {
   constexpr int kCols = 32;
   constexpr int kChunks = kH2BlockN / kCols;   // 8; this warp handles chunks half, half+2, ...
   const int row = q * 32 + lane;
-  const int wo = sc.w0 + (row & 7), ho = sc.h0 + (row >> 3);
   const bool sub_ok = sc.n < p.N;
-  const bool pix_ok = sub_ok && (wo < p.W) && (ho < p.H);
-  const long long pix = (static_cast<long long>(sc.n) * p.H + ho) * p.W + wo;
   const bool has_res = p.res != nullptr;
 
-  uint4 rres[kCols / 8];
-  auto load_res = [&](int c) {
-    const int c0 = n_base + c * kCols;
-    const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (pix * p.res_pix_stride + c0) * 2;
-#pragma unroll
-    for (int j = 0; j < kCols / 8; ++j) {
-      rres[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (pix_ok && c0 + j * 8 < p.Cout_store) rres[j] = __ldg(reinterpret_cast<const uint4*>(rp) + j);
-    }
-  };
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < kH2BlockN / 32; ++j) {
@@ -108,8 +106,9 @@ __device__ __forceinline__ void halo2_epilogue(const Halo2Tmaps& tm, const Halo2
   }
   __syncwarp();
 
-#pragma unroll 1
-  for (int c = half; c < kChunks; c += 2) {
+#pragma unroll
+  for (int ci = 0; ci < kChunks / 2; ++ci) {
+    const int c = half + 2 * ci;
     const int cl = c * kCols;
     const int cg0 = n_base + cl;
     const bool beyond = cg0 >= p.Cout_store || !sub_ok;
@@ -120,18 +119,21 @@ __device__ __forceinline__ void halo2_epilogue(const Halo2Tmaps& tm, const Halo2
       if (lane == 0) mbar_arrive_cluster(tempty_leader);
       break;
     }
-    if (has_res) load_res(c);
     uint32_t v[kCols];
+    const long long t_ld0 = (kH2Prof && p.prof) ? clock64() : 0;
     tmem_ld_32x32b_x32(t_row + cl, v);
     tmem_ld_wait();
+    if (kH2Prof && p.prof && prof_warp) prof_ld += clock64() - t_ld0;
     if (last) {
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader);
     }
     uint8_t* sbase = wstage + sbuf * 2048;
+    const long long t_st0 = (kH2Prof && p.prof) ? clock64() : 0;
     if (lane == 0) tma_store_wait_read<1>();
     __syncwarp();
+    if (kH2Prof && p.prof && prof_warp) prof_st += clock64() - t_st0;
 #pragma unroll
     for (int ch = 0; ch < kCols / 8; ++ch) {
       float o[8];
@@ -148,7 +150,8 @@ __device__ __forceinline__ void halo2_epilogue(const Halo2Tmaps& tm, const Halo2
       o[6] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 6]), sc1.z, bi1.z));
       o[7] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 7]), sc1.w, bi1.w));
       if (has_res) {
-        const uint32_t rr[4] = {rres[ch].x, rres[ch].y, rres[ch].z, rres[ch].w};
+        const uint4 rv = rres_all[ci][ch];
+        const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 f = unpack2<kBf16>(rr[e]);
@@ -243,17 +246,21 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int tl = 0;
+      long long w_data = 0, w_acc = 0;
+      const long long t_begin = (kH2Prof && p.prof) ? clock64() : 0;
+#define H2WAIT(bar, ph, var) do { const long long t0 = (kH2Prof && p.prof) ? clock64() : 0; mbar_wait(bar, ph); \
+                                  if (kH2Prof && p.prof) var += clock64() - t0; } while (0)
       for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++tl) {
         const int acc = tl & 1;
-        mbar_wait(&tempty[acc], ((tl >> 1) & 1) ^ 1);
+        H2WAIT(&tempty[acc], ((tl >> 1) & 1) ^ 1, w_acc);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * kH2BlockN;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          mbar_wait(&a_full[as], aph);
+          H2WAIT(&a_full[as], aph, w_data);
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(a_base + as * kH2ASlot);
           for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&b_full[bs], bph);
+            H2WAIT(&b_full[bs], bph, w_data);
             tc_fence_after_sync();
             const uint64_t bdesc = umma_desc_kmajor<128>(smem_u32(b_base + bs * kH2BSlot));
             const int r = tap / 3, s = tap - 3 * r;
@@ -274,6 +281,12 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
         }
         umma_commit_2sm(&tfull[acc]);
       }
+#undef H2WAIT
+      if (kH2Prof && p.prof) {
+        atomicAdd(p.prof + 0, (unsigned long long)w_data);
+        atomicAdd(p.prof + 1, (unsigned long long)w_acc);
+        atomicAdd(p.prof + 2, (unsigned long long)(clock64() - t_begin));
+      }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps per CTA, own 128 rows)
@@ -283,6 +296,9 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
     uint8_t* wstage = staging + ew * 4096;
     float* wvec = vecs + ew * kH2VecFloats;
     int tl = 0, sbuf = 0;
+    const bool prof_warp = leader && ew == 0;
+    long long prof_ld = 0, prof_st = 0, prof_wait = 0;
+    const long long t_begin = (kH2Prof && p.prof) ? clock64() : 0;
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++tl) {
       const int acc = tl & 1;
       const unsigned mt = fd_div((unsigned)tile, p.fd_nblocks);
@@ -290,10 +306,34 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
       const Sub2 sc = sub2_coord(p, mt * 2 + rank);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kH2BlockN;
       const uint32_t tempty_leader = leader_smem_addr(&tempty[acc]);
-      mbar_wait(&tfull[acc], (tl >> 1) & 1);
+      // residual operand of this thread's row: all four column chunks are requested before the accumulator wait, so
+      // their global-memory latency hides behind the main loop instead of being paid inside the epilogue
+      uint4 rres_all[4][4];
+      if (p.res != nullptr) {
+        const int row = q * 32 + lane;
+        const int wo = sc.w0 + (row & 7), ho = sc.h0 + (row >> 3);
+        const bool pix_ok = sc.n < p.N && wo < p.W && ho < p.H;
+        const long long pix = (static_cast<long long>(sc.n) * p.H + ho) * p.W + wo;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c0 = nblk * kH2BlockN + (half + 2 * ci) * 32;
+          const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (pix * p.res_pix_stride + c0) * 2;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            rres_all[ci][j] = make_uint4(0u, 0u, 0u, 0u);
+            if (pix_ok && c0 + j * 8 < p.Cout_store) rres_all[ci][j] = __ldg(reinterpret_cast<const uint4*>(rp) + j);
+          }
+        }
+      }
+      {
+        const long long t0 = (kH2Prof && p.prof) ? clock64() : 0;
+        mbar_wait(&tfull[acc], (tl >> 1) & 1);
+        if (kH2Prof && p.prof) prof_wait += clock64() - t0;
+      }
       tc_fence_after_sync();
 #define DYK_H2EPI(ACT) \
-  halo2_epilogue<kBf16, ACT>(tm, p, sc, nblk * kH2BlockN, t_row, wstage, wvec, sbuf, tempty_leader, q, lane, half)
+  halo2_epilogue<kBf16, ACT>(tm, p, sc, nblk * kH2BlockN, t_row, wstage, wvec, sbuf, tempty_leader, q, lane, half, \
+                             prof_warp, prof_ld, prof_st, rres_all)
       switch (p.act) {
         case DYK_ACT_LEAKY: DYK_H2EPI(DYK_ACT_LEAKY); break;
         case DYK_ACT_MISH: DYK_H2EPI(DYK_ACT_MISH); break;
@@ -306,6 +346,13 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
 #undef DYK_H2EPI
     }
     if (lane == 0) tma_store_wait_all<0>();
+    if (kH2Prof && p.prof && prof_warp && lane == 0) {
+      atomicAdd(p.prof + 3, (unsigned long long)prof_wait);
+      atomicAdd(p.prof + 4, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(p.prof + 5, (unsigned long long)prof_ld);
+      atomicAdd(p.prof + 6, (unsigned long long)prof_st);
+      atomicAdd(p.prof + 7, 1ull);
+    }
   }
 
   tc_fence_before_sync();
@@ -381,6 +428,7 @@ int conv3x3_halo2_try(const dyk_conv_params* p, cudaStream_t stream) {
   ka.fd_subs_h = make_fastdiv((unsigned)subs_h);
   ka.scale = p->scale; ka.bias = p->bias;
   ka.res = p->res; ka.res_pix_stride = p->res_pix_stride;
+  ka.prof = g_conv_prof;
   return p->dtype == DYK_BF16 ? launch_halo2<true>(tm, ka, stream) : launch_halo2<false>(tm, ka, stream);
 }
 
