@@ -360,31 +360,42 @@ def main():
     host = [tuple(t.pin_memory() for t in synthetic_frames(B, seed=1000 * rank + i)) for i in range(ring)]
     resident = [(v.to(dev), l.to(dev)) for v, l in host]
 
+    # The evaluate.py-style loop through the repo's public pipeline helper (dyk/pipeline.py): forward of batch i+1
+    # overlaps the batched NMS of batch i (second stream) and, in the e2e leg, the upload of batch i+2 (copy stream).
+    # Every batch's forward, NMS (and H2D / D2H) lies inside the timed region; `flush` drains the last one.
+    from dyk.pipeline import EvalPipeline
+    pipe = EvalPipeline(model, CONF, IOU, multi_label=False)
+
     def step_resident(i):
         v, l = resident[i % ring]
-        with torch.no_grad():
-            io, _ = model(v, l) if dual else model(v)
-        return nms_raw(io, CONF, IOU, False, None, False, 100)
+        return pipe.submit(v, l if dual else None)
 
     def step_e2e(i):
-        v, l = host[i % ring]
-        v, l = v.to(dev, non_blocking=True), l.to(dev, non_blocking=True)
-        with torch.no_grad():
-            io, _ = model(v, l) if dual else model(v)
-        out, counts = nms_raw(io, CONF, IOU, False, None, False, 100)
-        return out.cpu(), counts.cpu()     # detections read back: the step's result
+        if i == 0 or pipe._staged is None:
+            pipe.stage(*host[i % ring]) if dual else pipe.stage(host[i % ring][0])
+        res = pipe.submit()
+        nxt = host[(i + 1) % ring]
+        pipe.stage(*nxt) if dual else pipe.stage(nxt[0])      # upload of the next batch overlaps this batch's compute
+        if res is not None:
+            out, counts = res
+            return out.cpu(), counts.cpu()     # detections of the previous batch read back: the step's result
+        return None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, d2h=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(i)
+        last = pipe.flush()                 # the last batch's NMS (and read-back) belongs to the timed region
+        if d2h and last is not None:
+            last[0].cpu(), last[1].cpu()
+        pipe._staged = None
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -396,7 +407,12 @@ def main():
 
     for i in range(args.warmup):
         step_resident(i)
+    pipe.flush()
+    for i in range(args.warmup):
         step_e2e(i)
+    pipe.flush()
+    pipe._staged = None
+    torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -404,7 +420,7 @@ def main():
     ms = timed(step_resident, args.steps)
     launches = nat.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, args.steps, d2h=True)
 
     value = world * B * args.steps / (ms / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
@@ -424,6 +440,8 @@ def main():
                        "parallelism": f"dp{world} (independent shards, no data-path collective)",
                        "l2": "per-step working set (231 MB weights + >5 GB activations) exceeds the 126 MB L2; "
                              "4 distinct input batches cycled; no explicit flush",
+                       "pipeline": "dyk.pipeline.EvalPipeline: NMS of batch i on a second stream overlaps the forward of "
+                                   "batch i+1; e2e also uploads batch i+1 on a copy stream; all inside the timed region",
                        "conf_thres": CONF, "iou_thres": IOU},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,

@@ -146,3 +146,36 @@ def test_weights_refresh_after_inplace_update(native_lib):
         io_ref, _ = ref.forward(st2, v)
     err = (io1.cpu()[..., :4] - io_ref[..., :4]).abs() / (io_ref[..., :4].abs() + 8.0)
     assert float(err.mean()) < 0.03
+
+
+def test_eval_pipeline_matches_direct_calls(native_lib):
+    """dyk.pipeline.EvalPipeline (upload / forward / NMS on three streams, results one call later) returns exactly what
+    forward + non_max_suppression return when called one after the other."""
+    from build_utils.utils import nms_raw
+    from dyk.pipeline import EvalPipeline
+    m, ref, st = _build("kaist_dyolov3_add_sl.cfg", 128, 160)
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.randint(0, 256, (2, 3, 128, 160), dtype=torch.uint8, generator=g).pin_memory(),
+                torch.randint(0, 256, (2, 3, 128, 160), dtype=torch.uint8, generator=g).pin_memory()) for _ in range(4)]
+    want = []
+    for v, l in batches:
+        with torch.no_grad():
+            io, _ = m(v.to(DEV), l.to(DEV))
+        out, cnt = nms_raw(io, 0.01, 0.6, False, None, False, 100)
+        want.append((out.cpu(), cnt.cpu()))
+    pipe = EvalPipeline(m, 0.01, 0.6, multi_label=False)
+    got = []
+    pipe.stage(*batches[0])
+    for i in range(len(batches)):
+        res = pipe.submit()
+        if i + 1 < len(batches):
+            pipe.stage(*batches[i + 1])
+        if res is not None:
+            got.append((res[0].cpu(), res[1].cpu()))
+    last = pipe.flush()
+    got.append((last[0].cpu(), last[1].cpu()))
+    assert len(got) == len(want)
+    for (a, ca), (b, cb) in zip(got, want):
+        assert torch.equal(ca, cb)
+        for i, k in enumerate(ca.tolist()):
+            assert torch.equal(a[i, :k], b[i, :k])
