@@ -1,5 +1,6 @@
 // Error reporting, device checks and driver entry points shared by all C-ABI functions.
 #include "common.h"
+#include <cstdlib>
 
 #include <cstring>
 
@@ -46,6 +47,11 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static const bool on = !(getenv("DYK_PDL") != nullptr && getenv("DYK_PDL")[0] == '0');
+  return on;
 }
 
 }  // namespace dyk

@@ -205,6 +205,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloTmaps tm, const HaloKArgs p) {
   static_assert(kTmemCols <= 512, "accumulators do not fit TMEM");
   static_assert(kSub == 1 || kSub == 2, "kSub");
 
+  griddep_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_base = smem;
@@ -237,6 +238,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloTmaps tm, const HaloKArgs p) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();   // PDL: everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp_idx == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -385,7 +387,7 @@ static int launch_halo(const HaloTmaps& tm, const HaloKArgs& ka, cudaStream_t st
     configured = true;
   }
   const int grid = ka.num_tiles < num_sms() ? ka.num_tiles : num_sms();
-  kern<<<grid, kHaloThreads, S::kTotal, stream>>>(tm, ka);
+  DYK_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kHaloThreads), S::kTotal, stream, tm, ka));
   DYK_LAUNCH_OK("conv3x3_halo_kernel");
   return DYK_OK;
 }

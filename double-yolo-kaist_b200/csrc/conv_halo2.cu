@@ -178,6 +178,7 @@ __device__ __forceinline__ void halo2_epilogue(const Halo2Tmaps& tm, const Halo2
 template <bool kBf16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kH2Threads, 1)
 conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) {
+  griddep_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_base = smem;
@@ -214,6 +215,7 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
   cluster_sync_all();      // barriers of both CTAs initialised before any remote arrive / TMA credit
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();   // PDL: everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp_idx == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs, own halves)
@@ -370,7 +372,7 @@ static int launch_halo2(const Halo2Tmaps& tm, const Halo2KArgs& ka, cudaStream_t
   }
   int clusters = num_sms() / 2;
   if (ka.num_tiles < clusters) clusters = ka.num_tiles;
-  kern<<<2 * clusters, kH2Threads, kH2Total, stream>>>(tm, ka);
+  DYK_CUDA_OK(launch_pdl(kern, dim3(2 * clusters), dim3(kH2Threads), (size_t)kH2Total, stream, tm, ka));
   DYK_LAUNCH_OK("conv3x3_halo2_kernel");
   return DYK_OK;
 }

@@ -265,6 +265,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
   static_assert(BLOCK_K == 64 || BLOCK_K == 32, "BLOCK_K");
 
+  griddep_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // align by *offset* (not by casting through an integer) so the compiler keeps the shared state space
   // and emits LDS/STS instead of generic LD/ST for the staging buffer and the scale/bias vectors
@@ -303,6 +304,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();   // PDL: everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp_idx == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -501,7 +503,7 @@ static int launch_conv(const ConvTmaps& tm, const ConvKArgs& ka, cudaStream_t st
     configured = true;
   }
   int grid = ka.num_tiles < num_sms() ? ka.num_tiles : num_sms();
-  kern<<<grid, kNumThreads, S::kTotal, stream>>>(tm, ka);
+  DYK_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kNumThreads), S::kTotal, stream, tm, ka));
   DYK_LAUNCH_OK("conv_tc_kernel");
   return DYK_OK;
 }

@@ -207,6 +207,16 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 }  // namespace dyk
 
+// ================================================================ programmatic dependent launch (PDL)
+namespace dyk {
+// Lets the next kernel in the stream (launched with cudaLaunchAttributeProgrammaticStreamSerialization) start its CTAs on
+// SMs this grid no longer occupies; they run their prologue and then block in griddep_wait().
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Blocks until every grid this launch depends on has completed and its memory is visible.  Must precede the first
+// global-memory access of data another kernel may have produced, and every global write.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+}  // namespace dyk
+
 // ================================================================ CTA-pair (cta_group::2) variants
 namespace dyk {
 
