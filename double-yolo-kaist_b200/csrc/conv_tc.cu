@@ -20,8 +20,8 @@
 //  * epilogue: tcgen05.ld -> scale/bias/activation (+ residual) in fp32 -> fp16/bf16 -> swizzled smem
 //              staging -> TMA store (clipped at tensor edges; 4 parity stores when upsampling).
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..9 = epilogue (TMEM lane quarter = warp_idx & 3; two warps per quarter split the columns).
+// Warp roles (320 or 576 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2.. = 8 or 16 epilogue warps (TMEM lane quarter = warp_idx & 3; kSplit warps per quarter split the columns).
 #include "common.h"
 #include <cstdlib>
 #include <cstring>
@@ -71,22 +71,26 @@ constexpr bool kProf = true;
 #else
 constexpr bool kProf = false;
 #endif
-constexpr int kNumEpiWarps = 8;
-constexpr int kNumEpiThreads = kNumEpiWarps * 32;
-constexpr int kNumThreads = 64 + kNumEpiThreads;   // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue
+// Epilogue warps: 4 TMEM lane quarters x kSplit column parts.  kSplit = 2 (8 warps, 168 registers each) for layers with a
+// long main loop; kSplit = 4 (16 warps, 112 registers) for short main loops (1x1 layers, small Cin), whose time is the
+// epilogue's instruction issue: more warps per scheduler hide the MUFU / TMEM-load latencies (Mish layers: ~1.5x).
+template <int kSplit> constexpr int epi_warps() { return 4 * kSplit; }
+template <int kSplit> constexpr int num_threads() { return 64 + 32 * epi_warps<kSplit>(); }
 constexpr int kBlockM = 128;
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, int kSplit>
 struct ConvSmem {
+  static constexpr int kNumEpiWarps = 4 * kSplit;
   // Every epilogue warp owns rows [32q, 32q+32) of the tile and every second chunk of kColsW output channels;
   // it stages and TMA-stores its own 32 x kColsW sub-boxes, so the epilogue needs no CTA-wide barrier.
-  static constexpr int kColsW = BLOCK_N >= 64 ? 32 : BLOCK_N / 2;     // channels per warp chunk (32 or 16)
+  static constexpr int kColsW = BLOCK_N >= 32 * kSplit ? 32 : BLOCK_N / kSplit;     // channels per warp chunk (32 or 16)
+  static_assert(kColsW == 32 || kColsW == 16, "chunk width");
   static constexpr int kChunkBytes = 32 * kColsW * 2;                   // one staged sub-box: 2 KB or 1 KB
   static constexpr int kABytes = kBlockM * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = kNumEpiWarps * 2 * 2048;        // 2 buffers per warp, 2 KB apart
-  static constexpr int kVecFloats = BLOCK_N;                            // per warp: scale + bias of its BLOCK_N/2 columns
+  static constexpr int kVecFloats = 2 * BLOCK_N / kSplit;               // per warp: scale + bias of its BLOCK_N/kSplit columns
   static constexpr int kVecBytes = kNumEpiWarps * kVecFloats * 4;
   static constexpr int kBarrierBytes = 1024;
   static constexpr int kBudget = 227 * 1024 - kBarrierBytes - kStagingBytes - kVecBytes - 1024 /*align*/;
@@ -118,11 +122,11 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvKArgs& p, int tile) {
 // column chunks half, half+2, ... of kColsW channels.  Per chunk: tcgen05.ld -> scale/bias/activation
 // (+ residual) in fp32 -> 16-bit -> swizzled warp-private staging -> one TMA store of the 32-row sub-box issued
 // by lane 0.  kAct is a compile-time activation so that only one code path is resident in the instruction cache.
-template <int BLOCK_N, int BLOCK_K, bool kBf16, int kAct>
+template <int BLOCK_N, int BLOCK_K, int kSplit, bool kBf16, int kAct>
 __device__ __forceinline__ void epilogue_tile(const ConvTmaps& tm, const ConvKArgs& p, const TileCoord& tc,
                                               uint32_t t_row, uint8_t* wstage, float* wvec, int& sbuf,
                                               uint64_t* tempty, int q, int lane, int half) {
-  using S = ConvSmem<BLOCK_N, BLOCK_K>;
+  using S = ConvSmem<BLOCK_N, BLOCK_K, kSplit>;
   constexpr int kCols = S::kColsW;                  // 32 or 16
   constexpr int kRowBytes = kCols * 2;              // 64 or 32 (== TMA store swizzle span)
   constexpr int kChunks = BLOCK_N / kCols;          // column chunks per tile
@@ -154,22 +158,22 @@ __device__ __forceinline__ void epilogue_tile(const ConvTmaps& tm, const ConvKAr
   __syncwarp();   // the previous tile's reads of wvec are complete
   if (lane < kCols) {
 #pragma unroll
-    for (int j = 0; j < kChunks / 2; ++j) {
-      const int col = n_base + (half + 2 * j) * kCols + lane;
+    for (int j = 0; j < kChunks / kSplit; ++j) {
+      const int col = n_base + (half + kSplit * j) * kCols + lane;
       wvec[j * kCols + lane] = p.scale ? __ldg(p.scale + col) : 1.f;
-      wvec[(kChunks / 2) * kCols + j * kCols + lane] = p.bias ? __ldg(p.bias + col) : 0.f;
+      wvec[(kChunks / kSplit) * kCols + j * kCols + lane] = p.bias ? __ldg(p.bias + col) : 0.f;
     }
   }
   __syncwarp();
   const float* wscale = wvec;
-  const float* wbias = wvec + (kChunks / 2) * kCols;
+  const float* wbias = wvec + (kChunks / kSplit) * kCols;
 
 #pragma unroll 1
-  for (int c = half; c < kChunks; c += 2) {
+  for (int c = half; c < kChunks; c += kSplit) {
     const int cl = c * kCols;                // first column of the chunk within the tile
     const int cg0 = n_base + cl;             // first output channel of the chunk
     const bool beyond = cg0 >= p.Cout_store; // warp-uniform: the chunk lies outside the tensor
-    const bool last = (c + 2 >= kChunks) || (cg0 + 2 * kCols >= p.Cout_store);
+    const bool last = (c + kSplit >= kChunks) || (cg0 + kSplit * kCols >= p.Cout_store);
     if (beyond) {   // nothing to read: release the accumulator stage and stop
       tc_fence_before_sync();
       __syncwarp();
@@ -177,16 +181,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvTmaps& tm, const ConvKAr
       break;
     }
     if (has_res) load_res(c);   // in flight while the accumulator chunk is read from TMEM
-    uint32_t v[kCols];
-    if constexpr (kCols == 32) tmem_ld_32x32b_x32(t_row + cl, v);
-    else tmem_ld_32x32b_x16(t_row + cl, v);
-    tmem_ld_wait();
-    if (last) {
-      // all TMEM reads of this warp for this accumulator stage are done -> hand it back to the MMA warp
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty);
-    }
     uint8_t* sbase = wstage + sbuf * 2048;
     if (!p.out_f32) {
       // staging[sbuf] may still be read by the store issued two chunks ago
@@ -194,45 +188,59 @@ __device__ __forceinline__ void epilogue_tile(const ConvTmaps& tm, const ConvKAr
       __syncwarp();
     }
     float* yo = reinterpret_cast<float*>(p.y_f32) + pix * p.y_pix_stride + cg0;   // only used when out_f32
-    // 8 channels at a time keeps the live register set small (v[] + 8 outputs + their scale/bias)
+    // 16 accumulator columns per TMEM load, 8 channels at a time: keeps the live register set small
+    // (16 + 8 outputs + their scale/bias), which the 16-warp variant (112 registers) needs
 #pragma unroll
-    for (int ch = 0; ch < kCols / 8; ++ch) {
-      float o[8];
-      const int vo = (c >> 1) * kCols + ch * 8;
-      const float4 sc0 = *reinterpret_cast<const float4*>(wscale + vo);
-      const float4 sc1 = *reinterpret_cast<const float4*>(wscale + vo + 4);
-      const float4 bi0 = *reinterpret_cast<const float4*>(wbias + vo);
-      const float4 bi1 = *reinterpret_cast<const float4*>(wbias + vo + 4);
-      o[0] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 0]), sc0.x, bi0.x));
-      o[1] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 1]), sc0.y, bi0.y));
-      o[2] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 2]), sc0.z, bi0.z));
-      o[3] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 3]), sc0.w, bi0.w));
-      o[4] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 4]), sc1.x, bi1.x));
-      o[5] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 5]), sc1.y, bi1.y));
-      o[6] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 6]), sc1.z, bi1.z));
-      o[7] = act_apply<kAct>(fmaf(__uint_as_float(v[ch * 8 + 7]), sc1.w, bi1.w));
-      if (has_res) {
-        const uint32_t rr[4] = {rres[ch].x, rres[ch].y, rres[ch].z, rres[ch].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = unpack2<kBf16>(rr[e]);
-          o[e * 2 + 0] += f.x;
-          o[e * 2 + 1] += f.y;
-        }
+    for (int hh = 0; hh < kCols / 16; ++hh) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(t_row + cl + hh * 16, v);
+      tmem_ld_wait();
+      if (last && hh == kCols / 16 - 1) {
+        // all TMEM reads of this warp for this accumulator stage are done -> hand it back to the MMA warp
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty);
       }
-      if (p.out_f32) {
-        if (pix_ok) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (cg0 + ch * 8 + j < p.Cout_store) yo[ch * 8 + j] = o[j];
+      for (int c8 = 0; c8 < 2; ++c8) {
+        const int ch = hh * 2 + c8;
+        float o[8];
+        const int vo = (c / kSplit) * kCols + ch * 8;
+        const float4 sc0 = *reinterpret_cast<const float4*>(wscale + vo);
+        const float4 sc1 = *reinterpret_cast<const float4*>(wscale + vo + 4);
+        const float4 bi0 = *reinterpret_cast<const float4*>(wbias + vo);
+        const float4 bi1 = *reinterpret_cast<const float4*>(wbias + vo + 4);
+        o[0] = act_apply<kAct>(fmaf(__uint_as_float(v[c8 * 8 + 0]), sc0.x, bi0.x));
+        o[1] = act_apply<kAct>(fmaf(__uint_as_float(v[c8 * 8 + 1]), sc0.y, bi0.y));
+        o[2] = act_apply<kAct>(fmaf(__uint_as_float(v[c8 * 8 + 2]), sc0.z, bi0.z));
+        o[3] = act_apply<kAct>(fmaf(__uint_as_float(v[c8 * 8 + 3]), sc0.w, bi0.w));
+        o[4] = act_apply<kAct>(fmaf(__uint_as_float(v[c8 * 8 + 4]), sc1.x, bi1.x));
+        o[5] = act_apply<kAct>(fmaf(__uint_as_float(v[c8 * 8 + 5]), sc1.y, bi1.y));
+        o[6] = act_apply<kAct>(fmaf(__uint_as_float(v[c8 * 8 + 6]), sc1.z, bi1.z));
+        o[7] = act_apply<kAct>(fmaf(__uint_as_float(v[c8 * 8 + 7]), sc1.w, bi1.w));
+        if (has_res) {
+          const uint32_t rr[4] = {rres[ch].x, rres[ch].y, rres[ch].z, rres[ch].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack2<kBf16>(rr[e]);
+            o[e * 2 + 0] += f.x;
+            o[e * 2 + 1] += f.y;
+          }
         }
-      } else {
-        int phys;
-        if constexpr (kRowBytes == 64) phys = ch ^ ((lane >> 1) & 3);
-        else phys = ch ^ ((lane >> 2) & 1);
-        const uint4 val = make_uint4(pack2<kBf16>(o[0], o[1]), pack2<kBf16>(o[2], o[3]), pack2<kBf16>(o[4], o[5]),
-                                     pack2<kBf16>(o[6], o[7]));
-        *reinterpret_cast<uint4*>(sbase + lane * kRowBytes + phys * 16) = val;
+        if (p.out_f32) {
+          if (pix_ok) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (cg0 + ch * 8 + j < p.Cout_store) yo[ch * 8 + j] = o[j];
+          }
+        } else {
+          int phys;
+          if constexpr (kRowBytes == 64) phys = ch ^ ((lane >> 1) & 3);
+          else phys = ch ^ ((lane >> 2) & 1);
+          const uint4 val = make_uint4(pack2<kBf16>(o[0], o[1]), pack2<kBf16>(o[2], o[3]), pack2<kBf16>(o[4], o[5]),
+                                       pack2<kBf16>(o[6], o[7]));
+          *reinterpret_cast<uint4*>(sbase + lane * kRowBytes + phys * 16) = val;
+        }
       }
     }
     if (p.out_f32) {
@@ -255,10 +263,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvTmaps& tm, const ConvKAr
   }
 }
 
-template <int BLOCK_N, int BLOCK_K, bool kBf16>
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <int BLOCK_N, int BLOCK_K, int kSplit, bool kBf16>
+__global__ void __launch_bounds__(num_threads<kSplit>(), 1)
 conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
-  using S = ConvSmem<BLOCK_N, BLOCK_K>;
+  using S = ConvSmem<BLOCK_N, BLOCK_K, kSplit>;
+  constexpr int kNumEpiWarps = S::kNumEpiWarps;
   constexpr int kSwz = BLOCK_K * 2;            // bytes per smem operand row == swizzle span (128 / 64)
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
@@ -398,7 +407,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
     // ------------------------------------------------------------------ epilogue (8 warps)
     const int ew = warp_idx - 2;
     const int q = warp_idx & 3;            // TMEM lane quarter this warp may access
-    const int half = ew >> 2;              // which half of each store group's columns
+    const int half = ew >> 2;              // which of the kSplit column parts this warp owns
     uint8_t* wstage = staging + ew * 4096;   // this warp's two 2 KB staging buffers
     float* wvec = vecs + ew * S::kVecFloats;
     int tl = 0;
@@ -419,7 +428,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
       }
       tc_fence_after_sync();
 #define DYK_EPI(ACT)                                                                                         \
-  epilogue_tile<BLOCK_N, BLOCK_K, kBf16, ACT>(tm, p, tc, t_row, wstage, wvec, sbuf, &tempty_bar[as], q, lane, half)
+  epilogue_tile<BLOCK_N, BLOCK_K, kSplit, kBf16, ACT>(tm, p, tc, t_row, wstage, wvec, sbuf, &tempty_bar[as], q, lane, half)
       switch (p.act) {
         case DYK_ACT_LEAKY: DYK_EPI(DYK_ACT_LEAKY); break;
         case DYK_ACT_MISH: DYK_EPI(DYK_ACT_MISH); break;
@@ -493,28 +502,35 @@ static void pick_tile(int Wo, int Ho, int N, int* tw, int* th, int* tn) {
   }
 }
 
-template <int BLOCK_N, int BLOCK_K, bool kBf16>
+template <int BLOCK_N, int BLOCK_K, int kSplit, bool kBf16>
 static int launch_conv(const ConvTmaps& tm, const ConvKArgs& ka, cudaStream_t stream) {
-  using S = ConvSmem<BLOCK_N, BLOCK_K>;
-  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, kBf16>;
+  using S = ConvSmem<BLOCK_N, BLOCK_K, kSplit>;
+  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, kSplit, kBf16>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     DYK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
   int grid = ka.num_tiles < num_sms() ? ka.num_tiles : num_sms();
-  DYK_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kNumThreads), S::kTotal, stream, tm, ka));
+  DYK_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(num_threads<kSplit>()), S::kTotal, stream, tm, ka));
   DYK_LAUNCH_OK("conv_tc_kernel");
   return DYK_OK;
 }
 
 template <int BLOCK_K, bool kBf16>
-static int dispatch_n(int block_n, const ConvTmaps& tm, const ConvKArgs& ka, cudaStream_t stream) {
+static int dispatch_n(int block_n, int split, const ConvTmaps& tm, const ConvKArgs& ka, cudaStream_t stream) {
+  if (split == 4) {
+    switch (block_n) {
+      case 64: return launch_conv<64, BLOCK_K, 4, kBf16>(tm, ka, stream);
+      case 128: return launch_conv<128, BLOCK_K, 4, kBf16>(tm, ka, stream);
+      case 256: return launch_conv<256, BLOCK_K, 4, kBf16>(tm, ka, stream);
+    }
+  }
   switch (block_n) {
-    case 32: return launch_conv<32, BLOCK_K, kBf16>(tm, ka, stream);
-    case 64: return launch_conv<64, BLOCK_K, kBf16>(tm, ka, stream);
-    case 128: return launch_conv<128, BLOCK_K, kBf16>(tm, ka, stream);
-    case 256: return launch_conv<256, BLOCK_K, kBf16>(tm, ka, stream);
+    case 32: return launch_conv<32, BLOCK_K, 2, kBf16>(tm, ka, stream);
+    case 64: return launch_conv<64, BLOCK_K, 2, kBf16>(tm, ka, stream);
+    case 128: return launch_conv<128, BLOCK_K, 2, kBf16>(tm, ka, stream);
+    case 256: return launch_conv<256, BLOCK_K, 2, kBf16>(tm, ka, stream);
   }
   return fail(DYK_EINVAL, "bad BLOCK_N %d", block_n);
 }
@@ -637,6 +653,11 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   const int taps = p->kh * p->kw;
   const long long m_tiles = (long long)ceil_div(gW, tw) * ceil_div(gH, th) * ceil_div(gN, tn);
   const int BN = pick_block_n(p->Cout_store, m_tiles, taps * ceil_div(p->Cin, BK), BK);
+  // 16 epilogue warps when the tile time is the epilogue's: short main loop (<= 16 k-blocks) and an activation that costs
+  // MUFU issue slots (Mish).  Measured: dyolov4 (Mish) 8.33 -> 8.09 ms, dyolov3 (leaky) 5.65 -> 5.75 ms, hence the act test.
+  static const int force_split = getenv("DYK_EPI_SPLIT") ? atoi(getenv("DYK_EPI_SPLIT")) : 0;
+  int split = (taps * ceil_div(p->Cin, BK) <= 16 && BN >= 64 && !p->out_f32 && p->act == DYK_ACT_MISH) ? 4 : 2;
+  if (force_split == 2 || (force_split == 4 && BN >= 64)) split = force_split;
   {
     const cuuint64_t dims[3] = {(cuuint64_t)p->Cin, (cuuint64_t)taps, (cuuint64_t)p->Cout};
     const cuuint64_t str[2] = {(cuuint64_t)p->Cin * 2, (cuuint64_t)p->Cin * 2 * taps};
@@ -645,7 +666,7 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   }
   if (!p->out_f32) {
     // every epilogue warp stores 32-row x storeC-channel sub-boxes of the tile (see epilogue_tile)
-    const int storeC = BN >= 64 ? 32 : BN / 2;
+    const int storeC = BN >= 32 * split ? 32 : BN / split;
     const int sw = tw < 32 ? tw : 32;
     const int sh = th < 32 / sw ? th : 32 / sw;
     const int sn = 32 / (sw * sh);
@@ -694,6 +715,6 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   ka.prof = g_conv_prof;
 
   const bool bf = p->dtype == DYK_BF16;
-  if (BK == 64) return bf ? dispatch_n<64, true>(BN, tm, ka, stream) : dispatch_n<64, false>(BN, tm, ka, stream);
-  return bf ? dispatch_n<32, true>(BN, tm, ka, stream) : dispatch_n<32, false>(BN, tm, ka, stream);
+  if (BK == 64) return bf ? dispatch_n<64, true>(BN, split, tm, ka, stream) : dispatch_n<64, false>(BN, split, tm, ka, stream);
+  return bf ? dispatch_n<32, true>(BN, split, tm, ka, stream) : dispatch_n<32, false>(BN, split, tm, ka, stream);
 }

@@ -721,7 +721,7 @@ DYK_EXPORT int dyk_se_bwd(const void* x, int64_t xs, const void* dy, int64_t dys
   DYK_REQUIRE(C > 0 && C % 8 == 0 && xs % 8 == 0 && dys % 8 == 0 && dxs % 8 == 0 && Csq > 0 && N > 0 && HW > 0, "dyk_se_bwd: bad shape");
   DYK_REQUIRE((size_t)(2 * C + 2 * Csq) * 4 <= 48 * 1024, "dyk_se_bwd: C + Csq too large");
   // forward used slabs = clamp(HW/256, 1, 32) per image for `pooled` (dyk_se_gate)
-  int fslabs = HW / 256; if (fslabs < 1) fslabs = 1; if (fslabs > 32) fslabs = 32;
+  int fslabs = HW / 256; if (fslabs < 1) fslabs = 1; if (fslabs > 31) fslabs = 31;
   int dslabs = slabs_for(HW); if (dslabs > 32) dslabs = 32;
   float* dgate_part = workspace;                                   // [N][dslabs][2][C]
   float* dmean = workspace + (size_t)N * 32 * 2 * C;               // [N][C]

@@ -43,7 +43,7 @@ for s, ms in zip(plan.steps, acc):
                     + (opix * cout if s.kw["res"] is not None else 0))
         rows.append(dict(kind="conv", cin=s.x.C, cout=cout, k=k, stride=s.kw["stride"], H=s.x.H, W=s.x.W, res=s.kw["res"] is not None,
                          up=s.kw["upsample2x"], ms=ms, tflops=fl / ms / 1e9, gbs=by / ms / 1e6, gflop=fl / 1e9))
-    else:
+    elif hasattr(s, "fn"):
         rows.append(dict(kind=getattr(s.fn, "__name__", "?"), ms=ms))
 Path(out).parent.mkdir(exist_ok=True)
 json.dump(rows, open(out, "w"), indent=0)

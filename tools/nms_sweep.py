@@ -12,6 +12,7 @@ sys.path[:0] = [str(REPO), str(REPO / "double-yolo-kaist_b200")]
 import torch
 import torchvision
 from build_utils.utils import nms_raw
+from tools.nms_sweep_ref import reference_gpu_nms
 
 ROWS, CONF, IOU = 20160, 0.001, 0.6
 
@@ -37,23 +38,7 @@ def make(B, regime, seed=2):
 
 
 def reference_gpu(prediction):
-    out = [None] * prediction.shape[0]
-    for xi, x in enumerate(prediction):
-        x = x[x[:, 4] > CONF]
-        x = x[((x[:, 2:4] > 2) & (x[:, 2:4] < 4096)).all(1)]
-        if not x.shape[0]:
-            continue
-        x = x.clone()
-        x[..., 5:] *= x[..., 4:5]
-        box = torch.stack((x[:, 0] - x[:, 2] / 2, x[:, 1] - x[:, 3] / 2, x[:, 0] + x[:, 2] / 2, x[:, 1] + x[:, 3] / 2), 1)
-        conf, j = x[:, 5:].max(1)
-        x = torch.cat((box, conf.unsqueeze(1), j.float().unsqueeze(1)), 1)[conf > CONF]
-        if not x.shape[0]:
-            continue
-        boxes, scores = x[:, :4] + x[:, 5:6] * 4096, x[:, 4]
-        i = torchvision.ops.nms(boxes, scores, IOU)[:100]
-        out[xi] = x[i]
-    return out
+    return reference_gpu_nms(prediction, CONF, IOU)
 
 
 def timeit(fn, iters):
