@@ -16,6 +16,7 @@ LIB_PATH = Path(_os.environ.get("DYK_B200_LIB") or PKG_ROOT / "libdyk_b200.so") 
 DYK_F16, DYK_BF16 = 0, 1
 TRAIN_MAX_SLABS = 1024       # DYK_TRAIN_MAX_SLABS
 STEM_WGRAD_STRIPS = 592      # DYK_STEM_WGRAD_STRIPS
+DW_WGRAD_SLABS = 256         # DYK_DW_WGRAD_SLABS
 ACT_IDS = {
     "linear": 0, "leaky": 1, "mish": 2, "relu": 3, "relu6": 4, "hard-swish": 5, "hard-sigmoid": 6,
 }
@@ -80,6 +81,8 @@ SIGNATURES = {
     "dyk_frames_to_nhwc8": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_conv2d_stem_wgrad": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                      _vp, _vp]),
+    "dyk_dwconv2d_dgrad": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dyk_dwconv2d_wgrad": (_i32, [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "dyk_pack_weights_ohwi": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_nchw_f32_to_nhwc": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_nhwc_to_nchw_f32": (_i32, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -137,12 +137,16 @@ def conv_dgrad(dz: View, w_dgrad: torch.Tensor, dx: View, *, k: int, stride: int
     target = dx
     if accumulate:
         target = ops.new_view(dx.N, dx.H, dx.W, dx.C, dx.buf.dtype, dx.buf.device)
+    if k < 2:
+        # 1x1 stride 2 (MobileNetV3 expand convs carry the stride): only one parity plane of dx receives a gradient;
+        # the others are cleared (a memset of the gradient buffer, not arithmetic)
+        target.buf[..., target.c_off:target.c_off + target.C].zero_()
     for ph in range(2):
         rows = [r for r in range(k) if (r - pad) % 2 == ph]          # taps that reach input rows of parity ph
         for pw in range(2):
             cols = [s for s in range(k) if (s - pad) % 2 == pw]
             if not rows or not cols:
-                raise nat.NativeError("conv_dgrad: kernel too small for stride 2")
+                continue
             # dx[2i+ph] = sum_r dz[i + (ph + pad - r)/2] * W[r]; as a correlation over dz with offsets t = (ph+pad-r)/2 >= ...
             offs_h = sorted({(ph + pad - r) // 2 for r in rows})
             offs_w = sorted({(pw + pad - s) // 2 for s in cols})
@@ -186,6 +190,24 @@ def conv_wgrad(x: View, dz: View, grad_w: torch.Tensor, *, k: int, stride: int, 
     ws = scratch(need, x.buf.device, "w")
     nat.call("dyk_conv2d_wgrad", x.ptr, x.stride, dz.ptr, dz.stride, _p(grad_w), x.N, x.H, x.W, x.C, cin_real or x.C, dz.C,
              cout_real or dz.C, k, stride, pad, int(accumulate), x.dt, C.c_void_p(ws.data_ptr()), ws.numel(), _stream())
+    nat.count_launches(2)
+
+
+def dw_weight(conv) -> torch.Tensor:
+    """state_dict [C][1][k][k] -> the depthwise kernels' fp32 [k][k][C] (layout only)."""
+    Cc, _, k, _ = conv.weight.shape
+    return conv.weight.detach().float().reshape(Cc, k, k).permute(1, 2, 0).contiguous()
+
+
+def dwconv_dgrad(dz: View, w_kkc: torch.Tensor, dx: View, *, k: int, stride: int, pad: int, accumulate: bool) -> None:
+    nat.call("dyk_dwconv2d_dgrad", dz.ptr, dz.stride, _p(w_kkc), dx.ptr, dx.stride, dx.N, dx.H, dx.W, dx.C, k, stride, pad,
+             int(accumulate), dx.dt, _stream())
+    nat.count_launches()
+
+
+def dwconv_wgrad(x: View, dz: View, grad_w: torch.Tensor, *, k: int, stride: int, pad: int, accumulate: bool) -> None:
+    nat.call("dyk_dwconv2d_wgrad", x.ptr, x.stride, dz.ptr, dz.stride, _p(grad_w), x.N, x.H, x.W, x.C, k, stride, pad,
+             int(accumulate), x.dt, _ws_floats(nat.DW_WGRAD_SLABS * k * k * x.C, x.buf.device, "d"), _stream())
     nat.count_launches(2)
 
 

@@ -16,8 +16,10 @@ accumulate" is resolved when the plan is built):
   weights, accumulating through the residual operand) ; axpby routing for shortcut / route ; pool / upsample / SE backward.
 Parameter gradients are produced in one flat fp32 buffer (one view per parameter), zeroed once per backward.
 
-Limits (raise NativeError, never fall back): depthwise / grouped convolutions (MobileNet cfgs), Inception blocks and
-BatchNorm2d(momentum=None) have no training kernels yet; a second forward before the backward of the first overwrites the
+Depthwise convolutions (MobileNet backbones, DepthwiseSeparableConv2d) use the CUDA-core kernels of dwconv_bwd.cu; Inception
+blocks are their constituent convolutions, a 3x3 max-pool and a concat.
+Limits (raise NativeError, never fall back): grouped convolutions that are not depthwise, BatchNorm2d(momentum=None),
+shortcuts with more than two operands or unequal widths; a second forward before the backward of the first overwrites the
 saved activations (the reference never does that).
 """
 from __future__ import annotations
@@ -46,10 +48,8 @@ class TrainPlan:
         self.model, self.B, self.dtype, self.device, self.dual = model, B, dtype, device, dual
         self.ops, self.layer_vals, self.img0, self.img1 = P.build_ops(model, H, W, dual)
         for op in self.ops:
-            if isinstance(op, P.ConvOp) and op.flavor == "dw":
-                raise nat.NativeError(f"layer {op.layer}: depthwise convolutions have no training kernels yet")
-            if isinstance(op, P.ConvOp) and op.tag:
-                raise nat.NativeError(f"layer {op.layer}: Inception / separable blocks have no training kernels yet")
+            if isinstance(op, P.ConvOp):
+                op.flavor          # grouped (non-depthwise) convolutions raise NativeError here
         P.mark_heads(self.ops)
         P.place_concats(self.ops)
         self.params = list(model.parameters())
@@ -96,7 +96,9 @@ class TrainPlan:
             if isinstance(op, P.ConvOp):
                 conv, bn = op.conv, op.bn
                 k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
-                st = dict(op=op, conv=conv, bn=bn, k=k, s=s, p=p, stem=op.flavor == "stem")
+                st = dict(op=op, conv=conv, bn=bn, k=k, s=s, p=p, stem=op.flavor == "stem", dw=op.flavor == "dw")
+                if st["dw"] and bn is None:
+                    raise nat.NativeError(f"layer {op.layer}: a depthwise convolution without BatchNorm has no training kernels")
                 if bn is not None:
                     if bn.momentum is None:
                         raise nat.NativeError("BatchNorm2d(momentum=None) is not supported by the training kernels")
@@ -150,6 +152,9 @@ class TrainPlan:
                 st["x_in"] = src
                 w = conv.weight.detach().float().permute(0, 2, 3, 1).contiguous()
                 ops.nhwc_stem(src, w, None, None, st["z"], k=k, stride=s, pad=p, act="linear")
+            elif st["dw"]:
+                st["w"] = T.dw_weight(conv)
+                ops.nhwc_dwconv(op.src.view, st["w"], None, None, st["z"], k=k, stride=s, pad=p, act="linear")
             else:
                 st["w"] = ops.pack_conv_weight(conv.weight, self.dtype)
                 if bn is None:
@@ -310,8 +315,12 @@ class TrainPlan:
             if st["stem"]:
                 T.stem_wgrad_tc(st["x_in"], dz, gw, k=k, stride=s, pad=p, accumulate=True)
                 return
-            T.conv_wgrad(op.src.view, dz, gw, k=k, stride=s, pad=p, accumulate=True, cout_real=cout_real)
             gv, acc = gin
+            if st["dw"]:
+                T.dwconv_wgrad(op.src.view, dz, gw, k=k, stride=s, pad=p, accumulate=True)
+                T.dwconv_dgrad(dz, st["w"], gv, k=k, stride=s, pad=p, accumulate=acc)
+                return
+            T.conv_wgrad(op.src.view, dz, gw, k=k, stride=s, pad=p, accumulate=True, cout_real=cout_real)
             wd = T.pack_dgrad_weight(conv.weight, self.dtype, opad=dz.C)
             T.conv_dgrad(dz, wd, gv, k=k, stride=s, pad=p, accumulate=acc)
         self.bwd.append(run)

@@ -261,6 +261,19 @@ int dyk_conv2d_stem_wgrad(const void* x_nchw, const void* dz, int64_t dz_pix_str
                           int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride, int32_t pad,
                           int32_t accumulate, int32_t dtype, int32_t x_kind, float* workspace, void* stream);
 
+/* ---- depthwise convolution backward (nn.Conv2d(groups = C): models.py:41, build_utils/layers.py:224; autograd in the
+ * reference).  w and the forward layout are as in dyk_dwconv2d_fwd (fp32 [k][k][C]); H, W are the INPUT sizes.
+ * dgrad: dx (+)= sum over taps of dz[(h + pad - r)/stride, (w + pad - s)/stride] * w[r][s]   (gather form, no atomics).
+ * wgrad: grad_w is the state_dict layout [C][1][k][k] fp32; k = 3 or 5; workspace: DYK_DW_WGRAD_SLABS * k*k*C floats,
+ * reduced in a fixed order (bit-reproducible). */
+#define DYK_DW_WGRAD_SLABS 256
+int dyk_dwconv2d_dgrad(const void* dz, int64_t dz_pix_stride, const float* w, void* dx, int64_t dx_pix_stride, int32_t N,
+                       int32_t H, int32_t W, int32_t C, int32_t k, int32_t stride, int32_t pad, int32_t accumulate,
+                       int32_t dtype, void* stream);
+int dyk_dwconv2d_wgrad(const void* x, int64_t x_pix_stride, const void* dz, int64_t dz_pix_stride, float* grad_w, int32_t N,
+                       int32_t H, int32_t W, int32_t C, int32_t k, int32_t stride, int32_t pad, int32_t accumulate,
+                       int32_t dtype, float* workspace, void* stream);
+
 /* ---- layout / packing helpers ---------------------------------------------------------------------
  * pack: OIHW fp32 (state_dict layout, models.py:35) -> [O][kh][kw][I] dtype.
  */

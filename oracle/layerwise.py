@@ -96,6 +96,9 @@ def compare_backward(plan, frames):
         if st["stem"]:
             x = (frames[0] if op.src is plan.img0 else frames[1]).clone()
             w = conv.weight.detach().float().cpu().clone()
+        elif conv.groups > 1:           # depthwise: the native kernels read the fp32 filter
+            x = _nchw(op.src.view)
+            w = conv.weight.detach().float().cpu().clone()
         else:
             x = _nchw(op.src.view)
             w = conv.weight.detach().to(plan.dtype).float().cpu().clone()
@@ -113,8 +116,8 @@ def compare_backward(plan, frames):
             g = b = None
             bias = conv.bias.detach().float().cpu().clone().requires_grad_(True)
             dz = dy_full[:, :conv.out_channels]
-        w_grad = torch.nn.grad.conv2d_weight(x, w.shape, dz, stride=s, padding=p)
-        x_grad = None if st["stem"] else torch.nn.grad.conv2d_input(x.shape, w, dz, stride=s, padding=p)
+        w_grad = torch.nn.grad.conv2d_weight(x, w.shape, dz, stride=s, padding=p, groups=conv.groups)
+        x_grad = None if st["stem"] else torch.nn.grad.conv2d_input(x.shape, w, dz, stride=s, padding=p, groups=conv.groups)
         bias_grad = None if bias is None else dz.sum((0, 2, 3))
 
         def rel(got, want):

@@ -100,6 +100,9 @@ WGRAD_CASES = [
     (1, 1024, 4, 5, 24, 1, 1, 0),          # detection head, Cout padded 18 -> 24
     (2, 96, 12, 12, 40, 1, 1, 0),          # odd channel counts
     (4, 128, 64, 80, 256, 3, 1, 1),        # many pixel blocks -> several splits
+    (2, 24, 16, 20, 72, 1, 2, 0),          # MobileNetV3 expand conv that carries the stride
+    (2, 16, 16, 20, 48, 1, 1, 0),
+    (2, 72, 16, 20, 24, 1, 1, 0),
 ]
 
 
@@ -134,6 +137,9 @@ DGRAD_CASES = [
     (2, 64, 32, 40, 128, 3, 2, 1),
     (1, 128, 16, 16, 256, 3, 2, 1),
     (1, 1024, 4, 5, 32, 1, 1, 0),           # head: Cout 18 padded to 32 for the dgrad GEMM's K
+    (2, 24, 16, 20, 72, 1, 2, 0),           # 1x1 stride 2: three of the four parity planes of dx are zero
+    (2, 16, 16, 20, 48, 1, 1, 0),
+    (2, 72, 16, 20, 24, 1, 1, 0),
 ]
 
 
@@ -158,6 +164,42 @@ def test_conv_dgrad(dtype, case):
     _assert_close(_back(dx), want, 3 * EPS16[dtype], ("dgrad", case))
     T.conv_dgrad(dzv, wd, dx, k=k, stride=stride, pad=pad, accumulate=True)
     _assert_close(_back(dx), 2 * want, 6 * EPS16[dtype], ("dgrad accumulate", case))
+
+
+DW_CASES = [  # N, C, H, W, k, stride, pad   (pad 1 with k 5: DepthwiseSeparableConv2d's fixed padding, layers.py:224)
+    (2, 72, 17, 23, 3, 1, 1), (2, 48, 16, 20, 3, 2, 1), (3, 120, 13, 11, 5, 1, 2), (2, 72, 16, 24, 5, 2, 2),
+    (1, 960, 8, 10, 5, 1, 2), (2, 64, 9, 14, 5, 1, 1), (4, 16, 64, 80, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("case", DW_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_dwconv_backward(dtype, case):
+    """Depthwise data and weight gradients against autograd's conv2d_input / conv2d_weight (groups = C) in fp64."""
+    from dyk import train_ops as T
+    from dyk.ops import _p
+    N, Cc, H, W, k, stride, pad = case
+    g = torch.Generator().manual_seed(8)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    w = torch.randn((Cc, 1, k, k), generator=g) / k
+    x = torch.randn((N, Cc, H, W), generator=g)
+    dz = torch.randn((N, Cc, Ho, Wo), generator=g)
+    xv, xq = _nhwc(x, dtype)
+    dzv, dzq = _nhwc(dz, dtype)
+    wk = w.reshape(Cc, k, k).permute(1, 2, 0).contiguous().to(DEV)
+    dx = _new(N, H, W, Cc, dtype)
+    T.dwconv_dgrad(dzv, wk, dx, k=k, stride=stride, pad=pad, accumulate=False)
+    want = torch.nn.grad.conv2d_input((N, Cc, H, W), w.double(), dzq.double(), stride=stride, padding=pad, groups=Cc).float()
+    _assert_close(_back(dx), want, 3 * EPS16[dtype], ("dw dgrad", case))
+    T.dwconv_dgrad(dzv, wk, dx, k=k, stride=stride, pad=pad, accumulate=True)
+    _assert_close(_back(dx), 2 * want, 6 * EPS16[dtype], ("dw dgrad accumulate", case))
+    gw = torch.full((Cc, 1, k, k), 7.0, device=DEV)
+    T.dwconv_wgrad(xv, dzv, gw, k=k, stride=stride, pad=pad, accumulate=False)
+    want_w = torch.nn.grad.conv2d_weight(xq.double(), (Cc, 1, k, k), dzq.double(), stride=stride, padding=pad, groups=Cc).float()
+    _assert_close(gw.cpu(), want_w, 2e-5, ("dw wgrad", case))
+    first = gw.clone()
+    T.dwconv_wgrad(xv, dzv, gw, k=k, stride=stride, pad=pad, accumulate=True)
+    assert torch.equal(gw, 2 * first), "accumulating the same gradient twice must double it exactly (fixed reduction order)"
 
 
 @pytest.mark.parametrize("dtype", DT)

@@ -18,6 +18,7 @@ import torch
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TINY = str(Path(__file__).resolve().parent / "data" / "tiny_yolov3_train.cfg")
+TINY_MOBILE = str(Path(__file__).resolve().parent / "data" / "tiny_mobile_inc_train.cfg")
 
 
 def _teacher_forced(tol):
@@ -98,10 +99,38 @@ def test_training_is_deterministic_and_updates_eval(native_lib):
     assert not torch.equal(io1, io3)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_tiny_mobile_inception_training_step(native_lib, dtype):
+    """Depthwise 3x3 / 5x5 (stride 1 and 2), hard-swish / relu / relu6, SE, DepthwiseSeparableConv2d and Inception blocks."""
+    from oracle.train_check import run
+    rows, stats, fwd, loss, loss_o = run(TINY_MOBILE, 64, 96, 2, dtype)
+    eps = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    assert max(fwd) < 8 * eps, ("head logits", fwd)
+    assert max(e for _, e in stats) < 2 * eps, ("BatchNorm running statistics", stats)
+    assert all(r is not None for _, r, _ in rows), "a parameter received no gradient"
+    assert all(r == r and r < 10 for _, r, _ in rows), "non-finite gradient"
+    _teacher_forced(1e-3 if dtype == torch.float16 else 6e-3)
+
+
+def test_mobilenetv3_dual_training_step(native_lib):
+    """BASELINE config 4's model (dual MobileNetV3 + FSNet + concat-SE + depthwise-separable PANet) at 128x160, batch 2:
+    all 524 parameter tensors get finite gradients and every convolution block (dense and depthwise) passes the
+    teacher-forced backward check."""
+    from oracle.train_check import run
+    rows, stats, fwd, loss, loss_o = run("kaist_dyolov4_mobilenetv3_fshare_global_cse3.cfg", 128, 160, 2, torch.bfloat16)
+    assert all(r is not None for _, r, _ in rows), "a parameter received no gradient"
+    assert all(r == r and r < 10 for _, r, _ in rows), "non-finite gradient"
+    _teacher_forced(6e-3)
+
+
 def test_training_limits_raise(native_lib):
     import models
-    from dyk import _native, cfg_zoo
-    m = models.YOLO(cfg_zoo.materialize("kaist_dyolov4_mobilenetv3_fshare_global_cse3.cfg"), (64, 96)).to(DEV).train()
+    from dyk import _native
+    cfg = Path(TINY).read_text().replace("filters=16\nsize=1", "filters=16\ngroups=2\nsize=1")
+    assert "groups=2" in cfg
+    path = Path("/tmp/dyk_tiny_grouped.cfg")
+    path.write_text(cfg)
+    m = models.YOLO(str(path), (64, 96)).to(DEV).train()
     x = torch.rand((1, 3, 64, 96), device=DEV)
     with pytest.raises(_native.NativeError):
-        m(x, x)      # depthwise convolutions: no training kernels yet, and no silent fallback
+        m(x)         # grouped (non-depthwise) convolutions: no kernels, and no silent fallback
