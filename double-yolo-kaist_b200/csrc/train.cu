@@ -51,93 +51,195 @@ __device__ __forceinline__ float act_grad(float x, int act) {
   }
 }
 
+// ------------------------------------------------------------------ channel-fixed thread layout
+// Every per-channel kernel below gives a thread ONE 8-channel vector for its whole life, so per-channel parameters are
+// loaded once (registers / shared memory) instead of once per element, and walks pixels.  A block of 256 threads is
+// (256 >> lg) pixel lanes x (1 << lg) channel-vector lanes; lg is chosen per channel count so that few lanes idle
+// (C = 32 -> 4 lanes, C >= 64 -> 8 lanes, MobileNet's 40 / 72 / 120 ... -> whatever wastes < 15 %).
+struct ChanGeom {
+  int lg;   // log2(channel-vector lanes per block)
+  int gx;   // blocks along the channel dimension
+};
+static inline ChanGeom chan_geom(int C) {
+  const int cv = C / 8;
+  int best = 0;
+  for (int lg = 3; lg >= 0; --lg) {
+    const int L = 1 << lg, padded = (cv + L - 1) / L * L;
+    if ((padded - cv) * 100 <= 15 * padded) { best = lg; break; }
+  }
+  return ChanGeom{best, (cv + (1 << best) - 1) >> best};
+}
+
 // ------------------------------------------------------------------ per-channel slab reductions
-// block: 32 pixel lanes x 8 channel-vectors (64 channels); grid: (ceil(C/64), slabs).
+// grid: (geom.gx, slabs).
 //   kMode 0: part[slab][0][c] = sum z            part[slab][1][c] = sum z*z                 (BN forward statistics)
-//   kMode 1: part[slab][0][c] = sum g            part[slab][1][c] = sum g*xhat              (BN backward), g = dy*act'(zhat)
+//   kMode 1: part[slab][0][c] = sum g            part[slab][1][c] = sum g*(z - mean)        (BN backward), g = dy*act'(zhat);
+//                                                 the finalize kernel multiplies the second sum by invstd
 //   kMode 2: part[slab][0][c] = sum a            (bias gradient)
 //   kMode 3: part[slab][0][c] = sum a*b          (per-channel dot, reduced over channels later: fusion-weight grads,
 //                                                 and with pixel ranges restricted to one image: SE gate grads)
+// Two pixels per thread are in flight per iteration; lanes of a warp that hold the same channels are combined with
+// shuffles, the 8 warps through shared memory — all in a fixed order.
 template <bool kBf16, int kMode>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, kMode == 1 ? 3 : 4)
 chan_reduce_kernel(const uint8_t* __restrict__ a, long long as, const uint8_t* __restrict__ b, long long bs,
-                   long long pix0, long long npix, int C, int slabs, const float* __restrict__ scale,
-                   const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
-                   int act, float* __restrict__ part) {
-  const int cvec = blockIdx.x * 8 + (threadIdx.x & 7);
-  const int plane = threadIdx.x >> 3;
+                   long long pix0, long long npix, int C, int slabs, int lg, const float* __restrict__ scale,
+                   const float* __restrict__ shift, const float* __restrict__ mean, int act, float* __restrict__ part) {
+  const int L = 1 << lg, nplanes = 256 >> lg;
+  const int cl = threadIdx.x & (L - 1), plane = threadIdx.x >> lg;
+  const int cvec = blockIdx.x * L + cl;
+  const bool live = cvec * 8 < C;
   const long long per = (npix + slabs - 1) / slabs;
   const long long p0 = blockIdx.y * per;
   const long long p1 = p0 + per < npix ? p0 + per : npix;
+  __shared__ __align__(16) float prm[3][64];
+  if constexpr (kMode == 1) {
+    if (threadIdx.x < 3 * L * 8) {
+      const int k = threadIdx.x / (L * 8), j = threadIdx.x - k * (L * 8);
+      const int c = blockIdx.x * L * 8 + j;
+      const float* src = k == 0 ? scale : (k == 1 ? shift : mean);
+      prm[k][j] = c < C ? __ldg(src + c) : 0.f;
+    }
+    __syncthreads();
+  }
   float s0[8], s1[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) s0[q] = s1[q] = 0.f;
-  if (cvec * 8 < C) {
-    float sc[8], sh[8], mu[8], is[8];
-    if constexpr (kMode == 1) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        sc[q] = __ldg(scale + cvec * 8 + q); sh[q] = __ldg(shift + cvec * 8 + q);
-        mu[q] = __ldg(mean + cvec * 8 + q); is[q] = __ldg(invstd + cvec * 8 + q);
-      }
-    }
-    for (long long pidx = p0 + plane; pidx < p1; pidx += 32) {
-      const long long pix = pix0 + pidx;
+  if (live) {
+    const uint8_t* pa = a + (pix0 + p0 + plane) * as * 2 + cvec * 16;
+    const uint8_t* pb = kMode == 1 || kMode == 3 ? b + (pix0 + p0 + plane) * bs * 2 + cvec * 16 : nullptr;
+    const long long sa = (long long)nplanes * as * 2, sb = (long long)nplanes * bs * 2;
+    auto accum = [&](const uint4& va, const uint4& vb) {
       float fa[8];
-      unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(a + pix * as * 2) + cvec), fa);
+      unpack8<kBf16>(va, fa);
       if constexpr (kMode == 0) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { s0[q] += fa[q]; s1[q] += fa[q] * fa[q]; }
+        for (int q = 0; q < 8; ++q) { s0[q] += fa[q]; s1[q] = fmaf(fa[q], fa[q], s1[q]); }
       } else if constexpr (kMode == 2) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) s0[q] += fa[q];
       } else {
         float fb[8];
-        unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(b + pix * bs * 2) + cvec), fb);
+        unpack8<kBf16>(vb, fb);
         if constexpr (kMode == 3) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) s0[q] += fa[q] * fb[q];
+          for (int q = 0; q < 8; ++q) s0[q] = fmaf(fa[q], fb[q], s0[q]);
         } else {   // a = dy, b = z
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float g = fa[q] * act_grad(fmaf(fb[q], sc[q], sh[q]), act);
-            s0[q] += g;
-            s1[q] += g * ((fb[q] - mu[q]) * is[q]);
+          for (int h = 0; h < 2; ++h) {
+            const float4 sc = *reinterpret_cast<const float4*>(&prm[0][cl * 8 + h * 4]);
+            const float4 sh = *reinterpret_cast<const float4*>(&prm[1][cl * 8 + h * 4]);
+            const float4 mu = *reinterpret_cast<const float4*>(&prm[2][cl * 8 + h * 4]);
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w}, muv[4] = {mu.x, mu.y, mu.z, mu.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float z = fb[h * 4 + q];
+              const float g = fa[h * 4 + q] * act_grad(fmaf(z, scv[q], shv[q]), act);
+              s0[h * 4 + q] += g;
+              s1[h * 4 + q] = fmaf(g, z - muv[q], s1[h * 4 + q]);
+            }
           }
         }
       }
+    };
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    long long pidx = p0 + plane;
+    for (; pidx + nplanes < p1; pidx += 2 * nplanes) {          // two independent pixels in flight
+      const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(pa));
+      const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(pa + sa));
+      uint4 b0 = zero, b1 = zero;
+      if constexpr (kMode == 1 || kMode == 3) {
+        b0 = __ldg(reinterpret_cast<const uint4*>(pb));
+        b1 = __ldg(reinterpret_cast<const uint4*>(pb + sb));
+        pb += 2 * sb;
+      }
+      pa += 2 * sa;
+      accum(a0, b0);
+      accum(a1, b1);
+    }
+    if (pidx < p1) {
+      const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(pa));
+      uint4 b0 = zero;
+      if constexpr (kMode == 1 || kMode == 3) b0 = __ldg(reinterpret_cast<const uint4*>(pb));
+      accum(a0, b0);
     }
   }
-  __shared__ float red[2][32][8][8];
+  // lanes of a warp with equal cl -> lane cl (fixed xor tree), then the 8 warps in order
+  for (int off = L; off < 32; off <<= 1) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    red[0][plane][threadIdx.x & 7][q] = s0[q];
-    red[1][plane][threadIdx.x & 7][q] = s1[q];
+    for (int q = 0; q < 8; ++q) {
+      s0[q] += __shfl_xor_sync(0xffffffffu, s0[q], off);
+      if constexpr (kMode <= 1) s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], off);
+    }
+  }
+  __shared__ float red[2][8][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < L) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      red[0][warp][lane * 8 + q] = s0[q];
+      red[1][warp][lane * 8 + q] = s1[q];
+    }
   }
   __syncthreads();
-  if (threadIdx.x < 128) {
-    const int which = threadIdx.x >> 6, cv = (threadIdx.x >> 3) & 7, q = threadIdx.x & 7;
+  if ((int)threadIdx.x < 2 * L * 8) {
+    const int which = threadIdx.x / (L * 8), j = threadIdx.x - which * (L * 8);
     float s = 0.f;
-    for (int l = 0; l < 32; ++l) s += red[which][l][cv][q];
-    const int c = (blockIdx.x * 8 + cv) * 8 + q;
+    // with L == 8 a warp holds 4 pixel lanes; with smaller L the warps still partition the pixel lanes
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[which][w][j];
+    const int c = blockIdx.x * L * 8 + j;
     if (c < C) part[((long long)blockIdx.y * 2 + which) * C + c] = s;
+  }
+}
+
+template <int kMode>
+static int launch_chan_reduce(int dtype, const void* a, long long as, const void* b, long long bs, long long pix0,
+                              long long npix, int C, int slabs, const float* scale, const float* shift, const float* mean,
+                              int act, float* part, cudaStream_t stream) {
+  const ChanGeom g = chan_geom(C);
+  const dim3 grid(g.gx, slabs);
+  DYK_DISPATCH_DTYPE(dtype, (chan_reduce_kernel<kBf16, kMode><<<grid, 256, 0, stream>>>(
+                                (const uint8_t*)a, as, (const uint8_t*)b, bs, pix0, npix, C, slabs, g.lg, scale, shift, mean,
+                                act, part)));
+  DYK_LAUNCH_OK("chan_reduce_kernel");
+  return DYK_OK;
+}
+
+// Sum of the slab partials of 8 channels by one block: 32 slab lanes x 8 channels, each lane adds its slabs in order
+// (double), then the 32 lanes are added in order.  Returns the two sums to threads 0..7 (channel = threadIdx.x).
+__device__ __forceinline__ void slab_totals(const float* __restrict__ part, int slabs, int C, int c0, double& t0, double& t1) {
+  __shared__ double red[2][32][8];
+  const int ch = threadIdx.x & 7, sl0 = threadIdx.x >> 3;
+  const int c = c0 + ch;
+  double s0 = 0.0, s1 = 0.0;
+  if (c < C) {
+    for (int sl = sl0; sl < slabs; sl += 32) {
+      s0 += (double)part[((long long)sl * 2 + 0) * C + c];
+      s1 += (double)part[((long long)sl * 2 + 1) * C + c];
+    }
+  }
+  red[0][sl0][ch] = s0;
+  red[1][sl0][ch] = s1;
+  __syncthreads();
+  t0 = t1 = 0.0;
+  if (threadIdx.x < 8) {
+    for (int l = 0; l < 32; ++l) { t0 += red[0][l][threadIdx.x]; t1 += red[1][l][threadIdx.x]; }
   }
 }
 
 // BN forward finalize: batch mean / biased variance -> (scale, shift) for y = z*scale + shift, saved (mean, invstd),
 // running statistics updated in place exactly like nn.BatchNorm2d(momentum) (unbiased variance in running_var).
-__global__ void bn_fwd_finalize_kernel(const float* __restrict__ part, int slabs, float count, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, float eps, float momentum,
-                                       float* __restrict__ running_mean, float* __restrict__ running_var,
-                                       float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
-                                       float* __restrict__ invstd_out, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s0 = 0.0, s1 = 0.0;
-  for (int sl = 0; sl < slabs; ++sl) {
-    s0 += (double)part[((long long)sl * 2 + 0) * C + c];
-    s1 += (double)part[((long long)sl * 2 + 1) * C + c];
-  }
+// grid: C/8 blocks of 256 threads.
+__global__ void __launch_bounds__(256)
+bn_fwd_finalize_kernel(const float* __restrict__ part, int slabs, float count, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                       float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
+                       float* __restrict__ mean_out, float* __restrict__ invstd_out, int C) {
+  double s0, s1;
+  slab_totals(part, slabs, C, blockIdx.x * 8, s0, s1);
+  const int c = blockIdx.x * 8 + threadIdx.x;
+  if (threadIdx.x >= 8 || c >= C) return;
   const double m = s0 / count;
   double var = s1 / count - m * m;
   if (var < 0.0) var = 0.0;
@@ -154,89 +256,125 @@ __global__ void bn_fwd_finalize_kernel(const float* __restrict__ part, int slabs
   }
 }
 
-// y = act(z*scale[c] + shift[c])
+// y = act(z*scale[c] + shift[c]); grid (geom.gx, Y): channel-fixed threads, pixels interleaved over blockIdx.y
 template <bool kBf16>
-__global__ void bn_act_apply_kernel(const uint8_t* __restrict__ z, long long zs, const float* __restrict__ scale,
-                                    const float* __restrict__ shift, int act, uint8_t* __restrict__ y, long long ys,
-                                    long long npix, int cv) {
-  const long long total = npix * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / cv;
-    const int c = (int)(i - pix * cv);
+__global__ void __launch_bounds__(256, 4)
+bn_act_apply_kernel(const uint8_t* __restrict__ z, long long zs, const float* __restrict__ scale,
+                    const float* __restrict__ shift, int act, uint8_t* __restrict__ y, long long ys, long long npix, int C,
+                    int lg) {
+  const int L = 1 << lg, nplanes = 256 >> lg;
+  const int cvec = blockIdx.x * L + (threadIdx.x & (L - 1));
+  if (cvec * 8 >= C) return;
+  float sc[8], sh[8];
+  {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + cvec * 8)), a1 = __ldg(reinterpret_cast<const float4*>(scale + cvec * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + cvec * 8)), b1 = __ldg(reinterpret_cast<const float4*>(shift + cvec * 8) + 1);
+    sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+    sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+  }
+  const long long step = (long long)gridDim.y * nplanes;
+  long long pix = (long long)blockIdx.y * nplanes + (threadIdx.x >> lg);
+  auto one = [&](const uint4& v, long long p) {
     float f[8];
-    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(z + pix * zs * 2) + c), f);
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + c * 8)), a1 = __ldg(reinterpret_cast<const float4*>(scale + c * 8) + 1);
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + c * 8)), b1 = __ldg(reinterpret_cast<const float4*>(shift + c * 8) + 1);
-    const float sc[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    unpack8<kBf16>(v, f);
 #pragma unroll
     for (int q = 0; q < 8; ++q) f[q] = apply_act(fmaf(f[q], sc[q], sh[q]), act);
-    *(reinterpret_cast<uint4*>(y + pix * ys * 2) + c) = pack8<kBf16>(f);
+    *(reinterpret_cast<uint4*>(y + p * ys * 2) + cvec) = pack8<kBf16>(f);
+  };
+  for (; pix + step < npix; pix += 2 * step) {
+    const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(z + pix * zs * 2) + cvec);
+    const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(z + (pix + step) * zs * 2) + cvec);
+    one(v0, pix);
+    one(v1, pix + step);
   }
+  if (pix < npix) one(__ldg(reinterpret_cast<const uint4*>(z + pix * zs * 2) + cvec), pix);
 }
 
-// BN backward finalize: dgamma / dbeta (accumulated into the fp32 parameter gradients) and the three per-channel
-// coefficients of  dz = cA*g + cB + cC*xhat,  cA = gamma*invstd, cB = -cA*sum(g)/M, cC = -cA*sum(g*xhat)/M.
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int slabs, float count, const float* __restrict__ gamma,
-                                       const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       float* __restrict__ coef, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s0 = 0.0, s1 = 0.0;
-  for (int sl = 0; sl < slabs; ++sl) {
-    s0 += (double)part[((long long)sl * 2 + 0) * C + c];
-    s1 += (double)part[((long long)sl * 2 + 1) * C + c];
-  }
-  if (dgamma) dgamma[c] += (float)s1;
+// BN backward finalize: dgamma / dbeta (accumulated into the fp32 parameter gradients) and the per-channel coefficients of
+//   dz = cA*g + cD + cE*z   with  g = dy*act'(zhat),  cA = gamma*invstd,
+//   cD = -cA*(sum g)/M + cA*invstd^2*mean*(sum g*(z-mean))/M,   cE = -cA*invstd^2*(sum g*(z-mean))/M
+// (the usual  cA*(g - mean(g) - xhat*mean(g*xhat))  with xhat = (z-mean)*invstd expanded in z).
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ part, int slabs, float count, const float* __restrict__ gamma,
+                       const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, float* __restrict__ coef, int C) {
+  double s0, s1;
+  slab_totals(part, slabs, C, blockIdx.x * 8, s0, s1);
+  const int c = blockIdx.x * 8 + threadIdx.x;
+  if (threadIdx.x >= 8 || c >= C) return;
+  const double is = (double)invstd[c];
+  const double sgx = s1 * is;                       // sum g*xhat
+  if (dgamma) dgamma[c] += (float)sgx;
   if (dbeta) dbeta[c] += (float)s0;
-  const float cA = (gamma ? gamma[c] : 1.f) * invstd[c];
-  coef[c] = cA;
-  coef[C + c] = (float)(-(double)cA * s0 / count);
-  coef[2 * C + c] = (float)(-(double)cA * s1 / count);
+  const double cA = (double)(gamma ? gamma[c] : 1.f) * is;
+  const double cC = -cA * sgx / count;              // multiplies xhat
+  coef[c] = (float)cA;
+  coef[C + c] = (float)(-cA * s0 / count - cC * is * (double)mean[c]);
+  coef[2 * C + c] = (float)(cC * is);
 }
 
 template <bool kBf16>
-__global__ void bn_act_bwd_apply_kernel(const uint8_t* __restrict__ dy, long long dys, const uint8_t* __restrict__ z, long long zs,
-                                        const float* __restrict__ scale, const float* __restrict__ shift,
-                                        const float* __restrict__ mean, const float* __restrict__ invstd,
-                                        const float* __restrict__ coef, int C, int act, uint8_t* __restrict__ dz,
-                                        long long dzs, long long npix, int cv) {
-  const long long total = npix * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / cv;
-    const int c = (int)(i - pix * cv);
-    float g[8], fz[8], o[8];
-    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dy + pix * dys * 2) + c), g);
-    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(z + pix * zs * 2) + c), fz);
-    float ps[7][8];   // scale, shift, mean, invstd, cA, cB, cC of these 8 channels (two 16-byte loads each)
-    const float* srcs[7] = {scale, shift, mean, invstd, coef, coef + C, coef + 2 * C};
+__global__ void __launch_bounds__(256, 3)
+bn_act_bwd_apply_kernel(const uint8_t* __restrict__ dy, long long dys, const uint8_t* __restrict__ z, long long zs,
+                        const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ coef,
+                        int C, int act, uint8_t* __restrict__ dz, long long dzs, long long npix, int lg) {
+  const int L = 1 << lg, nplanes = 256 >> lg;
+  const int cvec = blockIdx.x * L + (threadIdx.x & (L - 1));
+  if (cvec * 8 >= C) return;
+  float ps[5][8];   // scale, shift, cA, cD, cE of these 8 channels
+  {
+    const float* srcs[5] = {scale, shift, coef, coef + C, coef + 2 * C};
 #pragma unroll
-    for (int v = 0; v < 7; ++v) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(srcs[v] + c * 8));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(srcs[v] + c * 8) + 1);
+    for (int v = 0; v < 5; ++v) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(srcs[v] + cvec * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(srcs[v] + cvec * 8) + 1);
       ps[v][0] = a.x; ps[v][1] = a.y; ps[v][2] = a.z; ps[v][3] = a.w;
       ps[v][4] = b.x; ps[v][5] = b.y; ps[v][6] = b.z; ps[v][7] = b.w;
     }
+  }
+  const long long step = (long long)gridDim.y * nplanes;
+  long long pix = (long long)blockIdx.y * nplanes + (threadIdx.x >> lg);
+  auto one = [&](const uint4& vg, const uint4& vz, long long p) {
+    float g[8], fz[8], o[8];
+    unpack8<kBf16>(vg, g);
+    unpack8<kBf16>(vz, fz);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float zhat = fmaf(fz[q], ps[0][q], ps[1][q]);
-      const float gg = g[q] * act_grad(zhat, act);
-      const float xhat = (fz[q] - ps[2][q]) * ps[3][q];
-      o[q] = ps[4][q] * gg + ps[5][q] + ps[6][q] * xhat;
+      const float gg = g[q] * act_grad(fmaf(fz[q], ps[0][q], ps[1][q]), act);
+      o[q] = fmaf(ps[2][q], gg, fmaf(ps[4][q], fz[q], ps[3][q]));
     }
-    *(reinterpret_cast<uint4*>(dz + pix * dzs * 2) + c) = pack8<kBf16>(o);
+    *(reinterpret_cast<uint4*>(dz + p * dzs * 2) + cvec) = pack8<kBf16>(o);
+  };
+  for (; pix + step < npix; pix += 2 * step) {
+    const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(dy + pix * dys * 2) + cvec);
+    const uint4 z0 = __ldg(reinterpret_cast<const uint4*>(z + pix * zs * 2) + cvec);
+    const uint4 g1 = __ldg(reinterpret_cast<const uint4*>(dy + (pix + step) * dys * 2) + cvec);
+    const uint4 z1 = __ldg(reinterpret_cast<const uint4*>(z + (pix + step) * zs * 2) + cvec);
+    one(g0, z0, pix);
+    one(g1, z1, pix + step);
   }
+  if (pix < npix)
+    one(__ldg(reinterpret_cast<const uint4*>(dy + pix * dys * 2) + cvec), __ldg(reinterpret_cast<const uint4*>(z + pix * zs * 2) + cvec), pix);
 }
 
-// out[c] (+)= sum over slabs of part[slab][0][c]   (bias gradients)
-__global__ void slab_sum_kernel(const float* __restrict__ part, int slabs, int C, float* __restrict__ out, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s = 0.f;
-  for (int sl = 0; sl < slabs; ++sl) s += part[((long long)sl * 2) * C + c];
-  out[c] = accumulate ? out[c] + s : s;
+// grid.y of the channel-fixed apply kernels: enough blocks to fill the GPU ~8 times over, at least 4 pixels per thread
+static inline int apply_grid_y(long long npix, const ChanGeom& g) {
+  const int nplanes = 256 >> g.lg;
+  long long y = (npix + (long long)nplanes * 4 - 1) / ((long long)nplanes * 4);
+  const long long cap = ((long long)num_sms() * 8 + g.gx - 1) / g.gx;
+  if (y > cap) y = cap;
+  if (y < 1) y = 1;
+  return (int)y;
+}
+
+// out[c] (+)= sum over slabs of part[slab][0][c]   (bias gradients); grid: C/8 blocks of 256 threads
+__global__ void __launch_bounds__(256)
+slab_sum_kernel(const float* __restrict__ part, int slabs, int C, float* __restrict__ out, int accumulate) {
+  double s0, s1;
+  slab_totals(part, slabs, C, blockIdx.x * 8, s0, s1);
+  const int c = blockIdx.x * 8 + threadIdx.x;
+  if (threadIdx.x >= 8 || c >= C) return;
+  out[c] = accumulate ? out[c] + (float)s0 : (float)s0;
 }
 
 // dst = alpha*src (+ dst)
@@ -579,13 +717,10 @@ DYK_EXPORT int dyk_bn_train_stats(const void* z, int64_t zs, int64_t npix, int32
   DYK_REQUIRE(z && scale && shift && mean && invstd && workspace, "dyk_bn_train_stats: null pointer");
   DYK_REQUIRE(C > 0 && C % 8 == 0 && zs % 8 == 0 && npix > 0 && DYK_AL16(z), "dyk_bn_train_stats: bad shape");
   const int slabs = slabs_for(npix);
-  const dim3 grid((C + 63) / 64, slabs);
-  DYK_DISPATCH_DTYPE(dtype, (chan_reduce_kernel<kBf16, 0><<<grid, 256, 0, stream>>>(
-                                (const uint8_t*)z, zs, nullptr, 0, 0, npix, C, slabs, nullptr, nullptr, nullptr, nullptr, 0,
-                                workspace)));
-  DYK_LAUNCH_OK("chan_reduce_kernel<0>");
-  bn_fwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(workspace, slabs, (float)npix, gamma, beta, eps, momentum,
-                                                             running_mean, running_var, scale, shift, mean, invstd, C);
+  if (int rc = launch_chan_reduce<0>(dtype, z, zs, nullptr, 0, 0, npix, C, slabs, nullptr, nullptr, nullptr, 0, workspace, stream))
+    return rc;
+  bn_fwd_finalize_kernel<<<(C + 7) / 8, 256, 0, stream>>>(workspace, slabs, (float)npix, gamma, beta, eps, momentum,
+                                                         running_mean, running_var, scale, shift, mean, invstd, C);
   DYK_LAUNCH_OK("bn_fwd_finalize_kernel");
   return DYK_OK;
 }
@@ -595,9 +730,10 @@ DYK_EXPORT int dyk_bn_act_apply(const void* z, int64_t zs, const float* scale, c
   DYK_REQUIRE(z && scale && shift && y, "dyk_bn_act_apply: null pointer");
   DYK_REQUIRE(C > 0 && C % 8 == 0 && zs % 8 == 0 && ys % 8 == 0 && DYK_AL16(z) && DYK_AL16(y), "dyk_bn_act_apply: bad shape");
   if (npix == 0) return DYK_OK;
-  const int cv = C / 8;
-  DYK_DISPATCH_DTYPE(dtype, (bn_act_apply_kernel<kBf16><<<grid_for_t(npix * cv, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-                                (const uint8_t*)z, zs, scale, shift, act, (uint8_t*)y, ys, npix, cv)));
+  const ChanGeom g = chan_geom(C);
+  const dim3 grid(g.gx, apply_grid_y(npix, g));
+  DYK_DISPATCH_DTYPE(dtype, (bn_act_apply_kernel<kBf16><<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+                                (const uint8_t*)z, zs, scale, shift, act, (uint8_t*)y, ys, npix, C, g.lg)));
   DYK_LAUNCH_OK("bn_act_apply_kernel");
   return DYK_OK;
 }
@@ -613,17 +749,14 @@ DYK_EXPORT int dyk_bn_act_bwd(const void* dy, int64_t dys, const void* z, int64_
   const int slabs = slabs_for(npix);
   float* part = workspace;                                  // [slabs][2][C]
   float* coef = workspace + (size_t)kMaxSlabs * 2 * C;      // [3][C]
-  const dim3 grid((C + 63) / 64, slabs);
-  DYK_DISPATCH_DTYPE(dtype, (chan_reduce_kernel<kBf16, 1><<<grid, 256, 0, stream>>>(
-                                (const uint8_t*)dy, dys, (const uint8_t*)z, zs, 0, npix, C, slabs, scale, shift, mean, invstd,
-                                act, part)));
-  DYK_LAUNCH_OK("chan_reduce_kernel<1>");
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(part, slabs, (float)npix, gamma, invstd, dgamma, dbeta, coef, C);
+  if (int rc = launch_chan_reduce<1>(dtype, dy, dys, z, zs, 0, npix, C, slabs, scale, shift, mean, act, part, stream)) return rc;
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, stream>>>(part, slabs, (float)npix, gamma, mean, invstd, dgamma, dbeta, coef, C);
   DYK_LAUNCH_OK("bn_bwd_finalize_kernel");
-  const int cv = C / 8;
-  DYK_DISPATCH_DTYPE(dtype, (bn_act_bwd_apply_kernel<kBf16><<<grid_for_t(npix * cv, 256), 256, 0, stream>>>(
-                                (const uint8_t*)dy, dys, (const uint8_t*)z, zs, scale, shift, mean, invstd, coef, C, act,
-                                (uint8_t*)dz, dzs, npix, cv)));
+  const ChanGeom g = chan_geom(C);
+  const dim3 grid(g.gx, apply_grid_y(npix, g));
+  DYK_DISPATCH_DTYPE(dtype, (bn_act_bwd_apply_kernel<kBf16><<<grid, 256, 0, stream>>>(
+                                (const uint8_t*)dy, dys, (const uint8_t*)z, zs, scale, shift, coef, C, act, (uint8_t*)dz, dzs,
+                                npix, g.lg)));
   DYK_LAUNCH_OK("bn_act_bwd_apply_kernel");
   return DYK_OK;
 }
@@ -634,12 +767,9 @@ DYK_EXPORT int dyk_chan_sum(const void* x, int64_t xs, int64_t npix, int32_t C, 
   DYK_REQUIRE(x && out && workspace, "dyk_chan_sum: null pointer");
   DYK_REQUIRE(C > 0 && C % 8 == 0 && xs % 8 == 0 && npix > 0 && DYK_AL16(x), "dyk_chan_sum: bad shape");
   const int slabs = slabs_for(npix);
-  const dim3 grid((C + 63) / 64, slabs);
-  DYK_DISPATCH_DTYPE(dtype, (chan_reduce_kernel<kBf16, 2><<<grid, 256, 0, stream>>>(
-                                (const uint8_t*)x, xs, nullptr, 0, 0, npix, C, slabs, nullptr, nullptr, nullptr, nullptr, 0,
-                                workspace)));
-  DYK_LAUNCH_OK("chan_reduce_kernel<2>");
-  slab_sum_kernel<<<(C + 127) / 128, 128, 0, stream>>>(workspace, slabs, C, out, accumulate);
+  if (int rc = launch_chan_reduce<2>(dtype, x, xs, nullptr, 0, 0, npix, C, slabs, nullptr, nullptr, nullptr, 0, workspace, stream))
+    return rc;
+  slab_sum_kernel<<<(C + 7) / 8, 256, 0, stream>>>(workspace, slabs, C, out, accumulate);
   DYK_LAUNCH_OK("slab_sum_kernel");
   return DYK_OK;
 }
@@ -666,15 +796,8 @@ DYK_EXPORT int dyk_fusion_weights_bwd(const void* dy, int64_t dys, const void* a
   const int slabs = slabs_for(npix);
   float* part0 = workspace;
   float* part1 = workspace + (size_t)kMaxSlabs * 2 * C;
-  const dim3 grid((C + 63) / 64, slabs);
-  DYK_DISPATCH_DTYPE(dtype, (chan_reduce_kernel<kBf16, 3><<<grid, 256, 0, stream>>>(
-                                (const uint8_t*)dy, dys, (const uint8_t*)a, as, 0, npix, C, slabs, nullptr, nullptr, nullptr,
-                                nullptr, 0, part0)));
-  DYK_LAUNCH_OK("chan_reduce_kernel<3>");
-  DYK_DISPATCH_DTYPE(dtype, (chan_reduce_kernel<kBf16, 3><<<grid, 256, 0, stream>>>(
-                                (const uint8_t*)dy, dys, (const uint8_t*)b, bs, 0, npix, C, slabs, nullptr, nullptr, nullptr,
-                                nullptr, 0, part1)));
-  DYK_LAUNCH_OK("chan_reduce_kernel<3>");
+  if (int rc = launch_chan_reduce<3>(dtype, dy, dys, a, as, 0, npix, C, slabs, nullptr, nullptr, nullptr, 0, part0, stream)) return rc;
+  if (int rc = launch_chan_reduce<3>(dtype, dy, dys, b, bs, 0, npix, C, slabs, nullptr, nullptr, nullptr, 0, part1, stream)) return rc;
   fusion_weights_bwd_kernel<<<1, 256, 0, stream>>>(w_raw, part0, part1, slabs, C, n, grad_w);
   DYK_LAUNCH_OK("fusion_weights_bwd_kernel");
   return DYK_OK;
@@ -726,12 +849,10 @@ DYK_EXPORT int dyk_se_bwd(const void* x, int64_t xs, const void* dy, int64_t dys
   float* dgate_part = workspace;                                   // [N][dslabs][2][C]
   float* dmean = workspace + (size_t)N * 32 * 2 * C;               // [N][C]
   float* keep = dmean + (size_t)N * C;                             // [N][2C + 2Csq]  (<= 4 N C floats)
-  const dim3 grid((C + 63) / 64, dslabs);
   for (int n = 0; n < N; ++n) {   // dgate[n][c] = sum_hw dy * x
-    DYK_DISPATCH_DTYPE(dtype, (chan_reduce_kernel<kBf16, 3><<<grid, 256, 0, stream>>>(
-                                  (const uint8_t*)dy, dys, (const uint8_t*)x, xs, (long long)n * HW, HW, C, dslabs, nullptr,
-                                  nullptr, nullptr, nullptr, 0, dgate_part + (size_t)n * dslabs * 2 * C)));
-    DYK_LAUNCH_OK("chan_reduce_kernel<3> (se)");
+    if (int rc = launch_chan_reduce<3>(dtype, dy, dys, x, xs, (long long)n * HW, HW, C, dslabs, nullptr, nullptr, nullptr, 0,
+                                       dgate_part + (size_t)n * dslabs * 2 * C, stream))
+      return rc;
   }
   DYK_REQUIRE(Csq <= C, "dyk_se_bwd: Csq > C");
   se_mlp_bwd_kernel<<<N, 1024, (2 * C + 2 * Csq) * sizeof(float), stream>>>(pooled, fslabs, 1.f / (float)HW, dgate_part, dslabs, C,
