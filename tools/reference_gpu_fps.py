@@ -39,3 +39,31 @@ for autocast in (False, True):
     dt = time.perf_counter() - t0
     print(f"{cfg} bs{B} reference-on-GPU ({'autocast fp16' if autocast else 'fp32 (TF32 convs)'}): "
           f"{B * steps / dt:8.1f} paired frames/s  ({dt / steps * 1e3:.1f} ms/step, forward + NMS, cudnn.benchmark=False)")
+
+# training step (BASELINE config 3): forward in train mode + backward through autograd + SGD, as the reference's loop does
+# (train_utils/kaist_train_eval_utils.py:74-108) minus compute_loss, which bench.py --mode train also replaces by a probe loss
+if "--train" in sys.argv:
+    params = {k: t.clone().requires_grad_(True) for k, t in st.items()
+              if t.dtype.is_floating_point and not k.endswith(("running_mean", "running_var"))}
+    state = dict(st)
+    state.update(params)
+    opt = torch.optim.SGD(list(params.values()), lr=1e-4, momentum=0.9)
+    for dt_name, dt in (("bf16 autocast", torch.bfloat16), ("fp16 autocast", torch.float16)):
+        def train_step():
+            v, l = v8.float() / 255.0, (l8.float() / 255.0 if dual else None)
+            with torch.autocast("cuda", dtype=dt):
+                p = ref.forward(state, v, l, training=True)
+            loss = sum((t.float() ** 2).mean() for t in p)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+        for _ in range(3):
+            train_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            train_step()
+        torch.cuda.synchronize()
+        dt_s = time.perf_counter() - t0
+        print(f"{cfg} bs{B} reference-on-GPU TRAIN ({dt_name}): {B * steps / dt_s:8.1f} paired frames/s  "
+              f"({dt_s / steps * 1e3:.1f} ms/step, forward + backward + SGD)")
