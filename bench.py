@@ -304,6 +304,15 @@ def run_train(args, rank, local, world, dev):
         dist.destroy_process_group()
 
 
+def conv_dram_traffic(cfg, B):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) moved by the convolution launches of one step, from the
+    committed ncu capture of this exact workload (profiles/r01_dram_traffic_dyolov3.txt); None for workloads that were not
+    captured.  It is below the algorithmic 11.04 GB because the 126 MB L2 keeps part of each layer's output for its consumer."""
+    if cfg == "kaist_dyolov3_add_sl.cfg" and B == 16:
+        return 8.147e9
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -448,8 +457,11 @@ def main():
                     "h2d_bytes_per_step": 2 * B * 3 * H * W, "d2h_bytes_per_step": B * 100 * 6 * 4 + B * 4},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_kind,
-                         "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all dense convs of the step)",
+                         "frac": achieved / peak_tf, "traffic": conv_dram_traffic(args.cfg, B), "peak_source": peak_kind,
+                         "traffic_note": "DRAM read+write bytes of all conv launches of one step (ncu dram__bytes_*; "
+                                         "profiles/r01_dram_traffic_dyolov3.txt); the step's algorithmic bytes are 11.04e9",
+                         "kernel": "conv_tc_kernel / conv3x3_halo*_kernel / stem_tc_kernel (tcgen05 implicit GEMM, all dense "
+                                   "convs of the step; a launch = one layer, figures are per step)",
                          "launches_per_step": n_conv, "conv_ms_per_step": conv_ms, "other_kernels_ms_per_step": other_ms,
                          "algorithmic_gflop_per_step": flops / 1e9},
             "cuda_graph": plan.graph is not None,

@@ -37,11 +37,12 @@ __device__ __forceinline__ float act_grad(float x, int act) {
   switch (act) {
     case DYK_ACT_LEAKY: return x > 0.f ? 1.f : 0.1f;
     case DYK_ACT_MISH: {
+      // mish'(x) = t + x*sigmoid(x)*(1 - t^2), t = tanh(softplus(x)) = n/(n+2), n = e^x (e^x + 2).  With n + 1 = (e^x + 1)^2
+      // this is (n (n+2) + 4 x e^x (e^x + 1)) / (n+2)^2: one exponential and one reciprocal per element.
       const float e = __expf(fminf(x, 20.f));
       const float n = e * (e + 2.f);
-      const float t = __fdividef(n, n + 2.f);            // tanh(softplus(x))
-      const float sg = __fdividef(e, e + 1.f);           // sigmoid(x)
-      return x > 20.f ? 1.f : t + x * sg * (1.f - t * t);
+      const float r = __fdividef(1.f, n + 2.f);
+      return x > 20.f ? 1.f : fmaf(n, n + 2.f, 4.f * x * e * (e + 1.f)) * r * r;
     }
     case DYK_ACT_RELU: return x > 0.f ? 1.f : 0.f;
     case DYK_ACT_RELU6: return (x > 0.f && x < 6.f) ? 1.f : 0.f;
