@@ -31,6 +31,7 @@ extern unsigned long long* g_conv_prof;   // conv_tc.cu (dyk_conv_set_profile)
 struct Halo2Tmaps {
   CUtensorMap a;  // input  (Cin, W, H, N), box {64, 10, 18, 1}
   CUtensorMap b;  // packed weights (Cin, 9, Cout), box {64, 1, 128}
+  CUtensorMap bs; // the same tensor with box {64, 1, 128 / tail_split} for the split items of the last round
   CUtensorMap y;  // output (Cout_store, W, H, N), box {32, 8, 4, 1}
 };
 
@@ -47,6 +48,10 @@ struct Halo2KArgs {
   int H, W, N;
   int num_subs;
   int n_blocks, num_tiles;      // pair tiles = ceil(num_subs / 2) * n_blocks, n-block fastest
+  // Work items: the first full_items tiles are computed whole (N = 256); the tiles of the last, partial round are
+  // split into (1 << tail_lg) items of 256 >> tail_lg output channels each, so that the round occupies all clusters for
+  // a fraction of a tile time instead of a few clusters for a whole one (the MMA's N is a run-time descriptor field).
+  int full_items, tail_lg, num_items;
   int k_chunks;
   int Cout_store;
   int act;
@@ -74,6 +79,15 @@ static_assert(kH2Total <= 227 * 1024, "halo2 shared memory budget");
 struct Sub2 {
   int w0, h0, n;
 };
+struct Item2 {
+  int tile, ncol0, ncols;
+};
+__device__ __forceinline__ Item2 item2_decode(const Halo2KArgs& p, int item) {
+  if (item < p.full_items) return Item2{item, 0, kH2BlockN};
+  const int j = item - p.full_items;
+  const int ncols = kH2BlockN >> p.tail_lg;
+  return Item2{p.full_items + (j >> p.tail_lg), (j & ((1 << p.tail_lg) - 1)) * ncols, ncols};
+}
 __device__ __forceinline__ Sub2 sub2_coord(const Halo2KArgs& p, unsigned sub) {
   Sub2 c;
   const unsigned rowt = fd_div(sub, p.fd_subs_w);
@@ -88,11 +102,11 @@ __device__ __forceinline__ Sub2 sub2_coord(const Halo2KArgs& p, unsigned sub) {
 
 template <bool kBf16, int kAct>
 __device__ __forceinline__ void halo2_epilogue(const Halo2Tmaps& tm, const Halo2KArgs& p, const Sub2& sc, int n_base,
-                                               uint32_t t_row, uint8_t* wstage, float* wvec, int& sbuf,
+                                               int nchunks, uint32_t t_row, uint8_t* wstage, float* wvec, int& sbuf,
                                                uint32_t tempty_leader, int q, int lane, int half, bool prof_warp,
                                                long long& prof_ld, long long& prof_st, const uint4 (&rres_all)[4][4]) {
   constexpr int kCols = 32;
-  constexpr int kChunks = kH2BlockN / kCols;   // 8; this warp handles chunks half, half+2, ...
+  constexpr int kChunks = kH2BlockN / kCols;   // up to 8 (nchunks of them in this item); this warp handles chunks half, half+2, ...
   const int row = q * 32 + lane;
   const bool sub_ok = sc.n < p.N;
   const bool has_res = p.res != nullptr;
@@ -100,9 +114,11 @@ __device__ __forceinline__ void halo2_epilogue(const Halo2Tmaps& tm, const Halo2
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < kH2BlockN / 32; ++j) {
-    const int col = n_base + j * 32 + lane;
-    wvec[j * 32 + lane] = p.scale ? __ldg(p.scale + col) : 1.f;
-    wvec[kH2BlockN + j * 32 + lane] = p.bias ? __ldg(p.bias + col) : 0.f;
+    if (j < nchunks) {
+      const int col = n_base + j * 32 + lane;
+      wvec[j * 32 + lane] = p.scale ? __ldg(p.scale + col) : 1.f;
+      wvec[kH2BlockN + j * 32 + lane] = p.bias ? __ldg(p.bias + col) : 0.f;
+    }
   }
   __syncwarp();
 
@@ -112,7 +128,7 @@ __device__ __forceinline__ void halo2_epilogue(const Halo2Tmaps& tm, const Halo2
     const int cl = c * kCols;
     const int cg0 = n_base + cl;
     const bool beyond = cg0 >= p.Cout_store || !sub_ok;
-    const bool last = (c + 2 >= kChunks) || (cg0 + 2 * kCols >= p.Cout_store);
+    const bool last = (c + 2 >= nchunks) || (cg0 + 2 * kCols >= p.Cout_store);
     if (beyond) {
       tc_fence_before_sync();
       __syncwarp();
@@ -179,6 +195,16 @@ template <bool kBf16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kH2Threads, 1)
 conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) {
   griddep_launch_dependents();
+  // profile build: wall-clock (globaltimer, ns) of kernel entry / prologue end / role-loop end / exit, min and max over CTAs
+  auto stamp = [&](int lo, int hi) {
+    if (kH2Prof && p.prof && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (lo >= 0) atomicMin(p.prof + lo, t);
+      if (hi >= 0) atomicMax(p.prof + hi, t);
+    }
+  };
+  stamp(8, 9);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_base = smem;
@@ -204,6 +230,7 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tm.a);
     tma_prefetch_desc(&tm.b);
+    tma_prefetch_desc(&tm.bs);
     tma_prefetch_desc(&tm.y);
     for (int i = 0; i < kH2AStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < kH2BStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
@@ -216,16 +243,23 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   griddep_wait();   // PDL: everything above overlapped the previous kernel's tail; its results are visible from here on
+  stamp(-1, 10);
 
   if (warp_idx == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs, own halves)
     if (lane == 0) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+        const Item2 it = item2_decode(p, item);
+        const int tile = it.tile;
         const unsigned mt = fd_div((unsigned)tile, p.fd_nblocks);
         const int nblk = tile - (int)(mt * p.fd_nblocks.div);
         const Sub2 sc = sub2_coord(p, mt * 2 + rank);
+        const bool whole = it.ncols == kH2BlockN;
+        const CUtensorMap* bmap = whole ? &tm.b : &tm.bs;
+        const uint32_t b_bytes = (uint32_t)it.ncols * 128u;              // both halves: ncols rows of 128 B
+        const int b_row = nblk * kH2BlockN + it.ncol0 + (int)rank * (it.ncols >> 1);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(&a_empty[as], aph ^ 1);
           if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * kH2HaloBytes);
@@ -233,9 +267,8 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
           if (++as == kH2AStages) { as = 0; aph ^= 1; }
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_empty[bs], bph ^ 1);
-            if (leader) mbar_arrive_expect_tx(&b_full[bs], 2 * kH2BSlot);
-            tma_load_3d_2sm(b_base + bs * kH2BSlot, &tm.b, leader_smem_addr(&b_full[bs]), kc * 64, tap,
-                            nblk * kH2BlockN + rank * 128);
+            if (leader) mbar_arrive_expect_tx(&b_full[bs], b_bytes);
+            tma_load_3d_2sm(b_base + bs * kH2BSlot, bmap, leader_smem_addr(&b_full[bs]), kc * 64, tap, b_row);
             if (++bs == kH2BStages) { bs = 0; bph ^= 1; }
           }
         }
@@ -244,7 +277,8 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
   } else if (warp_idx == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(256, kH2BlockN, kBf16 ? 1 : 0);
+      const uint32_t idesc_whole = umma_idesc_f16(256, kH2BlockN, kBf16 ? 1 : 0);
+      const uint32_t idesc_split = umma_idesc_f16(256, kH2BlockN >> p.tail_lg, kBf16 ? 1 : 0);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int tl = 0;
@@ -252,7 +286,8 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
       const long long t_begin = (kH2Prof && p.prof) ? clock64() : 0;
 #define H2WAIT(bar, ph, var) do { const long long t0 = (kH2Prof && p.prof) ? clock64() : 0; mbar_wait(bar, ph); \
                                   if (kH2Prof && p.prof) var += clock64() - t0; } while (0)
-      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++tl) {
+      for (int item = cluster_id; item < p.num_items; item += num_clusters, ++tl) {
+        const uint32_t idesc = item < p.full_items ? idesc_whole : idesc_split;
         const int acc = tl & 1;
         H2WAIT(&tempty[acc], ((tl >> 1) & 1) ^ 1, w_acc);
         tc_fence_after_sync();
@@ -301,7 +336,10 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
     const bool prof_warp = leader && ew == 0;
     long long prof_ld = 0, prof_st = 0, prof_wait = 0;
     const long long t_begin = (kH2Prof && p.prof) ? clock64() : 0;
-    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++tl) {
+    for (int item = cluster_id; item < p.num_items; item += num_clusters, ++tl) {
+      const Item2 it = item2_decode(p, item);
+      const int tile = it.tile;
+      const int nchunks = it.ncols >> 5;
       const int acc = tl & 1;
       const unsigned mt = fd_div((unsigned)tile, p.fd_nblocks);
       const int nblk = tile - (int)(mt * p.fd_nblocks.div);
@@ -318,12 +356,13 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
         const long long pix = (static_cast<long long>(sc.n) * p.H + ho) * p.W + wo;
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
-          const int c0 = nblk * kH2BlockN + (half + 2 * ci) * 32;
+          const int c0 = nblk * kH2BlockN + it.ncol0 + (half + 2 * ci) * 32;
           const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (pix * p.res_pix_stride + c0) * 2;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             rres_all[ci][j] = make_uint4(0u, 0u, 0u, 0u);
-            if (pix_ok && c0 + j * 8 < p.Cout_store) rres_all[ci][j] = __ldg(reinterpret_cast<const uint4*>(rp) + j);
+            if (pix_ok && half + 2 * ci < nchunks && c0 + j * 8 < p.Cout_store)
+              rres_all[ci][j] = __ldg(reinterpret_cast<const uint4*>(rp) + j);
           }
         }
       }
@@ -334,7 +373,7 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
       }
       tc_fence_after_sync();
 #define DYK_H2EPI(ACT) \
-  halo2_epilogue<kBf16, ACT>(tm, p, sc, nblk * kH2BlockN, t_row, wstage, wvec, sbuf, tempty_leader, q, lane, half, \
+  halo2_epilogue<kBf16, ACT>(tm, p, sc, nblk * kH2BlockN + it.ncol0, nchunks, t_row, wstage, wvec, sbuf, tempty_leader, q, lane, half, \
                              prof_warp, prof_ld, prof_st, rres_all)
       switch (p.act) {
         case DYK_ACT_LEAKY: DYK_H2EPI(DYK_ACT_LEAKY); break;
@@ -358,8 +397,10 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
   }
 
   tc_fence_before_sync();
+  if (kH2Prof) { __syncthreads(); stamp(12, 11); }
   cluster_sync_all();      // the peer's barriers / smem stay valid until the leader's last multicast commit landed
   if (warp_idx == 1) tmem_dealloc_2sm<512>(tmem_base);
+  stamp(-1, 13);
 }
 
 template <bool kBf16>
@@ -371,7 +412,7 @@ static int launch_halo2(const Halo2Tmaps& tm, const Halo2KArgs& ka, cudaStream_t
     configured = true;
   }
   int clusters = num_sms() / 2;
-  if (ka.num_tiles < clusters) clusters = ka.num_tiles;
+  if (ka.num_items < clusters) clusters = ka.num_items;
   DYK_CUDA_OK(launch_pdl(kern, dim3(2 * clusters), dim3(kH2Threads), (size_t)kH2Total, stream, tm, ka));
   DYK_LAUNCH_OK("conv3x3_halo2_kernel");
   return DYK_OK;
@@ -422,6 +463,33 @@ int conv3x3_halo2_try(const dyk_conv_params* p, cudaStream_t stream) {
   ka.num_subs = (int)num_subs;
   ka.n_blocks = n_blocks;
   ka.num_tiles = (int)(ceil_div64(num_subs, 2) * n_blocks);
+  {
+    // split the tiles of the last partial round.  Measured (tools/conv_bench.py, DYK_H2_TAIL=1|2|4): an item of N = 128
+    // still takes ~0.9 of a whole tile's time and one of N = 64 more than a whole tile on deep layers — an item walks
+    // the same number of pipeline steps (k-chunks x 9 taps) and each step has a latency floor of ~400 cycles (TMA ->
+    // full barrier -> MMA -> commit -> empty barrier), so narrowing N barely shortens it.  Worth 2 us on the 55 us
+    // layers (256->512 @32x40: 57.3 -> 55.3 us); the real fix for the partial round is a split along K.
+    static const int force = getenv("DYK_H2_TAIL") ? atoi(getenv("DYK_H2_TAIL")) : 0;   // 1, 2, 4 force; 0 = cost model
+    const int clusters = num_sms() / 2;
+    const int tail = ka.num_tiles % clusters;
+    int lg = 0;
+    if (tail > 0) {
+      const double cost[3] = {1.0, 0.9, 1.2};
+      double best = 1e9;
+      for (int l = 0; l < 3; ++l) {
+        const double est = ceil_div(tail << l, clusters) * cost[l];
+        if (est < best - 1e-9) { best = est; lg = l; }
+      }
+      if (force == 1) lg = 0; else if (force == 2) lg = 1; else if (force == 4) lg = 2;
+    }
+    ka.tail_lg = lg;
+    ka.full_items = ka.num_tiles - tail;
+    ka.num_items = ka.full_items + (tail << lg);
+    const cuuint64_t dims[3] = {(cuuint64_t)p->Cin, 9, (cuuint64_t)p->Cout};
+    const cuuint64_t str[2] = {(cuuint64_t)p->Cin * 2, (cuuint64_t)p->Cin * 2 * 9};
+    const cuuint32_t box[3] = {64, 1, (cuuint32_t)(128 >> lg)};
+    if ((rc = encode_map_generic(&tm.bs, p->w, 3, dims, str, box, 128, "halo2 B (split)"))) return rc;
+  }
   ka.k_chunks = ceil_div(p->Cin, 64);
   ka.Cout_store = p->Cout_store;
   ka.act = p->act;

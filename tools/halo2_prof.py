@@ -18,7 +18,7 @@ for (N, Cin, H, W, Cout, res) in [(16, 128, 64, 80, 256, True), (16, 256, 32, 40
     sc, bi = torch.ones(2048, device="cuda"), torch.zeros(2048, device="cuda")
     for _ in range(2):
         ops.nhwc_conv(x, w, sc, bi, y, k=3, stride=1, pad=1, act="leaky", res=r)
-    prof = torch.zeros(8, dtype=torch.int64, device="cuda")
+    prof = torch.zeros(16, dtype=torch.int64, device="cuda"); prof[8] = 1 << 62; prof[12] = 1 << 62
     nat.call("dyk_conv_set_profile", C.c_void_p(prof.data_ptr()))
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); ops.nhwc_conv(x, w, sc, bi, y, k=3, stride=1, pad=1, act="leaky", res=r); b.record()
@@ -31,3 +31,7 @@ for (N, Cin, H, W, Cout, res) in [(16, 128, 64, 80, 256, True), (16, 256, 32, 40
     print(f"{Cin}->{Cout} {H}x{W} res={int(res)}: {a.elapsed_time(b) * 1e3:7.1f} us  clusters {n} tiles/cluster {tpc:.2f} | MMA loop {p[2] / n:8.0f} cyc "
           f"(wait data {p[0] / max(p[2], 1):4.0%}, wait acc {p[1] / max(p[2], 1):4.0%}) | epilogue total {p[4] / n:8.0f} cyc: wait acc {p[3] / max(p[4], 1):4.0%}, "
           f"tmem ld {p[5] / max(p[4], 1):4.0%}, store-buffer wait {p[6] / max(p[4], 1):4.0%}, busy/tile {(p[4] - p[3]) / n / tpc:7.0f} cyc")
+    t0 = p[8]
+    print(f"      timeline (globaltimer, us after the first CTA's entry): last entry {(p[9] - t0) / 1e3:5.1f} | last prologue end "
+          f"{(p[10] - t0) / 1e3:5.1f} | role loops end: first CTA {(p[12] - t0) / 1e3:5.1f}, last CTA {(p[11] - t0) / 1e3:5.1f} | last exit "
+          f"{(p[13] - t0) / 1e3:5.1f}")
