@@ -1,11 +1,11 @@
 """Hot-path part of the reference's build_utils/utils.py: ``non_max_suppression`` (utils.py:387-464),
-``xywh2xyxy`` (:50-57) and ``get_yolo_layers`` (:467-469).
+``xywh2xyxy`` (:50-57), ``get_yolo_layers`` (:467-469), and the training loss ``compute_loss`` / ``build_targets``
+(:209-384), which runs as fused native kernels (dyk/loss.py, csrc/yolo_loss.cu).
 
 ``non_max_suppression`` keeps the reference's signature and its list-of-(n,6)-tensors-or-None return
 contract but processes the whole batch with three native kernel launches (csrc/nms.cu) instead of a
-per-image Python loop around torchvision.ops.nms.  The loss / target-building half of the reference file
-is a caller of the hot path, not part of it and is not re-implemented here; see
-INTEGRATION.md for how to bind this function into an unmodified reference checkout.
+per-image Python loop around torchvision.ops.nms.  See INTEGRATION.md for how to bind these functions into an
+unmodified reference checkout.
 
 Deliberate difference: the reference aborts after a 10 s wall-clock budget and leaves later images as
 None (utils.py:400,461-462), which makes its output timing dependent; the batched kernels have no such
@@ -17,8 +17,9 @@ import torch
 
 from dyk import _native as nat
 from dyk import ops as _ops
+from dyk.loss import build_targets, compute_loss
 
-__all__ = ['non_max_suppression', 'xywh2xyxy', 'get_yolo_layers']
+__all__ = ['non_max_suppression', 'xywh2xyxy', 'get_yolo_layers', 'compute_loss', 'build_targets']
 
 _workspaces = {}
 

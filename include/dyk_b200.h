@@ -274,6 +274,31 @@ int dyk_dwconv2d_wgrad(const void* x, int64_t x_pix_stride, const void* dz, int6
                        int32_t H, int32_t W, int32_t C, int32_t k, int32_t stride, int32_t pad, int32_t accumulate,
                        int32_t dtype, float* workspace, void* stream);
 
+/* ---- training loss of the YOLO heads (build_utils/utils.py:209-384: compute_loss + build_targets; bbox_iou :95-138,
+ * wh_iou :166-172), forward and gradient fused, one head per call, no host synchronisation.
+ *
+ * dyk_yolo_build_targets: targets [nt][6] fp32 (image, class, x, y, w, h normalised) against the na anchors of one head
+ *   (anchor_vec = anchors / stride) on an ny x nx grid; positives in the reference's anchor-major order:
+ *   *count (device) = nb, idx[k] = (b, a, gj, gi), tbox[k] = (gx - gi, gy - gj, gw, gh), tcls[k].  Arrays hold na*nt entries.
+ * dyk_yolo_loss_head: p, dp fp32 [B][na][ny][nx][no].  dp is fully written with d(w_box*lbox + w_obj*lobj + w_cls*lcls)/dp of
+ *   this head (box channels 0-3, objectness 4, classes 5+; class loss only when no > 6 as in the reference's nc > 1).
+ *   acc[3] (device, zeroed by the caller before the first head) accumulates the per-head means; with finalize != 0 the
+ *   call also writes out[3] = acc * (w_box, w_obj, w_cls) (utils.py:296-298).  ciou selects CIoU (hyp has the key 'ciou')
+ *   or GIoU; gr = model.gr; focal loss (fl_gamma > 0) is not implemented.  err (device int) is set to 1 when a target
+ *   indexes outside the batch / grid, 2 when a class id is >= nc (the reference raises for both).
+ *   workspace: dyk_yolo_loss_workspace_floats(max_pos = na*nt, no, cells = B*na*ny*nx) floats.
+ * dyk_yolo_loss_scale_grad: out = dp * upstream[group of the channel] (upstream = 3 device floats: grads of the box / obj /
+ *   class loss outputs), the backward of the autograd node. */
+int dyk_yolo_build_targets(const float* targets, int32_t nt, const float* anchor_vec, int32_t na, int32_t ny, int32_t nx,
+                           float iou_t, int32_t* count, int32_t* idx, float* tbox, int32_t* tcls, void* stream);
+int64_t dyk_yolo_loss_workspace_floats(int32_t max_pos, int32_t no, int64_t cells);
+int dyk_yolo_loss_head(const float* p, float* dp, int32_t B, int32_t na, int32_t ny, int32_t nx, int32_t no,
+                       const int32_t* count, const int32_t* idx, const float* tbox, const int32_t* tcls,
+                       const float* anchor_vec, int32_t max_pos, int32_t v4, int32_t ciou, float gr, float obj_pw, float cls_pw,
+                       float w_box, float w_obj, float w_cls, float* acc, int32_t finalize, float* out, int32_t* err,
+                       float* workspace, void* stream);
+int dyk_yolo_loss_scale_grad(const float* dp, float* out, int64_t n, int32_t no, const float* upstream, void* stream);
+
 /* ---- layout / packing helpers ---------------------------------------------------------------------
  * pack: OIHW fp32 (state_dict layout, models.py:35) -> [O][kh][kw][I] dtype.
  */
