@@ -206,12 +206,14 @@ def conv_flops_per_frame(model, Hh, Ww):
 
 
 def run_train(args, rank, local, world, dev):
-    """BASELINE configs[2]: one optimizer step = forward (batch-statistics BN) + synthetic loss + backward + gradient
-    all-reduce over NCCL + SGD(momentum, nesterov) update, batch 16 per GPU, bf16 storage / fp32 accumulation.
-    The loss (a caller of the path) is a plain torch expression over the three head tensors."""
+    """BASELINE configs[2]: one optimizer step = forward (batch-statistics BN) + compute_loss on synthetic labels + backward
+    + gradient all-reduce over NCCL + SGD(momentum, nesterov) update, batch 16 per GPU, bf16 storage / fp32 accumulation.
+    The loss is the native compute_loss (reference build_utils/utils.py:209-384) with the reference's
+    hyp.scratch.4.yaml weights; labels as SURVEY §8d: 3 boxes per frame, cls 0, xy~U(.1,.9), w~U(.03,.1), h~U(.1,.3)."""
     import torch.distributed as dist
     import models
     from dyk import _native as nat
+    from build_utils.utils import compute_loss
     from dyk import cfg_zoo, dist_utils
 
     path = cfg_zoo.materialize(args.cfg)
@@ -225,10 +227,23 @@ def run_train(args, rank, local, world, dev):
     ring = 2
     host = [tuple(t.pin_memory() for t in synthetic_frames(B, seed=1000 * rank + i)) for i in range(ring)]
     resident = [(v.to(dev), l.to(dev)) for v, l in host]
+    model.nc, model.gr = 1, 1.0
+    model.hyp = {"box": 3.54, "cls": 37.4, "obj": 64.3, "cls_pw": 1.0, "obj_pw": 1.0, "iou_t": 0.20, "fl_gamma": 0.0}
+    if "yolov4" in model.cfg:
+        model.hyp["ciou"] = 1.0
+    g = torch.Generator().manual_seed(1 + rank)
+    nt = 3 * B
+    labels = torch.zeros((nt, 6))
+    labels[:, 0] = torch.arange(nt) // 3
+    labels[:, 2:4] = torch.rand((nt, 2), generator=g) * 0.8 + 0.1
+    labels[:, 4] = torch.rand((nt,), generator=g) * 0.07 + 0.03
+    labels[:, 5] = torch.rand((nt,), generator=g) * 0.2 + 0.1
+    labels = labels.to(dev)
 
     def step(v, l):
         p = model(v, l) if dual else model(v)
-        loss = sum((t.float() ** 2).mean() for t in p)
+        parts = compute_loss(p, labels, model)
+        loss = parts["box_loss"] + parts["obj_loss"] + parts["class_loss"]
         opt.zero_grad(set_to_none=True)
         loss.backward()
         dist_utils.allreduce_gradients(params)
@@ -284,8 +299,8 @@ def run_train(args, rank, local, world, dev):
             "value": world * B * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"{args.cfg} {W}x{H} train step, batch {B}/GPU, default-initialised weights, synthetic "
-                                   "squared-logit loss, SGD nesterov", "batch_per_gpu": B, "global_batch": B * world,
+            "config": {"workload": f"{args.cfg} {W}x{H} train step, batch {B}/GPU, default-initialised weights, native "
+                                   "compute_loss (CIoU + objectness BCE) on 3 synthetic labels per frame, SGD nesterov", "batch_per_gpu": B, "global_batch": B * world,
                        "parallelism": f"dp{world} (replicas; one flat-bucket gradient all-reduce per step)",
                        "l2": "activations saved for backward (tens of GB) exceed the 126 MB L2; no explicit flush"},
             "clocks": clocks,
