@@ -183,14 +183,38 @@ def conv_breakdown(plan, x, y, iters=3):
     other_ms = sum(t for t, s in zip(mean, plan.steps) if not isinstance(s, _ConvStep))
     flops = 0.0
     n_conv = 0
-    for s in plan.steps:
+    dom = {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0}      # launches that dispatch to conv3x3_halo2_kernel
+    for t, s in zip(mean, plan.steps):
         if isinstance(s, _ConvStep):
             n_conv += 1
             k = s.kw["k"]
             up = 4 if s.kw["upsample2x"] else 1
             opix = s.y.N * s.y.H * s.y.W // up
-            flops += 2.0 * opix * s.e["conv"].out_channels * s.x.C * k * k
-    return conv_ms, other_ms, flops, n_conv
+            cout = s.e["conv"].out_channels
+            fl = 2.0 * opix * cout * s.x.C * k * k
+            flops += fl
+            if uses_halo2(s):
+                dom["ms"] += t
+                dom["flops"] += fl
+                dom["n"] += 1
+                res = 1 if s.kw.get("res") is not None else 0
+                dom["bytes"] += 2.0 * (s.x.N * s.x.H * s.x.W * s.x.C + opix * cout * (1 + res) + cout * s.x.C * k * k)
+    return conv_ms, other_ms, flops, n_conv, dom
+
+
+def uses_halo2(step):
+    """Mirror of the dispatch rule in csrc/conv_halo2.cu (conv3x3_halo2_try): 3x3 stride-1 pad-1 layers with >= 256 stored
+    output channels, >= 64 input channels and a spatial size that fills >= 60 % of the 8x16-pixel sub-tiles."""
+    kw = step.kw
+    if os.environ.get("DYK_HALO2", "1") == "0" or os.environ.get("DYK_NO_HALO", "0") == "1":
+        return False
+    if not (kw["k"] == 3 and kw["stride"] == 1 and kw["pad"] == 1 and not kw["upsample2x"] and not kw.get("out_f32", False)):
+        return False
+    x, y = step.x, step.y
+    if y.C < 256 or x.C < 64:
+        return False
+    eff = x.W * x.H / (-(-x.W // 8) * 8 * -(-x.H // 16) * 16)
+    return eff >= 0.6
 
 
 def conv_flops_per_frame(model, Hh, Ww):
@@ -328,6 +352,14 @@ def conv_dram_traffic(cfg, B):
     return None
 
 
+def halo2_dram_traffic(cfg, B):
+    """DRAM bytes of the conv3x3_halo2_kernel launches of one step (52 launches, 2.008 GB read + 0.080 GB written) from
+    the committed ncu capture of this workload; None for workloads that were not captured."""
+    if cfg == "kaist_dyolov3_add_sl.cfg" and B == 16:
+        return 2.088e9
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -452,9 +484,13 @@ def main():
     if rank == 0:
         plan = model._plans.last_plan
         v, l = resident[0]
-        conv_ms, other_ms, flops, n_conv = conv_breakdown(plan, v, l if dual else None)
+        conv_ms, other_ms, flops, n_conv, dom = conv_breakdown(plan, v, l if dual else None)
         peak_tf, peak_gb, peak_kind = peaks()
-        achieved = flops / (conv_ms / 1e3) / 1e12
+        achieved_all = flops / (conv_ms / 1e3) / 1e12
+        if dom["n"]:
+            achieved = dom["flops"] / (dom["ms"] / 1e3) / 1e12
+        else:                      # models without a CTA-pair layer (MobileNet): all dense convs together
+            achieved, dom = achieved_all, {"ms": conv_ms, "flops": flops, "bytes": None, "n": n_conv}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -472,13 +508,21 @@ def main():
                     "h2d_bytes_per_step": 2 * B * 3 * H * W, "d2h_bytes_per_step": B * 100 * 6 * 4 + B * 4},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": conv_dram_traffic(args.cfg, B), "peak_source": peak_kind,
-                         "traffic_note": "DRAM read+write bytes of all conv launches of one step (ncu dram__bytes_*; "
-                                         "profiles/r01_dram_traffic_dyolov3.txt); the step's algorithmic bytes are 11.04e9",
-                         "kernel": "conv_tc_kernel / conv3x3_halo*_kernel / stem_tc_kernel (tcgen05 implicit GEMM, all dense "
-                                   "convs of the step; a launch = one layer, figures are per step)",
-                         "launches_per_step": n_conv, "conv_ms_per_step": conv_ms, "other_kernels_ms_per_step": other_ms,
-                         "algorithmic_gflop_per_step": flops / 1e9},
+                         "frac": achieved / peak_tf, "traffic": halo2_dram_traffic(args.cfg, B) if dom["bytes"] else None,
+                         "peak_source": peak_kind,
+                         "kernel": "conv3x3_halo2_kernel (tcgen05 cta_group::2 implicit GEMM, the 3x3 stride-1 layers with "
+                                   ">= 256 output channels): the dominant kernel of the step by time",
+                         "note": "a launch = one layer, so figures are sums over the kernel's launches of one step: "
+                                 "achieved = algorithmic FLOPs / summed CUDA-event durations (each launch bracketed on "
+                                 "the launching stream, run eagerly, so launch latency is inside the brackets); traffic = "
+                                 "ncu dram__bytes_read.sum + dram__bytes_write.sum of the same launches "
+                                 "(profiles/r01_dram_traffic_dyolov3.txt)",
+                         "launches_per_step": dom["n"], "kernel_ms_per_step": dom["ms"],
+                         "algorithmic_gflop_per_step": dom["flops"] / 1e9, "algorithmic_bytes_per_step": dom["bytes"],
+                         "all_dense_convs": {"achieved": achieved_all, "frac": achieved_all / peak_tf, "launches_per_step": n_conv,
+                                             "ms_per_step": conv_ms, "algorithmic_gflop_per_step": flops / 1e9,
+                                             "traffic": conv_dram_traffic(args.cfg, B)},
+                         "other_kernels_ms_per_step": other_ms},
             "cuda_graph": plan.graph is not None,
         }
         if not args.no_cpu_baseline:
