@@ -60,12 +60,18 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        """Call when the timed region starts: only samples taken from here on are reported.  (The process itself is
+        started before the warm-up: nvidia-smi's start-up attaches to the driver and was seen to stall kernel launches
+        for tens of milliseconds when it coincided with the timed region.)"""
+        self.first = len(self.rows)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:  # noqa: BLE001
@@ -78,11 +84,14 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        rows = self.rows[self.first:]
+        if not rows:                   # timed region shorter than one sampling period: keep the GPU busy state's last sample
+            time.sleep(0.06)
+            rows = self.rows[-1:]
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             parts = [p.strip() for p in r.split(",")]
             if len(parts) < 6:
                 continue
@@ -297,12 +306,14 @@ def run_train(args, rank, local, world, dev):
         barrier()
         return dist_utils.max_over_ranks(e0.elapsed_time(e1), dev)
 
-    for i in range(args.warmup):
-        step_resident(i)
-    step_e2e(0)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        step_resident(i)
+    step_e2e(0)
+    torch.cuda.synchronize()
+    sampler.mark()
     l0 = nat.launch_count()
     ms = timed(step_resident, args.steps)
     launches = nat.launch_count() - l0
@@ -461,6 +472,9 @@ def main():
             ms = float(t.item())
         return ms
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         step_resident(i)
     pipe.flush()
@@ -469,9 +483,7 @@ def main():
     pipe.flush()
     pipe._staged = None
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     l0 = nat.launch_count()
     ms = timed(step_resident, args.steps)
     launches = nat.launch_count() - l0

@@ -46,6 +46,7 @@ struct ConvKArgs {
   int num_tiles;
   int k_chunks;                    // ceil(Cin / BLOCK_K)
   int kh, kw, stride, pad;
+  int pair_w;                      // stride-2 Cin = 32 layers: two W-adjacent pixels form one 64-channel K block (see host)
   int Ho, Wo, N;
   int Cout_store;
   int act;
@@ -328,7 +329,17 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
           const int r = tap / p.kw, s = tap - r * p.kw;
           int dh = r - p.pad, dw = s - p.pad;
           int map_idx = 0;
-          if (p.stride == 2) {
+          int b_k0 = 0, b_tap = tap;
+          if (p.pair_w) {
+            // rows: parity planes as for any stride-2 conv; columns: pixel pairs (2j, 2j+1) are one 128-byte K block, tap
+            // s = 1 of the kw = 2 kernel covers original taps 1, 2 of pair j, tap s = 0 covers tap 0 = second pixel of
+            // pair j-1 (its first half meets zero weights: the B box starts 32 elements before the row, OOB = 0)
+            const int ph = dh & 1;
+            map_idx = ph * 2;
+            dh = (dh - ph) >> 1;
+            b_k0 = s == 0 ? -32 : 32;
+            b_tap = r;
+          } else if (p.stride == 2) {
             const int ph = dh & 1, pw = dw & 1;
             map_idx = ph * 2 + pw;
             dh = (dh - ph) >> 1;
@@ -347,7 +358,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
             uint8_t* sb = sa + S::kABytes;
             mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
             tma_load_4d(sa, amap, &full_bar[stage], kc * BLOCK_K, tc.w0 + dw, tc.h0 + dh, tc.n0);
-            tma_load_3d(sb, &tm.b, &full_bar[stage], kc * BLOCK_K, tap, tc.nblk * BLOCK_N);
+            tma_load_3d(sb, &tm.b, &full_bar[stage], kc * BLOCK_K + b_k0, b_tap, tc.nblk * BLOCK_N);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -609,7 +620,14 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
     if (hr <= 0) return hr;   // launched (0) or failed (< 0); 1 = not eligible
   }
 
-  const int BK = (p->Cin <= 32) ? 32 : 64;
+  // Stride-2 3x3 layers with 32 input channels (the first downsampling conv of every backbone, 335 MB in at 512x640 x 16)
+  // moved 64-byte rows per TMA request and ran at 2.0 TB/s.  With a dense input two W-adjacent pixels are 128 contiguous
+  // bytes, so the layer is run as a 3x2 convolution over pixel PAIRS with 64 "channels": 6 K blocks of 64 instead of 9 of
+  // 32, 128-byte rows; the weight tile of a tap is a window of the packed [Cout][3][3][32] rows (no re-packing).
+  static const bool pair_off = getenv("DYK_PAIR_W") != nullptr && getenv("DYK_PAIR_W")[0] == '0';
+  const bool pair_w = !pair_off && p->stride == 2 && p->kh == 3 && p->kw == 3 && p->pad == 1 && p->Cin == 32 &&
+                      p->x_pix_stride == 32 && p->W % 2 == 0 && !p->upsample2x && !p->y_plane && p->out_h == 0 && p->out_w == 0;
+  const int BK = (p->Cin <= 32 && !pair_w) ? 32 : 64;
   const int swz = BK * 2;
   ConvTmaps tm;
   ConvKArgs ka;
@@ -635,6 +653,15 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
     const cuuint64_t dims[4] = {(cuuint64_t)p->Cin, (cuuint64_t)gW, 1, 1};
     const cuuint64_t str[3] = {(cuuint64_t)xs, (cuuint64_t)xs * gW, (cuuint64_t)xs * gW};
     if ((rc = encode_map(&tm.a[0], p->x, 4, dims, str, abox, swz, "A/flat"))) return rc;
+  } else if (pair_w) {
+    for (int ph = 0; ph < 2; ++ph) {
+      const int Hp = (p->H - ph + 1) / 2;
+      if (Hp <= 0) continue;
+      const cuuint64_t dims[4] = {64, (cuuint64_t)(p->W / 2), (cuuint64_t)Hp, (cuuint64_t)p->N};
+      const cuuint64_t str[3] = {(cuuint64_t)xs * 2, (cuuint64_t)xs * p->W * 2, (cuuint64_t)xs * p->W * p->H};
+      const uint8_t* base = reinterpret_cast<const uint8_t*>(p->x) + (long long)ph * p->W * xs;
+      if ((rc = encode_map(&tm.a[ph * 2], base, 4, dims, str, abox, swz, "A/pair"))) return rc;
+    }
   } else if (p->stride == 1) {
     const cuuint64_t dims[4] = {(cuuint64_t)p->Cin, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->N};
     const cuuint64_t str[3] = {(cuuint64_t)xs, (cuuint64_t)xs * p->W, (cuuint64_t)xs * p->W * p->H};
@@ -650,15 +677,21 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
         if ((rc = encode_map(&tm.a[ph * 2 + pw], base, 4, dims, str, abox, swz, "A/parity"))) return rc;
       }
   }
-  const int taps = p->kh * p->kw;
+  const int taps = pair_w ? 6 : p->kh * p->kw;
+  const int cin_eff = pair_w ? 64 : p->Cin;
   const long long m_tiles = (long long)ceil_div(gW, tw) * ceil_div(gH, th) * ceil_div(gN, tn);
-  const int BN = pick_block_n(p->Cout_store, m_tiles, taps * ceil_div(p->Cin, BK), BK);
+  const int BN = pick_block_n(p->Cout_store, m_tiles, taps * ceil_div(cin_eff, BK), BK);
   // 16 epilogue warps when the tile time is the epilogue's: short main loop (<= 16 k-blocks) and an activation that costs
   // MUFU issue slots (Mish).  Measured: dyolov4 (Mish) 8.33 -> 8.09 ms, dyolov3 (leaky) 5.65 -> 5.75 ms, hence the act test.
   static const int force_split = getenv("DYK_EPI_SPLIT") ? atoi(getenv("DYK_EPI_SPLIT")) : 0;
-  int split = (taps * ceil_div(p->Cin, BK) <= 16 && BN >= 64 && !p->out_f32 && p->act == DYK_ACT_MISH) ? 4 : 2;
+  int split = (taps * ceil_div(cin_eff, BK) <= 16 && BN >= 64 && !p->out_f32 && p->act == DYK_ACT_MISH) ? 4 : 2;
   if (force_split == 2 || (force_split == 4 && BN >= 64)) split = force_split;
-  {
+  if (pair_w) {      // one filter row = 96 contiguous elements [s][c]; a tap's tile is a 64-element window of it
+    const cuuint64_t dims[3] = {96, 3, (cuuint64_t)p->Cout};
+    const cuuint64_t str[2] = {96 * 2, 288 * 2};
+    const cuuint32_t box[3] = {64, 1, (cuuint32_t)BN};
+    if ((rc = encode_map(&tm.b, p->w, 3, dims, str, box, swz, "B/pair"))) return rc;
+  } else {
     const cuuint64_t dims[3] = {(cuuint64_t)p->Cin, (cuuint64_t)taps, (cuuint64_t)p->Cout};
     const cuuint64_t str[2] = {(cuuint64_t)p->Cin * 2, (cuuint64_t)p->Cin * 2 * taps};
     const cuuint32_t box[3] = {(cuuint32_t)BK, 1, (cuuint32_t)BN};
@@ -701,8 +734,9 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   const long long nt = m_tiles * ka.n_blocks;
   DYK_REQUIRE(nt < (1ll << 31), "dyk_conv2d_fwd: too many tiles");
   ka.num_tiles = (int)nt;
-  ka.k_chunks = ceil_div(p->Cin, BK);
-  ka.kh = p->kh; ka.kw = p->kw; ka.stride = flat ? 1 : p->stride; ka.pad = p->pad;
+  ka.k_chunks = ceil_div(cin_eff, BK);
+  ka.kh = p->kh; ka.kw = pair_w ? 2 : p->kw; ka.stride = flat ? 1 : p->stride; ka.pad = p->pad;
+  ka.pair_w = pair_w ? 1 : 0;
   ka.Ho = gH; ka.Wo = gW; ka.N = gN;
   ka.Cout_store = p->Cout_store;
   ka.act = p->act;

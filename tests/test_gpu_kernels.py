@@ -44,7 +44,10 @@ CONV_CASES = [
     (2, 64, 16, 20, 64, 1, 1, "leaky", False, False, True),
     (2, 64, 16, 20, 128, 3, 1, "leaky", False, False, True),
     (2, 128, 16, 20, 128, 3, 1, "mish", True, False, True),
-    (1, 32, 32, 40, 64, 3, 2, "leaky", False, False, True),
+    (1, 32, 32, 40, 64, 3, 2, "leaky", False, False, True),      # Cin 32 stride 2: pixel-pair K blocks
+    (3, 32, 34, 46, 64, 3, 2, "mish", False, False, True),      # the same with ragged tiles
+    (2, 32, 31, 42, 128, 3, 2, "leaky", False, False, True),    # odd height
+    (2, 32, 30, 41, 64, 3, 2, "leaky", False, False, True),     # odd width: falls back to the parity-plane path
     (2, 64, 17, 23, 96, 3, 2, "mish", False, False, True),      # odd sizes: parity planes + edge clipping
     (2, 256, 8, 10, 512, 3, 1, "leaky", True, False, True),
     (2, 512, 4, 5, 256, 1, 1, "leaky", False, True, True),      # fused 2x upsample
