@@ -261,6 +261,10 @@ def run_train(args, rank, local, world, dev):
     host = [tuple(t.pin_memory() for t in synthetic_frames(B, seed=1000 * rank + i)) for i in range(ring)]
     resident = [(v.to(dev), l.to(dev)) for v, l in host]
     model.nc, model.gr = 1, 1.0
+    # gradient all-reduce overlapped with the backward pass (dyk.dist_utils.OverlappedAllReduce); DYK_OVERLAP=0 = after it
+    overlap = world > 1 and os.environ.get("DYK_OVERLAP", "1") != "0"
+    if overlap:
+        model.grad_reducer = dist_utils.OverlappedAllReduce()
     model.hyp = {"box": 3.54, "cls": 37.4, "obj": 64.3, "cls_pw": 1.0, "obj_pw": 1.0, "iou_t": 0.20, "fl_gamma": 0.0}
     if "yolov4" in model.cfg:
         model.hyp["ciou"] = 1.0
@@ -279,7 +283,8 @@ def run_train(args, rank, local, world, dev):
         loss = parts["box_loss"] + parts["obj_loss"] + parts["class_loss"]
         opt.zero_grad(set_to_none=True)
         loss.backward()
-        dist_utils.allreduce_gradients(params)
+        if not overlap:
+            dist_utils.allreduce_gradients(params)
         opt.step()
         return loss
 
@@ -336,7 +341,8 @@ def run_train(args, rank, local, world, dev):
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{args.cfg} {W}x{H} train step, batch {B}/GPU, default-initialised weights, native "
                                    "compute_loss (CIoU + objectness BCE) on 3 synthetic labels per frame, SGD nesterov", "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": f"dp{world} (replicas; one flat-bucket gradient all-reduce per step)",
+                       "parallelism": f"dp{world} (replicas; gradient all-reduce in flat buckets"
+                                      + (" overlapped with the backward pass)" if overlap else " after the backward pass)"),
                        "l2": "activations saved for backward (tens of GB) exceed the 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,

@@ -58,6 +58,7 @@ class TrainPlan:
             self.offsets[id(prm)] = off
             off += (prm.numel() + 31) // 32 * 32          # padded so vector kernels may write whole 32-float groups
         self.grad_numel = off
+        self.reducer = None      # set by TrainPlanCache from model.grad_reducer (dyk.dist_utils.OverlappedAllReduce)
         self._alloc_forward()
         self._bind_forward()
         self._bind_backward()
@@ -235,6 +236,7 @@ class TrainPlan:
 
         self.grads, self.consumers = grads, consumers
         self.bwd = []
+        self.bwd_writes = {}     # index into self.bwd -> parameters whose gradient that step writes
         max_z = max((st["z"].buf.numel() for st in self.convs if "z" in st), default=0)
         self.dz_scratch = torch.empty(max_z, dtype=self.dtype, device=self.device)
         conv_state = {id(st["op"]): st for st in self.convs}
@@ -264,6 +266,7 @@ class TrainPlan:
                     self.bwd.append(lambda flat, dps, d=dy, g=gv, a=acc, o=op, i=i:
                                     T.axpby(d, g, o.wall[i:i + 1] if o.wall is not None else None, a))
                 if m.weight:
+                    self.bwd_writes[len(self.bwd)] = [m.w]
                     self.bwd.append(lambda flat, dps, d=dy, o=op, mm=m:
                                     T.fusion_weights_bwd(d, o.x.view, o.others[0].view, mm.w.detach(), self._pgrad(flat, mm.w)))
             elif isinstance(op, P.ConcatOp):
@@ -290,7 +293,23 @@ class TrainPlan:
                     T.se_bwd(o.src.view, d, g, w1, b1, w2, b2, o.pooled, o.gate,
                              self._pgrad(flat, m.fc1.weight).view(w1.shape), self._pgrad(flat, m.fc1.bias),
                              self._pgrad(flat, m.fc2.weight).view(w2.shape), self._pgrad(flat, m.fc2.bias), a)
+                self.bwd_writes[len(self.bwd)] = [op.module.fc1.weight, op.module.fc1.bias, op.module.fc2.weight, op.module.fc2.bias]
                 self.bwd.append(se)
+        self._schedule_ready()
+
+    def _schedule_ready(self):
+        """ready_after[i] = flat ranges (lo, hi) whose gradients are final once bwd step i has been enqueued; ranges of
+        parameters no step writes (their gradient stays zero) are ready from the start (key -1).  Used to start the
+        gradient all-reduce of finished buckets while the rest of the backward still runs (dyk/dist_utils.py)."""
+        last = {}
+        for i, prms in self.bwd_writes.items():
+            for prm in prms:
+                last[id(prm)] = max(last.get(id(prm), -1), i)
+        self.ready_after = {}
+        for prm in self.params:
+            o = self.offsets[id(prm)]
+            n = (prm.numel() + 31) // 32 * 32
+            self.ready_after.setdefault(last.get(id(prm), -1), []).append((o, o + n))
 
     def _conv_bwd(self, st, dy, claim):
         op, conv, bn = st["op"], st["conv"], st["bn"]
@@ -323,14 +342,24 @@ class TrainPlan:
             T.conv_wgrad(op.src.view, dz, gw, k=k, stride=s, pad=p, accumulate=True, cout_real=cout_real)
             wd = T.pack_dgrad_weight(conv.weight, self.dtype, opad=dz.C)
             T.conv_dgrad(dz, wd, gv, k=k, stride=s, pad=p, accumulate=acc)
+        self.bwd_writes[len(self.bwd)] = [q for q in (conv.weight, conv.bias, bn.weight if bn is not None else None,
+                                                       bn.bias if bn is not None else None) if q is not None]
         self.bwd.append(run)
 
     def backward(self, dps):
         flat = torch.zeros(self.grad_numel, dtype=torch.float32, device=self.device)
         dps = [d.detach().float().contiguous() if d is not None else torch.zeros_like(po)
                for d, po in zip(dps, self.p_outs)]
-        for f in self.bwd:
+        reducer = self.reducer
+        if reducer is not None:
+            reducer.begin(flat, self.grad_numel)
+            reducer.feed(self.ready_after.get(-1, ()))
+        for i, f in enumerate(self.bwd):
             f(flat, dps)
+            if reducer is not None:
+                reducer.feed(self.ready_after.get(i, ()))
+        if reducer is not None:
+            reducer.finish()
         self.last_flat = flat
         return [self._pgrad(flat, prm) if prm.requires_grad else None for prm in self.params]
 
@@ -390,5 +419,6 @@ class TrainPlanCache:
                 plan = TrainPlan(model, B, H, W, dtype, y is not None, x.device)
             self.plans[key] = plan           # re-insert = most recently used
             self.last_plan = plan
+            plan.reducer = getattr(model, "grad_reducer", None)
             outs = _TrainFunction.apply(plan, x, y, *plan.params)
         return list(outs)

@@ -38,6 +38,28 @@ def _worker(rank, world, port, out):
     mean = sum(range(1, world + 1)) / world
     for i, p in enumerate(params):
         assert torch.allclose(p.grad, torch.full_like(p, mean * (i + 1)))
+    # contiguous views of one flat buffer are reduced in place (no temporary bucket)
+    flat = torch.arange(96, dtype=torch.float32) * (rank + 1)
+    views = [torch.nn.Parameter(torch.zeros(n)) for n in (32, 20, 32)]
+    for p_, (o, n) in zip(views, ((0, 32), (32, 20), (64, 32))):
+        p_.grad = flat[o:o + n]
+    assert du.allreduce_gradients(views, bucket_bytes=1 << 20) == 1
+    assert torch.allclose(flat[:52], torch.arange(52, dtype=torch.float32) * mean)
+    # overlapped all-reduce: ranges become final from the end of the buffer downwards (and slightly out of order);
+    # buckets are sent as soon as enough contiguous finished gradients exist, the rest at finish()
+    n = 4096
+    flat = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    red = du.OverlappedAllReduce(bucket_bytes=1024 * 4)
+    red.begin(flat, n)
+    red.feed([(3584, 4096)])
+    red.feed([(2048, 3072)])                 # not contiguous with the sent region yet
+    red.feed([(3072, 3584)])                 # closes the gap: [2048, 3584) can go
+    assert red.calls >= 1 and red.sent_lo == 2048
+    red.feed([(0, 1000)])
+    red.feed([(1000, 2048)])
+    red.finish()
+    assert red.sent_lo == 0 and not red.ready
+    assert torch.allclose(flat, torch.arange(n, dtype=torch.float32) * mean)
     du.barrier()
     out.put(rank)
 
