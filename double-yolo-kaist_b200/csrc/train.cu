@@ -10,6 +10,7 @@
 // All per-channel reductions are two-stage with a fixed slab order (no floating-point atomics), so training runs are
 // bit-reproducible.  Tensors are NHWC 16-bit with (base, pixel stride) addressing like the forward kernels.
 #include "common.h"
+#include <cstdlib>
 #include "vec.cuh"
 #include "act.cuh"
 
@@ -79,13 +80,18 @@ static inline ChanGeom chan_geom(int C) {
 //   kMode 2: part[slab][0][c] = sum a            (bias gradient)
 //   kMode 3: part[slab][0][c] = sum a*b          (per-channel dot, reduced over channels later: fusion-weight grads,
 //                                                 and with pixel ranges restricted to one image: SE gate grads)
+//   kMode 4: kMode 1 that also stores g (16-bit) to gout — for activations with an expensive derivative (Mish: the
+//            reduce and the apply pass were both bound by instruction issue, not by HBM), so the apply pass is a plain
+//            dz = cA*g + cD + cE*z over (g, z) and the exponential is evaluated once per element
 // Two pixels per thread are in flight per iteration; lanes of a warp that hold the same channels are combined with
 // shuffles, the 8 warps through shared memory — all in a fixed order.
 template <bool kBf16, int kMode>
-__global__ void __launch_bounds__(256, kMode == 1 ? 3 : 4)
+__global__ void __launch_bounds__(256, (kMode == 1 || kMode == 4) ? 3 : 4)
 chan_reduce_kernel(const uint8_t* __restrict__ a, long long as, const uint8_t* __restrict__ b, long long bs,
                    long long pix0, long long npix, int C, int slabs, int lg, const float* __restrict__ scale,
-                   const float* __restrict__ shift, const float* __restrict__ mean, int act, float* __restrict__ part) {
+                   const float* __restrict__ shift, const float* __restrict__ mean, int act, float* __restrict__ part,
+                   uint8_t* __restrict__ gout, long long gs) {
+  constexpr bool kBn = kMode == 1 || kMode == 4;
   const int L = 1 << lg, nplanes = 256 >> lg;
   const int cl = threadIdx.x & (L - 1), plane = threadIdx.x >> lg;
   const int cvec = blockIdx.x * L + cl;
@@ -94,7 +100,7 @@ chan_reduce_kernel(const uint8_t* __restrict__ a, long long as, const uint8_t* _
   const long long p0 = blockIdx.y * per;
   const long long p1 = p0 + per < npix ? p0 + per : npix;
   __shared__ __align__(16) float prm[3][64];
-  if constexpr (kMode == 1) {
+  if constexpr (kBn) {
     if (threadIdx.x < 3 * L * 8) {
       const int k = threadIdx.x / (L * 8), j = threadIdx.x - k * (L * 8);
       const int c = blockIdx.x * L * 8 + j;
@@ -108,9 +114,10 @@ chan_reduce_kernel(const uint8_t* __restrict__ a, long long as, const uint8_t* _
   for (int q = 0; q < 8; ++q) s0[q] = s1[q] = 0.f;
   if (live) {
     const uint8_t* pa = a + (pix0 + p0 + plane) * as * 2 + cvec * 16;
-    const uint8_t* pb = kMode == 1 || kMode == 3 ? b + (pix0 + p0 + plane) * bs * 2 + cvec * 16 : nullptr;
-    const long long sa = (long long)nplanes * as * 2, sb = (long long)nplanes * bs * 2;
-    auto accum = [&](const uint4& va, const uint4& vb) {
+    const uint8_t* pb = kBn || kMode == 3 ? b + (pix0 + p0 + plane) * bs * 2 + cvec * 16 : nullptr;
+    uint8_t* pg = kMode == 4 ? gout + (pix0 + p0 + plane) * gs * 2 + cvec * 16 : nullptr;
+    const long long sa = (long long)nplanes * as * 2, sb = (long long)nplanes * bs * 2, sg = (long long)nplanes * gs * 2;
+    auto accum = [&](const uint4& va, const uint4& vb, uint8_t* gdst) {
       float fa[8];
       unpack8<kBf16>(va, fa);
       if constexpr (kMode == 0) {
@@ -126,6 +133,7 @@ chan_reduce_kernel(const uint8_t* __restrict__ a, long long as, const uint8_t* _
 #pragma unroll
           for (int q = 0; q < 8; ++q) s0[q] = fmaf(fa[q], fb[q], s0[q]);
         } else {   // a = dy, b = z
+          float gv[8];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const float4 sc = *reinterpret_cast<const float4*>(&prm[0][cl * 8 + h * 4]);
@@ -136,10 +144,12 @@ chan_reduce_kernel(const uint8_t* __restrict__ a, long long as, const uint8_t* _
             for (int q = 0; q < 4; ++q) {
               const float z = fb[h * 4 + q];
               const float g = fa[h * 4 + q] * act_grad(fmaf(z, scv[q], shv[q]), act);
+              if constexpr (kMode == 4) gv[h * 4 + q] = g;    // stored rounded to 16 bits; the sums keep fp32
               s0[h * 4 + q] += g;
               s1[h * 4 + q] = fmaf(g, z - muv[q], s1[h * 4 + q]);
             }
           }
+          if constexpr (kMode == 4) *reinterpret_cast<uint4*>(gdst) = pack8<kBf16>(gv);
         }
       }
     };
@@ -149,20 +159,21 @@ chan_reduce_kernel(const uint8_t* __restrict__ a, long long as, const uint8_t* _
       const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(pa));
       const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(pa + sa));
       uint4 b0 = zero, b1 = zero;
-      if constexpr (kMode == 1 || kMode == 3) {
+      if constexpr (kBn || kMode == 3) {
         b0 = __ldg(reinterpret_cast<const uint4*>(pb));
         b1 = __ldg(reinterpret_cast<const uint4*>(pb + sb));
         pb += 2 * sb;
       }
       pa += 2 * sa;
-      accum(a0, b0);
-      accum(a1, b1);
+      accum(a0, b0, pg);
+      accum(a1, b1, pg + sg);
+      if constexpr (kMode == 4) pg += 2 * sg;
     }
     if (pidx < p1) {
       const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(pa));
       uint4 b0 = zero;
-      if constexpr (kMode == 1 || kMode == 3) b0 = __ldg(reinterpret_cast<const uint4*>(pb));
-      accum(a0, b0);
+      if constexpr (kBn || kMode == 3) b0 = __ldg(reinterpret_cast<const uint4*>(pb));
+      accum(a0, b0, pg);
     }
   }
   // lanes of a warp with equal cl -> lane cl (fixed xor tree), then the 8 warps in order
@@ -170,7 +181,7 @@ chan_reduce_kernel(const uint8_t* __restrict__ a, long long as, const uint8_t* _
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       s0[q] += __shfl_xor_sync(0xffffffffu, s0[q], off);
-      if constexpr (kMode <= 1) s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], off);
+      if constexpr (kMode <= 1 || kMode == 4) s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], off);
     }
   }
   __shared__ float red[2][8][64];
@@ -197,12 +208,12 @@ chan_reduce_kernel(const uint8_t* __restrict__ a, long long as, const uint8_t* _
 template <int kMode>
 static int launch_chan_reduce(int dtype, const void* a, long long as, const void* b, long long bs, long long pix0,
                               long long npix, int C, int slabs, const float* scale, const float* shift, const float* mean,
-                              int act, float* part, cudaStream_t stream) {
+                              int act, float* part, cudaStream_t stream, void* gout = nullptr, long long gs = 0) {
   const ChanGeom g = chan_geom(C);
   const dim3 grid(g.gx, slabs);
   DYK_DISPATCH_DTYPE(dtype, (chan_reduce_kernel<kBf16, kMode><<<grid, 256, 0, stream>>>(
                                 (const uint8_t*)a, as, (const uint8_t*)b, bs, pix0, npix, C, slabs, g.lg, scale, shift, mean,
-                                act, part)));
+                                act, part, (uint8_t*)gout, gs)));
   DYK_LAUNCH_OK("chan_reduce_kernel");
   return DYK_OK;
 }
@@ -314,11 +325,12 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int slabs, float count, c
   coef[2 * C + c] = (float)(cC * is);
 }
 
-template <bool kBf16>
+// kFromG: dy already holds g = dy*act'(zhat) (written by chan_reduce mode 4, possibly the dz buffer itself: in place)
+template <bool kBf16, bool kFromG>
 __global__ void __launch_bounds__(256, 3)
-bn_act_bwd_apply_kernel(const uint8_t* __restrict__ dy, long long dys, const uint8_t* __restrict__ z, long long zs,
+bn_act_bwd_apply_kernel(const uint8_t* dy, long long dys, const uint8_t* __restrict__ z, long long zs,
                         const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ coef,
-                        int C, int act, uint8_t* __restrict__ dz, long long dzs, long long npix, int lg) {
+                        int C, int act, uint8_t* dz, long long dzs, long long npix, int lg) {
   const int L = 1 << lg, nplanes = 256 >> lg;
   const int cvec = blockIdx.x * L + (threadIdx.x & (L - 1));
   if (cvec * 8 >= C) return;
@@ -341,21 +353,21 @@ bn_act_bwd_apply_kernel(const uint8_t* __restrict__ dy, long long dys, const uin
     unpack8<kBf16>(vz, fz);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float gg = g[q] * act_grad(fmaf(fz[q], ps[0][q], ps[1][q]), act);
+      const float gg = kFromG ? g[q] : g[q] * act_grad(fmaf(fz[q], ps[0][q], ps[1][q]), act);
       o[q] = fmaf(ps[2][q], gg, fmaf(ps[4][q], fz[q], ps[3][q]));
     }
     *(reinterpret_cast<uint4*>(dz + p * dzs * 2) + cvec) = pack8<kBf16>(o);
   };
   for (; pix + step < npix; pix += 2 * step) {
-    const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(dy + pix * dys * 2) + cvec);
+    const uint4 g0 = *(reinterpret_cast<const uint4*>(dy + pix * dys * 2) + cvec);      // plain loads: may alias dz
     const uint4 z0 = __ldg(reinterpret_cast<const uint4*>(z + pix * zs * 2) + cvec);
-    const uint4 g1 = __ldg(reinterpret_cast<const uint4*>(dy + (pix + step) * dys * 2) + cvec);
+    const uint4 g1 = *(reinterpret_cast<const uint4*>(dy + (pix + step) * dys * 2) + cvec);
     const uint4 z1 = __ldg(reinterpret_cast<const uint4*>(z + (pix + step) * zs * 2) + cvec);
     one(g0, z0, pix);
     one(g1, z1, pix + step);
   }
   if (pix < npix)
-    one(__ldg(reinterpret_cast<const uint4*>(dy + pix * dys * 2) + cvec), __ldg(reinterpret_cast<const uint4*>(z + pix * zs * 2) + cvec), pix);
+    one(*(reinterpret_cast<const uint4*>(dy + pix * dys * 2) + cvec), __ldg(reinterpret_cast<const uint4*>(z + pix * zs * 2) + cvec), pix);
 }
 
 // grid.y of the channel-fixed apply kernels: enough blocks to fill the GPU ~8 times over, at least 4 pixels per thread
@@ -704,6 +716,49 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, void* __restrict_
   }
 }
 
+// All convolution weights of a model in ONE launch: OIHW fp32 -> the forward layout [O][kh][kw][I] and the data-gradient
+// layout [I][kh][kw][Opad] (taps rotated by 180 degrees) from a single coalesced read.  A block owns a 32 x 32
+// (out-channel x in-channel) tile of one layer with all its taps in shared memory and writes >= 64-byte segments to both
+// destinations.  descs: device int64 [n][8] = (w, fwd, dgrad or 0, O, I, taps (<= 9), Opad, first tile of this layer).
+constexpr int kPackTaps = 9;
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+pack_multi_kernel(const long long* __restrict__ descs, int n) {
+  __shared__ float tile[32][32 * kPackTaps + 1];
+  int lo = 0, hi = n - 1;                                    // last layer whose first tile is <= blockIdx.x
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid * 8 + 7] <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const long long* d = descs + lo * 8;
+  const float* w = reinterpret_cast<const float*>(d[0]);
+  void* fwd = reinterpret_cast<void*>(d[1]);
+  void* dg = reinterpret_cast<void*>(d[2]);
+  const int O = (int)d[3], I = (int)d[4], taps = (int)d[5], Opad = (int)d[6];
+  const int t = blockIdx.x - (int)d[7];
+  const int tiles_i = (I + 31) / 32;
+  const int o0 = (t / tiles_i) * 32, i0 = (t % tiles_i) * 32;
+  const int no = min(32, O - o0), ni = min(32, I - i0);
+  const int row = ni * taps;
+  for (int e = threadIdx.x; e < no * row; e += 256) {
+    const int o = e / row, j = e - o * row;
+    tile[o][j] = __ldg(w + ((long long)(o0 + o) * I + i0) * taps + j);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < no * row; e += 256) {       // forward layout, in-channel fastest
+    const int ci = e % ni, r = e / ni;
+    const int tap = r % taps, o = r / taps;
+    store1<kBf16>(fwd, ((long long)(o0 + o) * taps + tap) * I + i0 + ci, tile[o][ci * taps + tap]);
+  }
+  if (dg != nullptr) {
+    for (int e = threadIdx.x; e < no * row; e += 256) {     // dgrad layout, out-channel fastest, taps reversed
+      const int o = e % no, r = e / no;
+      const int tap = r % taps, ci = r / taps;
+      store1<kBf16>(dg, ((long long)(i0 + ci) * taps + (taps - 1 - tap)) * Opad + o0 + o, tile[o][ci * taps + tap]);
+    }
+  }
+}
+
 }  // namespace dyk
 
 using namespace dyk;
@@ -750,14 +805,28 @@ DYK_EXPORT int dyk_bn_act_bwd(const void* dy, int64_t dys, const void* z, int64_
   const int slabs = slabs_for(npix);
   float* part = workspace;                                  // [slabs][2][C]
   float* coef = workspace + (size_t)kMaxSlabs * 2 * C;      // [3][C]
-  if (int rc = launch_chan_reduce<1>(dtype, dy, dys, z, zs, 0, npix, C, slabs, scale, shift, mean, act, part, stream)) return rc;
+  // expensive derivative: evaluate it once, store g in the dz buffer, apply in place (see chan_reduce mode 4)
+  static const bool g_off = getenv("DYK_BN_GSTORE") != nullptr && getenv("DYK_BN_GSTORE")[0] == '0';
+  const bool store_g = act == DYK_ACT_MISH && !g_off;
+  if (store_g) {
+    if (int rc = launch_chan_reduce<4>(dtype, dy, dys, z, zs, 0, npix, C, slabs, scale, shift, mean, act, part, stream, dz, dzs))
+      return rc;
+  } else {
+    if (int rc = launch_chan_reduce<1>(dtype, dy, dys, z, zs, 0, npix, C, slabs, scale, shift, mean, act, part, stream)) return rc;
+  }
   bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, stream>>>(part, slabs, (float)npix, gamma, mean, invstd, dgamma, dbeta, coef, C);
   DYK_LAUNCH_OK("bn_bwd_finalize_kernel");
   const ChanGeom g = chan_geom(C);
   const dim3 grid(g.gx, apply_grid_y(npix, g));
-  DYK_DISPATCH_DTYPE(dtype, (bn_act_bwd_apply_kernel<kBf16><<<grid, 256, 0, stream>>>(
-                                (const uint8_t*)dy, dys, (const uint8_t*)z, zs, scale, shift, coef, C, act, (uint8_t*)dz, dzs,
-                                npix, g.lg)));
+  if (store_g) {
+    DYK_DISPATCH_DTYPE(dtype, (bn_act_bwd_apply_kernel<kBf16, true><<<grid, 256, 0, stream>>>(
+                                  (const uint8_t*)dz, dzs, (const uint8_t*)z, zs, scale, shift, coef, C, act, (uint8_t*)dz, dzs,
+                                  npix, g.lg)));
+  } else {
+    DYK_DISPATCH_DTYPE(dtype, (bn_act_bwd_apply_kernel<kBf16, false><<<grid, 256, 0, stream>>>(
+                                  (const uint8_t*)dy, dys, (const uint8_t*)z, zs, scale, shift, coef, C, act, (uint8_t*)dz, dzs,
+                                  npix, g.lg)));
+  }
   DYK_LAUNCH_OK("bn_act_bwd_apply_kernel");
   return DYK_OK;
 }
@@ -883,6 +952,14 @@ DYK_EXPORT int dyk_pack_weights_dgrad(const float* w_oihw, void* w_packed, int32
   DYK_DISPATCH_DTYPE(dtype, (pack_dgrad_kernel<kBf16><<<grid_for_t((long long)I * kh * kw * Opad, 256), 256, 0,
                                                       static_cast<cudaStream_t>(stream_)>>>(w_oihw, w_packed, O, I, kh, kw, Opad)));
   DYK_LAUNCH_OK("pack_dgrad_kernel");
+  return DYK_OK;
+}
+
+DYK_EXPORT int dyk_pack_weights_multi(const int64_t* descs, int32_t n, int32_t total_tiles, int32_t dtype, void* stream_) {
+  DYK_REQUIRE(descs && n > 0 && total_tiles > 0, "dyk_pack_weights_multi: bad arguments");
+  DYK_DISPATCH_DTYPE(dtype, (pack_multi_kernel<kBf16><<<total_tiles, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+                                reinterpret_cast<const long long*>(descs), n)));
+  DYK_LAUNCH_OK("pack_multi_kernel");
   return DYK_OK;
 }
 

@@ -112,6 +112,14 @@ class TrainPlan:
                     self.bns.append(bn)
                 elif not op.out.f32:
                     raise nat.NativeError(f"layer {op.layer}: a convolution without BatchNorm must be a detection head")
+                if not st["stem"] and not st["dw"] and k * k <= 9 and conv.weight.dtype == torch.float32:
+                    # persistent packed copies, refreshed for all layers by one launch per step (_pack_all)
+                    O, I = conv.out_channels, conv.in_channels
+                    opad = O if bn is not None else HEAD_PAD
+                    st["w"] = torch.empty((O, k, k, I), dtype=self.dtype, device=dev)
+                    st["wd"] = torch.zeros((I, k, k, opad), dtype=self.dtype, device=dev)
+                    st["multi"] = True
+                    self.bytes_allocated += (st["w"].numel() + st["wd"].numel()) * 2
                 self.convs.append(st)
                 self.fwd.append(self._conv_fwd(st))
             elif isinstance(op, P.AddOp):
@@ -157,7 +165,8 @@ class TrainPlan:
                 st["w"] = T.dw_weight(conv)
                 ops.nhwc_dwconv(op.src.view, st["w"], None, None, st["z"], k=k, stride=s, pad=p, act="linear")
             else:
-                st["w"] = ops.pack_conv_weight(conv.weight, self.dtype)
+                if not st.get("multi"):
+                    st["w"] = ops.pack_conv_weight(conv.weight, self.dtype)
                 if bn is None:
                     st["bias"] = ops.pad_vec(conv.bias) if conv.bias is not None else None
                     ops.nhwc_conv(op.src.view, st["w"], None, st["bias"], op.out.view, k=k, stride=s, pad=p, act="linear",
@@ -182,7 +191,30 @@ class TrainPlan:
         steps.append(lambda x, y, o=op: ops.nhwc_add(o.x.view, o.others[0].view, o.out.view, o.wall))
         return steps
 
+    def _pack_all(self):
+        """One launch re-packs every dense convolution weight into its forward and data-gradient layouts (the optimizer
+        changed them since the last step).  The descriptor table holds raw pointers, so it is rebuilt whenever a
+        parameter's storage moved (.to(), load of a new tensor, ...)."""
+        sts = [st for st in self.convs if st.get("multi")]
+        if not sts:
+            return
+        sig = tuple(st["conv"].weight.data_ptr() for st in sts)
+        if getattr(self, "_pack_sig", None) != sig:
+            rows, tiles = [], 0
+            for st in sts:
+                wt = st["conv"].weight
+                if not wt.is_contiguous() or wt.dtype != torch.float32:
+                    raise nat.NativeError("convolution weights must be contiguous float32 parameters")
+                O, I, k = wt.shape[0], wt.shape[1], st["k"]
+                rows.append([wt.data_ptr(), st["w"].data_ptr(), st["wd"].data_ptr(), O, I, k * k, st["wd"].shape[3], tiles])
+                tiles += ((O + 31) // 32) * ((I + 31) // 32)
+            self._pack_desc = torch.tensor(rows, dtype=torch.int64).to(self.device)
+            self._pack_tiles, self._pack_sig = tiles, sig
+        nat.call("dyk_pack_weights_multi", ops._p(self._pack_desc), len(sts), self._pack_tiles, ops._DT[self.dtype], ops._stream())
+        nat.count_launches()
+
     def forward(self, x, y):
+        self._pack_all()
         for f in self.fwd:
             f(x, y)
         if self.bns:
@@ -340,7 +372,7 @@ class TrainPlan:
                 T.dwconv_dgrad(dz, st["w"], gv, k=k, stride=s, pad=p, accumulate=acc)
                 return
             T.conv_wgrad(op.src.view, dz, gw, k=k, stride=s, pad=p, accumulate=True, cout_real=cout_real)
-            wd = T.pack_dgrad_weight(conv.weight, self.dtype, opad=dz.C)
+            wd = st["wd"] if st.get("multi") else T.pack_dgrad_weight(conv.weight, self.dtype, opad=dz.C)
             T.conv_dgrad(dz, wd, gv, k=k, stride=s, pad=p, accumulate=acc)
         self.bwd_writes[len(self.bwd)] = [q for q in (conv.weight, conv.bias, bn.weight if bn is not None else None,
                                                        bn.bias if bn is not None else None) if q is not None]

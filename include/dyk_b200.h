@@ -250,6 +250,11 @@ int dyk_conv2d_wgrad(const void* x, int64_t x_pix_stride, const void* dz, int64_
                      int64_t workspace_bytes, void* stream);
 /* Cin_real / Cout_real: channels of the OIHW gradient actually written when x / dz carry zero-padded channels
  * (stem frames padded 3 -> 8, head logits padded 18 -> 32). */
+/* every convolution weight of a model in one launch (the weights change each optimizer step): descs is a DEVICE array
+ * int64 [n][8] = (w OIHW fp32 ptr, forward-layout ptr [O][kh][kw][I], dgrad-layout ptr [I][kh][kw][Opad] or 0, O, I,
+ * taps = kh*kw <= 9, Opad, index of this layer's first tile), tiles = ceil(O/32)*ceil(I/32) per layer in order,
+ * total_tiles their sum.  Rows O..Opad of the dgrad layout are not written (zero them once). */
+int dyk_pack_weights_multi(const int64_t* descs, int32_t n, int32_t total_tiles, int32_t dtype, void* stream);
 /* caller's NCHW fp32 / uint8 frames (as dyk_conv2d_stem_nchw_fwd, uint8 divided by 255) -> NHWC 16-bit with the channel
  * dimension zero-padded to 8, the operand layout the tensor-core wgrad kernel needs for the stem convolutions. */
 int dyk_frames_to_nhwc8(const void* x_nchw, void* y, int32_t N, int32_t Cin, int32_t H, int32_t W, int32_t dtype,

@@ -109,7 +109,20 @@ def compare_backward(plan, frames):
             g = bn.weight.detach().float().cpu().clone().requires_grad_(True)
             b = bn.bias.detach().float().cpu().clone().requires_grad_(True)
             z = _nchw(st["z"]).requires_grad_(True)
-            activation(F.batch_norm(z, None, None, g, b, True, 0.0, bn.eps), op.act).backward(dy_full)
+            zb = F.batch_norm(z, None, None, g, b, True, 0.0, bn.eps)
+            if op.act == "mish":
+                # storage-rounding model of the native BN backward for Mish: g = dy * mish'(zhat) is written to the 16-bit
+                # dz buffer between its two passes (the reference under autocast rounds the same tensor between its
+                # mish_backward and batch_norm_backward kernels)
+                zb_d = zb.detach().requires_grad_(True)
+                activation(zb_d, op.act).backward(dy_full)
+                zb.backward(zb_d.grad, retain_graph=True)             # dgamma / dbeta: the per-channel sums use the fp32 g
+                gg, bg = g.grad.clone(), b.grad.clone()
+                z.grad = None
+                zb.backward(zb_d.grad.to(plan.dtype).float())         # dz: from the stored (rounded) g
+                g.grad, b.grad = gg, bg
+            else:
+                activation(zb, op.act).backward(dy_full)
             dz = z.grad.to(plan.dtype).float()
             bias = None
         else:
