@@ -202,6 +202,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradTmaps tm, const WgradKArgs p) {
 }
 
 // grad_w[co][ci][r][s] (+)= sum over splits (fixed order) of part[split][tap][co][ci]
+// One thread per output, coalesced over ci.  (A variant with 8 split lanes per output was not faster: the cost is the
+// volume of the partials — e.g. 58 MB for 128x128x9 weights at 98 splits — not the length of the serial sum.)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int taps, int Cout_pad, int Cin_pad, int Cout,
                                     int Cin, float* __restrict__ grad, int accumulate) {   // Cin = real input channels
   const long long total = (long long)Cout * taps * Cin;
@@ -218,7 +220,6 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, 
     grad[gi] = accumulate ? grad[gi] + s : s;
   }
 }
-
 // Stem convolutions (Cin <= 4): the frames are NCHW fp32 / uint8 and K = 27 is far too small for a GEMM tile, so
 // this is a CUDA-core reduction: block = 32 pixel lanes x 8 threads, each thread owns 4 out channels ... kept simple:
 // thread t of 256 handles output column (co, tap*Cin+ci) pairs round-robin over a strip of pixels; strips are reduced

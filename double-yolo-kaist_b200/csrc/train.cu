@@ -698,6 +698,45 @@ __global__ void frames_to_nhwc8_kernel(const TIn* __restrict__ x, uint8_t* __res
   }
 }
 
+// ------------------------------------------------------------------ stem frames -> im2col rows (3x3, pad 1, Cin = 3)
+// y[n][h][w][ci*9 + r*3 + s] = frame[n][ci][h + r - 1][w + s - 1] (0 outside, channels 27..31 zero): with the 3x3
+// neighbourhood as 32 "channels" the stem weight gradient is the weight gradient of a 1x1 convolution, and the channel
+// order makes its [Cout][27] result the OIHW gradient itself.
+template <bool kBf16, typename TIn>
+__global__ void frames_to_im2col32_kernel(const TIn* __restrict__ x, uint8_t* __restrict__ y, int N, int H, int W) {
+  const long long total = (long long)N * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const long long t = i / W;
+    const int h = (int)(t % H);
+    const long long n = t / H;
+    float f[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) f[k] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hh = h + r - 1;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int ww = w + q - 1;
+          if (ww < 0 || ww >= W) continue;
+          const TIn v = __ldg(&x[((n * 3 + ci) * H + hh) * W + ww]);
+          if constexpr (sizeof(TIn) == 1) f[ci * 9 + r * 3 + q] = (float)v / 255.0f;
+          else f[ci * 9 + r * 3 + q] = (float)v;
+        }
+      }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float g[8] = {f[8 * c], f[8 * c + 1], f[8 * c + 2], f[8 * c + 3], f[8 * c + 4], f[8 * c + 5], f[8 * c + 6], f[8 * c + 7]};
+      *reinterpret_cast<uint4*>(y + i * 64 + c * 16) = pack8<kBf16>(g);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ dgrad weight packing
 // OIHW fp32 -> [I][kh][kw][Opad] 16-bit with the taps rotated by 180 degrees: W'[i][r][s][o] = W[o][i][kh-1-r][kw-1-s]
 template <bool kBf16>
@@ -952,6 +991,20 @@ DYK_EXPORT int dyk_pack_weights_dgrad(const float* w_oihw, void* w_packed, int32
   DYK_DISPATCH_DTYPE(dtype, (pack_dgrad_kernel<kBf16><<<grid_for_t((long long)I * kh * kw * Opad, 256), 256, 0,
                                                       static_cast<cudaStream_t>(stream_)>>>(w_oihw, w_packed, O, I, kh, kw, Opad)));
   DYK_LAUNCH_OK("pack_dgrad_kernel");
+  return DYK_OK;
+}
+
+DYK_EXPORT int dyk_frames_to_im2col32(const void* x_nchw, void* y, int32_t N, int32_t H, int32_t W, int32_t dtype,
+                                      int32_t x_kind, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYK_REQUIRE(x_nchw && y && N > 0 && H > 0 && W > 0 && DYK_AL16(y), "dyk_frames_to_im2col32: bad arguments");
+  const int grid = grid_for_t((long long)N * H * W, 128);
+  if (x_kind == 1) {
+    DYK_DISPATCH_DTYPE(dtype, (frames_to_im2col32_kernel<kBf16, uint8_t><<<grid, 128, 0, stream>>>((const uint8_t*)x_nchw, (uint8_t*)y, N, H, W)));
+  } else {
+    DYK_DISPATCH_DTYPE(dtype, (frames_to_im2col32_kernel<kBf16, float><<<grid, 128, 0, stream>>>((const float*)x_nchw, (uint8_t*)y, N, H, W)));
+  }
+  DYK_LAUNCH_OK("frames_to_im2col32_kernel");
   return DYK_OK;
 }
 

@@ -88,6 +88,7 @@ SIGNATURES = {
     "dyk_yolo_loss_head": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32,
                                   _f32, _f32, _f32, _f32, _vp, _i32, _vp, _vp, _vp, _vp]),
     "dyk_yolo_loss_scale_grad": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "dyk_frames_to_im2col32": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_pack_weights_multi": (_i32, [_vp, _i32, _i32, _i32, _vp]),
     "dyk_pack_weights_ohwi": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_nchw_f32_to_nhwc": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -219,6 +219,15 @@ def stem_wgrad_tc(x_nchw: torch.Tensor, dz: View, grad_w: torch.Tensor, *, k: in
     N, Cin, H, W = x_nchw.shape
     kind = {torch.float32: 0, torch.uint8: 1}[x_nchw.dtype]
     dtype = dz.buf.dtype
+    if Cin == 3 and k == 3 and stride == 1 and pad == 1:
+        # the 3x3 neighbourhood as 32 im2col "channels" (order ci, r, s = OIHW): a 1x1 weight gradient with one tap and
+        # half-filled operand boxes instead of nine taps over boxes that are 7/8 zero padding (1.55 -> ~0.5 ms at 512x640x16)
+        xc = scratch(2 * N * H * W * 32, x_nchw.device, "x32")[:2 * N * H * W * 32].view(dtype).view(N, H, W, 32)
+        nat.call("dyk_frames_to_im2col32", _p(x_nchw), _p(xc), N, H, W, dz.dt, kind, _stream())
+        nat.count_launches()
+        conv_wgrad(View(xc, 0, 32), dz, grad_w.view(grad_w.shape[0], 27, 1, 1), k=1, stride=1, pad=0, accumulate=accumulate,
+                   cin_real=27)
+        return
     xp = scratch(2 * N * H * W * 8, x_nchw.device, "x8")[:2 * N * H * W * 8].view(dtype).view(N, H, W, 8)
     nat.call("dyk_frames_to_nhwc8", _p(x_nchw), _p(xp), N, Cin, H, W, dz.dt, kind, _stream())
     nat.count_launches()

@@ -259,6 +259,10 @@ int dyk_pack_weights_multi(const int64_t* descs, int32_t n, int32_t total_tiles,
  * dimension zero-padded to 8, the operand layout the tensor-core wgrad kernel needs for the stem convolutions. */
 int dyk_frames_to_nhwc8(const void* x_nchw, void* y, int32_t N, int32_t Cin, int32_t H, int32_t W, int32_t dtype,
                         int32_t x_kind, void* stream);
+/* 3-channel frames -> NHWC 16-bit im2col rows of the 3x3 / pad 1 neighbourhood: y[n][h][w][ci*9 + r*3 + s], 32 channels
+ * (27..31 zero).  dyk_conv2d_wgrad on it with k = 1, Cin = 32, Cin_real = 27 yields the stem's OIHW weight gradient. */
+int dyk_frames_to_im2col32(const void* x_nchw, void* y, int32_t N, int32_t H, int32_t W, int32_t dtype, int32_t x_kind,
+                           void* stream);
 /* weight gradient of the stem convolutions (Cin <= 4, NCHW fp32 / uint8 frames as in dyk_conv2d_stem_nchw_fwd).
  * workspace: DYK_STEM_WGRAD_STRIPS * Cout * k*k*Cin floats. */
 #define DYK_STEM_WGRAD_STRIPS 592
