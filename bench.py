@@ -545,7 +545,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count())
-            fps, done, dt = time_cpu_port(ref, st, args.ref_frames, 6, 1, budget_s=20.0)
+            fps, done, dt = time_cpu_port(ref, st, args.ref_frames, 40, 1, budget_s=15.0)   # ~15 s of host work
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{done} steps of {args.ref_frames} paired frames (fp32 oracle port, "
                                               f"torch threads={os.cpu_count()}, {dt:.1f} s)"}
