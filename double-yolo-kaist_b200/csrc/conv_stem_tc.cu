@@ -26,13 +26,12 @@ template <bool kBf16>
 __device__ __forceinline__ uint32_t pack2h(float a, float b) { return pack2<kBf16>(a, b); }
 
 template <bool kBf16, typename TIn>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 stem_tc_kernel(const TIn* __restrict__ x, const float* __restrict__ w /* [32][3][3][Cin] fp32 */,
                const float* __restrict__ scale, const float* __restrict__ bias, uint8_t* __restrict__ y, long long ys,
                int N, int H, int W, int Cin, int act, int tiles_w, long long num_tiles) {
   __shared__ __align__(1024) uint8_t sa[128 * 64];     // A: 128 pixels x 32 K (16-bit), SWIZZLE_64B
   __shared__ __align__(1024) uint8_t sb[32 * 64];      // B: 32 out channels x 32 K
-  __shared__ float lut[256];
   __shared__ uint64_t mma_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float ssc[32], sbi[32];
@@ -41,10 +40,10 @@ stem_tc_kernel(const TIn* __restrict__ x, const float* __restrict__ w /* [32][3]
   constexpr int KK = 9 * kCin;
   (void)Cin;
 
-  if constexpr (sizeof(TIn) == 1) {                    // exact IEEE v / 255 once per byte value
-    lut[t] = __fdiv_rn((float)t, 255.f);
-    lut[t + 128] = __fdiv_rn((float)(t + 128), 255.f);
-  }
+  // uint8 frames: v * (1/255) instead of the IEEE division v / 255 — the two differ in fp32 for 126 byte values but are
+  // identical for all 256 after the rounding to fp16 / bf16 that follows (checked exhaustively), so the 256-entry table
+  // of the first version (27 bank-conflicting shared-memory lookups per pixel) is not needed.
+  constexpr float kInv255 = 1.0f / 255.0f;
   // weights -> sb (row = out channel, 64 B per row, 16-byte chunk c stored at c ^ ((row >> 1) & 3))
   if (t < 32) {
     uint32_t pk[16];
@@ -81,21 +80,36 @@ stem_tc_kernel(const TIn* __restrict__ x, const float* __restrict__ w /* [32][3]
     // ---- gather the im2col row of this thread's pixel
     float v[32];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = 0.f;
-    if (wo < W) {
+    for (int k = 27; k < 32; ++k) v[k] = 0.f;
+    auto cvt = [&](TIn raw) -> float {
+      if constexpr (sizeof(TIn) == 1) return (float)raw * kInv255;
+      else return (float)raw;
+    };
+    const long long plane = (long long)H * W;
+    const TIn* xb = x + ((long long)n * kCin * H + (ho - 1)) * W + (wo - 1);     // top-left tap of channel 0
+    if (ho >= 1 && ho + 1 < H && wo >= 1 && wo + 1 < W) {                        // interior pixel: no bounds checks
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int h = ho - 1 + r;
-        if (h < 0 || h >= H) continue;
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const int ww = wo - 1 + s;
-          if (ww < 0 || ww >= W) continue;
+        for (int ci = 0; ci < kCin; ++ci) {
+          const TIn* row = xb + ci * plane + (long long)r * W;
 #pragma unroll
-          for (int ci = 0; ci < kCin; ++ci) {
-            const TIn raw = __ldg(&x[(((long long)n * kCin + ci) * H + h) * W + ww]);
-            if constexpr (sizeof(TIn) == 1) v[(r * 3 + s) * kCin + ci] = lut[raw];
-            else v[(r * 3 + s) * kCin + ci] = (float)raw;
+          for (int q = 0; q < 3; ++q) v[(r * 3 + q) * kCin + ci] = cvt(__ldg(row + q));
+        }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 27; ++k) v[k] = 0.f;
+      if (wo < W) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int h = ho - 1 + r;
+          if (h < 0 || h >= H) continue;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const int ww = wo - 1 + q;
+            if (ww < 0 || ww >= W) continue;
+#pragma unroll
+            for (int ci = 0; ci < kCin; ++ci) v[(r * 3 + q) * kCin + ci] = cvt(__ldg(xb + ci * plane + (long long)r * W + q));
           }
         }
       }
