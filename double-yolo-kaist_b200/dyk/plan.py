@@ -267,6 +267,22 @@ def fuse(ops_):
     return out
 
 
+def cascade_pools(ops_):
+    """SPP (models.py:91-94): the 5x5, 9x9 and 13x13 stride-1 max pools of one tensor.  Max pooling with -inf padding
+    composes — mp5(mp5(x)) = mp9(x), mp5(mp9(x)) = mp13(x), bit for bit — so the larger windows are computed from the
+    previous pool's output with a 5x5 window: 25 loads per output instead of 81 / 169."""
+    by_src = {}
+    for op in ops_:
+        if isinstance(op, PoolOp) and op.stride == 1:
+            prev = by_src.get((id(op.src), op.k - 4))
+            by_src[(id(op.src), op.k)] = op
+            if prev is not None and op.k in (9, 13):
+                op.src.uses -= 1
+                op.src = prev.out
+                op.src.uses += 1
+                op.k = 5
+
+
 def mark_heads(ops_):
     """Head convs (no BN, linear) that only feed [yolo] blocks keep their logits in fp32."""
     consumers = {}
@@ -407,6 +423,7 @@ class Plan:
         raw, vals, self.img0, self.img1 = build_ops(model, H, W, dual)
         self.layer_vals = vals   # Value visible at every cfg layer index (diagnostics: tools/layer_parity.py)
         self.ops = fuse(raw)
+        cascade_pools(self.ops)
         mark_heads(self.ops)
         place_concats(self.ops)
         liveness(self.ops)
