@@ -22,6 +22,8 @@ CASES = [  # name, v4, ciou, nc, gr, obj_pw, cls_pw, nt, seed
     ("v4_ciou", True, True, 1, 0.5, 1.5, 1.0, 12, 2),
     ("v3_ciou_nc3", False, True, 3, 1.0, 1.0, 2.0, 10, 3),
     ("v4_giou_empty", True, False, 1, 1.0, 1.0, 1.0, 0, 4),
+    ("v3_ciou_edges", False, True, 1, 0.3, 1.0, 1.0, 8, 5),       # labels on cell boundaries / image borders / unmatched sizes
+    ("v4_giou_nc2_pw", True, False, 2, 0.7, 0.7, 1.3, 11, 6),
 ]
 H, W, B = 128, 192, 2
 
@@ -43,6 +45,12 @@ def case_inputs(v4, nc, nt, seed):
         t[1, 4:6] *= 1.1
         if nt > 4:
             t[4, 0], t[4, 2:4] = t[3, 0], t[3, 2:4] + 0.001
+        if seed == 5:                     # edge geometry
+            t[2, 2:4] = torch.tensor([0.5, 0.25])          # exactly on cell boundaries of every grid
+            t[3, 2:4] = torch.tensor([0.0, 0.0])           # image corner (cell 0, 0)
+            t[5, 2:4] = torch.tensor([0.999, 0.999])       # last cell
+            t[6, 4:6] = torch.tensor([0.9, 0.95])          # matches only the largest anchors
+            t[7, 4:6] = torch.tensor([0.002, 0.002])       # matches no anchor at all
     return p, anchor_vecs, t
 
 

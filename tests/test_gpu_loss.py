@@ -14,7 +14,7 @@ import torch
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 GOLD = Path(__file__).resolve().parent / "golden" / "loss_cases.npz"
-CASES = ["v3_giou", "v4_ciou", "v3_ciou_nc3", "v4_giou_empty"]
+CASES = ["v3_giou", "v4_ciou", "v3_ciou_nc3", "v4_giou_empty", "v3_ciou_edges", "v4_giou_nc2_pw"]
 
 
 def _model(c):
