@@ -19,9 +19,39 @@ from dyk import _native as nat
 from dyk import ops as _ops
 from dyk.loss import build_targets, compute_loss
 
-__all__ = ['non_max_suppression', 'xywh2xyxy', 'get_yolo_layers', 'compute_loss', 'build_targets']
+__all__ = ['non_max_suppression', 'xywh2xyxy', 'get_yolo_layers', 'compute_loss', 'build_targets', 'scale_coords',
+           'clip_coords']
 
 _workspaces = {}
+
+
+def _boxes_inplace(coords, pad_x, pad_y, gain, img_shape):
+    _ops._require_cuda(coords, "scale_coords / clip_coords")
+    if coords.dtype != torch.float32 or coords.dim() != 2 or coords.shape[1] < 4 or (coords.shape[0] and coords.stride(1) != 1):
+        raise ValueError("boxes must be a float32 (n, >= 4) tensor with unit column stride")
+    with torch.cuda.device(coords.device):
+        nat.call("dyk_scale_coords", C.c_void_p(coords.data_ptr()), coords.stride(0) if coords.shape[0] else 4, coords.shape[0],
+                 float(pad_x), float(pad_y), float(gain), float(img_shape[1]), float(img_shape[0]),
+                 torch.cuda.current_stream().cuda_stream)
+    nat.count_launches()
+    return coords
+
+
+def scale_coords(img1_shape, coords, img0_shape, ratio_pad=None):
+    """Rescales xyxy boxes from the network input size (img1_shape) to the original image (img0_shape) and clips them, in
+    place, like the reference (utils.py:60-84) — one native launch instead of four indexed tensor ops + four clamps."""
+    if ratio_pad is None:
+        gain = max(img1_shape) / max(img0_shape)
+        pad = (img1_shape[1] - img0_shape[1] * gain) / 2, (img1_shape[0] - img0_shape[0] * gain) / 2
+    else:
+        gain = ratio_pad[0][0]
+        pad = ratio_pad[1]
+    return _boxes_inplace(coords, pad[0], pad[1], gain, img0_shape)
+
+
+def clip_coords(boxes, img_shape):
+    """Clips xyxy boxes to (height, width) in place (utils.py:87-92)."""
+    _boxes_inplace(boxes, 0.0, 0.0, 1.0, img_shape)
 
 
 def get_yolo_layers(model):

@@ -83,3 +83,31 @@ extern "C" __attribute__((visibility("default"))) int dyk_yolo_decode(const void
   DYK_LAUNCH_OK("yolo_decode_kernel");
   return DYK_OK;
 }
+
+// ---- post-NMS box rescaling: scale_coords + clip_coords (build_utils/utils.py:60-92), in place on n rows of xyxy boxes.
+// Same fp32 operation order as the reference's in-place tensor ops: (x - pad) / gain, then clamp to [0, size].
+namespace dyk {
+__global__ void scale_coords_kernel(float* __restrict__ boxes, long long row_stride, int n, float pad_x, float pad_y, float gain,
+                                    float img_w, float img_h) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 4) return;
+  const int r = i >> 2, c = i & 3;
+  float* p = boxes + (long long)r * row_stride + c;
+  const bool is_x = (c & 1) == 0;
+  float v = __fdiv_rn(__fsub_rn(*p, is_x ? pad_x : pad_y), gain);
+  v = fminf(fmaxf(v, 0.f), is_x ? img_w : img_h);
+  *p = v;
+}
+}  // namespace dyk
+
+extern "C" __attribute__((visibility("default"))) int dyk_scale_coords(float* boxes, int64_t row_stride, int32_t n, float pad_x,
+                                                                        float pad_y, float gain, float img_w, float img_h,
+                                                                        void* stream_) {
+  DYK_REQUIRE(n == 0 || boxes, "dyk_scale_coords: null pointer");
+  DYK_REQUIRE(n >= 0 && row_stride >= 4 && gain != 0.f, "dyk_scale_coords: bad arguments");
+  if (n == 0) return DYK_OK;
+  dyk::scale_coords_kernel<<<(n * 4 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream_)>>>(boxes, row_stride, n, pad_x, pad_y,
+                                                                                            gain, img_w, img_h);
+  DYK_LAUNCH_OK("scale_coords_kernel");
+  return DYK_OK;
+}

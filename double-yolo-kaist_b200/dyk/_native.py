@@ -83,6 +83,7 @@ SIGNATURES = {
                                      _vp, _vp]),
     "dyk_dwconv2d_dgrad": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_dwconv2d_wgrad": (_i32, [_vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "dyk_scale_coords": (_i32, [_vp, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "dyk_yolo_build_targets": (_i32, [_vp, _i32, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "dyk_yolo_loss_workspace_floats": (_i64, [_i32, _i32, _i64]),
     "dyk_yolo_loss_head": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32,

@@ -283,6 +283,12 @@ int dyk_dwconv2d_wgrad(const void* x, int64_t x_pix_stride, const void* dz, int6
                        int32_t H, int32_t W, int32_t C, int32_t k, int32_t stride, int32_t pad, int32_t accumulate,
                        int32_t dtype, float* workspace, void* stream);
 
+/* ---- scale_coords + clip_coords (build_utils/utils.py:60-92): xyxy boxes from the network input size back to the
+ * original image, in place: x = clamp((x - pad_x) / gain, 0, img_w), y = clamp((y - pad_y) / gain, 0, img_h) for the first
+ * four columns of n rows (row_stride floats apart).  clip_coords alone = pad 0, gain 1. */
+int dyk_scale_coords(float* boxes, int64_t row_stride, int32_t n, float pad_x, float pad_y, float gain, float img_w,
+                     float img_h, void* stream);
+
 /* ---- training loss of the YOLO heads (build_utils/utils.py:209-384: compute_loss + build_targets; bbox_iou :95-138,
  * wh_iou :166-172), forward and gradient fused, one head per call, no host synchronisation.
  *
