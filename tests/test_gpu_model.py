@@ -179,3 +179,20 @@ def test_eval_pipeline_matches_direct_calls(native_lib):
         assert torch.equal(ca, cb)
         for i, k in enumerate(ca.tolist()):
             assert torch.equal(a[i, :k], b[i, :k])
+    # the same with the detections read back to pinned host memory on the nms stream
+    pipe = EvalPipeline(m, 0.01, 0.6, multi_label=False, to_host=True)
+    got = []
+    pipe.stage(*batches[0])
+    for i in range(len(batches)):
+        res = pipe.submit()
+        if i + 1 < len(batches):
+            pipe.stage(*batches[i + 1])
+        if res is not None:
+            assert not res[0].is_cuda and res[0].is_pinned()
+            got.append((res[0].clone(), res[1].clone()))
+    last = pipe.flush()
+    got.append((last[0].clone(), last[1].clone()))
+    for (a, ca), (b, cb) in zip(got, want):
+        assert torch.equal(ca, cb)
+        for i, k in enumerate(ca.tolist()):
+            assert torch.equal(a[i, :k], b[i, :k])
