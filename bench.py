@@ -521,7 +521,8 @@ def main():
                        "l2": "per-step working set (231 MB weights + >5 GB activations) exceeds the 126 MB L2; "
                              "4 distinct input batches cycled; no explicit flush",
                        "pipeline": "dyk.pipeline.EvalPipeline: NMS of batch i on a second stream overlaps the forward of "
-                                   "batch i+1; e2e also uploads batch i+1 on a copy stream; all inside the timed region",
+                                   "batch i+1; e2e also uploads batch i+1 on a copy stream and reads the detections back to pinned host memory "
+                                   "on the NMS stream; all inside the timed region",
                        "conf_thres": CONF, "iou_thres": IOU},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
