@@ -158,3 +158,102 @@ class Concat(nn.Module):
         if self.d != 1:
             raise NotImplementedError("Concat: only channel concatenation is on the hot path")
         return _ops.concat_channels(list(x))
+
+
+class ResBlock(nn.Module):
+    """`block_nums` x (1x1 conv -> 3x3 conv [+ input]) — defined by the reference (layers.py:125-145) but used by no cfg;
+    kept for `from build_utils.layers import *`.  Each conv is a native ConvBnActivation, the add a native fused add."""
+
+    def __init__(self, in_channels, filter_1, out_channels, block_nums=1, activation='mish', shortcut=True):
+        super().__init__()
+        self.shortcut = shortcut
+        self.module_list = nn.ModuleList()
+        for _ in range(block_nums):
+            # the reference passes (…, 1, 1, 1, activation, True) positionally: kernel 1, stride 1, pad 1, groups=activation —
+            # i.e. it cannot be constructed there; the evident intent is built here
+            self.module_list.append(nn.ModuleList([
+                ConvBnActivation(in_channels, filter_1, 1, 1, 1, activation=activation, bn=True),
+                ConvBnActivation(filter_1, out_channels, 3, 1, 1, activation=activation, bn=True)]))
+
+    def forward(self, x):
+        for pair in self.module_list:
+            y = x
+            for conv in pair:
+                y = conv(y)
+            x = _ops.weighted_fusion(y, [x], None) if self.shortcut else y
+        return x
+
+
+class SEInceptionFusion(nn.Module):
+    """concat(layers) -> 1x1 conv -> [Inception] -> [SqueezeExcitation] (reference layers.py:193-215; no cfg block type
+    builds it).  Composed of the native modules above."""
+
+    def __init__(self, in_channels, out_channels, layers, inception=False, icp_param_list=(), tmse=False, squeeze_factor=4):
+        super().__init__()
+        self.concat = FeatureConcat(layers)
+        self.enhance = nn.ModuleList([ConvBnActivation(in_channels, out_channels, kernel_size=1)])
+        if inception:
+            self.enhance.append(Inception(out_channels, *icp_param_list))
+        if tmse:
+            self.enhance.append(SqueezeExcitation(out_channels, squeeze_factor))
+
+    def forward(self, x, outputs):
+        y = self.concat(x, outputs)
+        for m in self.enhance:
+            y = m(y)
+        return y
+
+
+class MixConv2d(nn.Module):
+    """Parallel convolutions with different kernel sizes, concatenated (reference layers.py:237-268; unused by every cfg).
+    Channel split rules as in the reference: 'equal_ch' or 'equal_params'."""
+
+    def __init__(self, in_ch, out_ch, k=(3, 5, 7), stride=1, dilation=1, bias=True, method='equal_params'):
+        super().__init__()
+        import numpy as np
+        groups = len(k)
+        if method == 'equal_ch':
+            idx = torch.linspace(0, groups - 1E-6, out_ch).floor()
+            ch = [int((idx == g).sum()) for g in range(groups)]
+        else:
+            a = np.eye(groups + 1, groups, k=-1)
+            a -= np.roll(a, 1, axis=1)
+            a *= np.array(k) ** 2
+            a[0] = 1
+            ch = np.linalg.lstsq(a, [out_ch] + [0] * groups, rcond=None)[0].round().astype(int)
+        if dilation != 1:
+            raise _ops.nat.NativeError("MixConv2d: dilated convolutions have no native kernel")
+        self.m = nn.ModuleList([nn.Conv2d(in_ch, int(ch[g]), k[g], stride, k[g] // 2, bias=bias) for g in range(groups)])
+
+    def forward(self, x):
+        return _ops.concat_channels([_ops.conv_bn_act(x, m, None, 'linear') for m in self.m])
+
+
+class _NativeActivation(nn.Module):
+    """Stand-alone activation modules the reference defines next to nn.Mish / nn.Hardswish (layers.py:271-320); the
+    model never instantiates them (create_modules uses the torch.nn classes as parameter-free markers)."""
+    act = 'linear'
+
+    def forward(self, x):
+        return _ops.activation(x, self.act)
+
+
+class Mish(_NativeActivation):
+    act = 'mish'
+
+
+class MemoryEfficientMish(Mish):
+    pass
+
+
+class HardSwish(_NativeActivation):
+    act = 'hard-swish'
+
+
+class Swish(nn.Module):
+    def forward(self, x):
+        raise _ops.nat.NativeError("Swish (x*sigmoid(x)) is not an activation of any Darknet cfg block and has no native kernel")
+
+
+class MemoryEfficientSwish(Swish):
+    pass

@@ -166,7 +166,7 @@ def allreduce_gradients(params, bucket_bytes: int = 64 << 20) -> int:
         flat = torch.cat([g.reshape(-1) for g in chunk]) if len(chunk) > 1 else chunk[0].reshape(-1)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         flat.div_(world)
-        if len(chunk) > 1:
+        if len(chunk) > 1 or flat.data_ptr() != chunk[0].data_ptr():     # reshape(-1) of a non-contiguous grad is a copy
             off = 0
             for g in chunk:
                 g.copy_(flat[off:off + g.numel()].view_as(g))

@@ -304,6 +304,21 @@ def upsample(x: torch.Tensor, s: int, dtype=None) -> torch.Tensor:
     return to_nchw(y)
 
 
+def activation(x: torch.Tensor, act: str, dtype=None) -> torch.Tensor:
+    """act(x) for an NCHW CUDA tensor through the BatchNorm-apply kernel with unit scale / zero shift."""
+    _require_cuda(x, "activation")
+    xv = to_nhwc(x, dtype)
+    if xv.C % 8:
+        raise nat.NativeError("activation: channel count must be a multiple of 8")
+    y = new_view(xv.N, xv.H, xv.W, xv.C, xv.buf.dtype, x.device)
+    one = torch.ones(xv.C, dtype=torch.float32, device=x.device)
+    zero = torch.zeros(xv.C, dtype=torch.float32, device=x.device)
+    nat.call("dyk_bn_act_apply", xv.ptr, xv.stride, _p(one), _p(zero), nat.ACT_IDS[act], y.ptr, y.stride, xv.npix, xv.C,
+             xv.dt, _stream())
+    nat.count_launches()
+    return to_nchw(y)
+
+
 def se_weights(fc1, fc2):
     w1 = fc1.weight.detach().float().reshape(fc1.out_channels, fc1.in_channels).contiguous()
     w2 = fc2.weight.detach().float().reshape(fc2.out_channels, fc2.in_channels).contiguous()

@@ -199,7 +199,8 @@ def build_ops(model, H, W, dual):
             cur = Value(sum(s.C for s in srcs), x.H, x.W, "concat", f"L{i}")
             ops_.append(ConcatOp(i, [use(s) for s in srcs], cur))
         elif t == "dropout":
-            pass  # identity in eval mode
+            if model.training and getattr(m, "p", 0.0) > 0:
+                raise nat.NativeError(f"layer {i}: [dropout] with p = {m.p} has no native training kernel (eval mode: identity)")
         elif t == "se":
             out = Value(cur.C, cur.H, cur.W, "se", f"L{i}")
             ops_.append(SEOp(i, use(cur), out, m))
@@ -716,6 +717,11 @@ class PlanCache:
         self.plans.clear()
         self.bank = WeightBank()
         self._tensors = None
+
+    def mark_stale(self):
+        """Force a re-pack of every cached weight on the next run (same device buffers, so captured graphs stay valid)."""
+        if self.bank.signature is not None:
+            self.bank.signature = ("stale",)
 
     def run(self, x, y):
         model = self.model

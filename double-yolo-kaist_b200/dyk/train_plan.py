@@ -33,7 +33,13 @@ from . import plan as P
 from . import train_ops as T
 from .ops import View
 
-HEAD_PAD = 32   # head logits gradients are padded to 32 channels (K of the dgrad GEMM, 16-byte TMA rows)
+HEAD_PAD = 32   # head logits gradients are padded to a multiple of 32 channels (K of the dgrad GEMM, 16-byte TMA rows)
+
+
+def head_pad(channels: int) -> int:
+    """Padded channel count of a detection head's gradient / data-gradient weights: na*(5+nc) rounded up to 32
+    (18 -> 32 for the KAIST cfgs, 75 -> 96 for VOC, 255 -> 256 for COCO)."""
+    return (channels + HEAD_PAD - 1) // HEAD_PAD * HEAD_PAD
 
 
 class _Grad:
@@ -115,7 +121,7 @@ class TrainPlan:
                 if not st["stem"] and not st["dw"] and k * k <= 9 and conv.weight.dtype == torch.float32:
                     # persistent packed copies, refreshed for all layers by one launch per step (_pack_all)
                     O, I = conv.out_channels, conv.in_channels
-                    opad = O if bn is not None else HEAD_PAD
+                    opad = O if bn is not None else head_pad(O)
                     st["w"] = torch.empty((O, k, k, I), dtype=self.dtype, device=dev)
                     st["wd"] = torch.zeros((I, k, k, opad), dtype=self.dtype, device=dev)
                     st["multi"] = True
@@ -206,6 +212,8 @@ class TrainPlan:
                 if not wt.is_contiguous() or wt.dtype != torch.float32:
                     raise nat.NativeError("convolution weights must be contiguous float32 parameters")
                 O, I, k = wt.shape[0], wt.shape[1], st["k"]
+                if st["wd"].shape[3] < O or st["wd"].shape[0] != I or st["w"].shape[0] != O:
+                    raise nat.NativeError("internal: packed weight buffers do not match the convolution's shape")
                 rows.append([wt.data_ptr(), st["w"].data_ptr(), st["wd"].data_ptr(), O, I, k * k, st["wd"].shape[3], tiles])
                 tiles += ((O + 31) // 32) * ((I + 31) // 32)
             self._pack_desc = torch.tensor(rows, dtype=torch.int64).to(self.device)
@@ -249,7 +257,7 @@ class TrainPlan:
                     g = _Grad(View(pg.view.buf, pg.view.c_off + alias[1], v.C))
                     g.alias_of = pg
                 elif v.f32:      # head logits: gradient kept as padded 16-bit NHWC
-                    g = _Grad(self._new(HEAD_PAD, v.H, v.W))
+                    g = _Grad(self._new(head_pad(v.C), v.H, v.W))
                 else:
                     g = _Grad(self._new(v.C, v.H, v.W))
                     self.bytes_allocated += g.view.buf.numel() * 2
@@ -362,7 +370,7 @@ class TrainPlan:
                 cout_real = conv.out_channels
                 if conv.bias is not None:
                     o = self.offsets[id(conv.bias)]
-                    T.chan_sum(dz, flat[o:o + HEAD_PAD], accumulate=True)
+                    T.chan_sum(dz, flat[o:o + dz.C], accumulate=True)     # dz.C = head_pad(Cout) = the padded slot of the bias
             if st["stem"]:
                 T.stem_wgrad_tc(st["x_in"], dz, gw, k=k, stride=s, pad=p, accumulate=True)
                 return

@@ -217,6 +217,13 @@ class YOLO(nn.Module):
             self._train_plans.invalidate()
         return out
 
+    def refresh_weights(self):
+        """Re-pack the native copies of the parameters (packed 16-bit weights, folded BatchNorm, captured graphs) on the
+        next forward.  In-place updates through the tensors themselves (optimizer.step, load_state_dict, copy_ under
+        no_grad) are detected by their version counters; writes through ``param.data`` are NOT — call this after them."""
+        if '_plans' in self.__dict__:
+            self._plans.mark_stale()
+
     def forward(self, x, y=None):
         di = "second_index" in self.net_info and y is not None
         if self.training:
@@ -241,7 +248,10 @@ def load_darknet_weights(model, weights, cutoff=-1):
     def take(dst):
         nonlocal ptr
         n = dst.numel()
-        dst.data.copy_(torch.from_numpy(blob[ptr:ptr + n]).view_as(dst))
+        if ptr + n > blob.size:
+            raise ValueError(f"{weights}: file ends after {blob.size} floats, the model needs more")
+        with torch.no_grad():   # an in-place copy on the tensor itself bumps its version counter (a `.data` write does not)
+            dst.copy_(torch.from_numpy(blob[ptr:ptr + n]).view_as(dst))
         ptr += n
 
     for mdef, module in zip(model.module_defs[:cutoff], model.module_list[:cutoff]):
@@ -255,3 +265,4 @@ def load_darknet_weights(model, weights, cutoff=-1):
         else:
             take(conv.bias)
         take(conv.weight)
+    model.refresh_weights()
