@@ -52,6 +52,7 @@ struct ConvKArgs {
   int act;
   int upsample2x;
   int out_f32;                     // 1: y is fp32, written with plain stores (head convs feeding decode)
+  int acc_main_k;                  // acc32 variant: K-elements of a tap whose MMAs go to the main accumulator
   void* y_f32;
   long long y_pix_stride;
   const float* scale;              // may be null
@@ -264,14 +265,39 @@ __device__ __forceinline__ void epilogue_tile(const ConvTmaps& tm, const ConvKAr
   }
 }
 
-template <int BLOCK_N, int BLOCK_K, int kSplit, bool kBf16>
+// kAcc32 (fp32-accurate mode, out_f32 == 2).  The tensor core's adder aligns the 16 products of an MMA and the fp32
+// accumulator to the largest exponent and TRUNCATES every addend there (measured: ~2e-5 relative error after 864
+// accumulating MMAs, 5e-6 after 27; sign-symmetric — a negated twin accumulator cancels nothing), i.e. every MMA adds
+// ~16 truncations at the ulp of the running sum.  Two measures bring the result to within a small factor of an fp32 FMA chain:
+//  * chunks: the MMA warp accumulates only kAccChunkKb k-blocks (8 MMAs) per TMEM stage, and the epilogue warps add every
+//    finished chunk into fp32 registers with round-to-nearest (the two TMEM stages double-buffer chunks instead of
+//    tiles), so the running sum the truncation is relative to stays a short partial sum;
+//  * two accumulators per stage: MMAs over the leading `acc_main_k` K-elements of a filter tap (the x1*w1 products of the
+//    split operand, csrc/f32_path.cu) go to M, all others (the five correction terms, 2^-8 .. 2^-16 smaller) go to S,
+//    whose truncation unit is smaller by the same factor; the epilogue adds M + S.
+constexpr int kAccChunkKb = 2;
+// which accumulators the MMAs of k-blocks [kb0, kb1) touch: bit 0 = M, bit 1 = S  (MMA j of k-block kb starts at K-element
+// (kb % k_chunks) * BLOCK_K + 16 j of its tap; it goes to S when that is >= main_k)
+template <int BLOCK_K>
+__device__ __forceinline__ int acc32_touch(int kb0, int kb1, int k_chunks, int main_k) {
+  int m = 0;
+  for (int kb = kb0; kb < kb1; ++kb) {
+    const int k0 = (kb % k_chunks) * BLOCK_K;
+    if (k0 < main_k) m |= 1;
+    if (k0 + BLOCK_K - 16 >= main_k) m |= 2;
+  }
+  return m;
+}
+
+template <int BLOCK_N, int BLOCK_K, int kSplit, bool kBf16, bool kAcc32 = false>
 __global__ void __launch_bounds__(num_threads<kSplit>(), 1)
 conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
   using S = ConvSmem<BLOCK_N, BLOCK_K, kSplit>;
   constexpr int kNumEpiWarps = S::kNumEpiWarps;
   constexpr int kSwz = BLOCK_K * 2;            // bytes per smem operand row == swizzle span (128 / 64)
   constexpr int kStages = S::kStages;
-  constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  // acc32: two accumulators (main products, correction terms) per stage
+  constexpr uint32_t kTmemCols = kAcc32 ? 4 * BLOCK_N : (2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N);
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
   static_assert(BLOCK_K == 64 || BLOCK_K == 32, "BLOCK_K");
 
@@ -379,6 +405,40 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
       long long t_wfull = 0, t_wtempty = 0;
       const long long t_begin = clock64();
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+        if constexpr (kAcc32) {
+          for (int kb0 = 0; kb0 < num_kb; kb0 += kAccChunkKb, ++tl) {
+            const int as = tl & 1;
+            mbar_wait(&tempty_bar[as], ((tl >> 1) & 1) ^ 1);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + as * 2 * BLOCK_N;
+            bool first_m = true, first_s = true;
+            const int kb1 = kb0 + kAccChunkKb < num_kb ? kb0 + kAccChunkKb : num_kb;
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after_sync();
+              const uint32_t sa = smem_u32(stage_base + stage * S::kStageBytes);
+              const uint64_t adesc = umma_desc_kmajor<kSwz>(sa);
+              const uint64_t bdesc = umma_desc_kmajor<kSwz>(sa + S::kABytes);
+#pragma unroll
+              const int k0 = (kb % p.k_chunks) * BLOCK_K;
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / 16; ++k) {
+                if (k0 + 16 * k < p.acc_main_k) {
+                  umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, first_m ? 0u : 1u);
+                  first_m = false;
+                } else {
+                  umma_f16_ss(d_tmem + BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, first_s ? 0u : 1u);
+                  first_s = false;
+                }
+              }
+              umma_commit(&empty_bar[stage]);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tfull_bar[as]);
+          }
+          --tl;      // the tile loop's own increment
+          continue;
+        }
         const int as = tl & 1;
         const uint32_t aphase = (tl >> 1) & 1;
         {
@@ -426,6 +486,63 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
     long long t_wtfull = 0;
     const long long t_begin = clock64();
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+      if constexpr (kAcc32) {
+        static_assert(!kAcc32 || (kSplit == 2 && BLOCK_N == 64), "acc32 variant: 2 x 32 register accumulators per thread");
+        constexpr int kMy = BLOCK_N / 64;           // 32-column chunks per thread (chunks half, half + 2)
+        const TileCoord tc = tile_coord(p, tile);
+        float acc[kMy][32], acc_s[kMy][32];       // main products / correction terms, summed at the end
+#pragma unroll
+        for (int j = 0; j < kMy; ++j)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[j][i] = acc_s[j][i] = 0.f;
+        for (int kb0 = 0; kb0 < num_kb; kb0 += kAccChunkKb, ++tl) {
+          const int as = tl & 1;
+          mbar_wait(&tfull_bar[as], (tl >> 1) & 1);
+          tc_fence_after_sync();
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 2 * BLOCK_N;
+          const int kb1 = kb0 + kAccChunkKb < num_kb ? kb0 + kAccChunkKb : num_kb;
+          const int touch = acc32_touch<BLOCK_K>(kb0, kb1, p.k_chunks, p.acc_main_k);
+#pragma unroll
+          for (int j = 0; j < kMy; ++j) {
+            uint32_t v[32];
+            if (touch & 2) {         // correction terms first: small + small, then the main partial sum on top
+              tmem_ld_32x32b_x32(t_row + BLOCK_N + (half + 2 * j) * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) acc_s[j][i] += __uint_as_float(v[i]);
+            }
+            if (touch & 1) {
+              tmem_ld_32x32b_x32(t_row + (half + 2 * j) * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) acc[j][i] += __uint_as_float(v[i]);     // fp32 add, round to nearest
+            }
+          }
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        --tl;
+        const int row = q * 32 + lane;
+        const int wo = tc.w0 + (row & (p.tw - 1)), ho = tc.h0 + ((row >> p.tw_log2) & (p.th - 1)),
+                  nn = tc.n0 + (row >> (p.tw_log2 + p.th_log2));
+        if (wo < p.Wo && ho < p.Ho && nn < p.N) {
+          const long long pix = (static_cast<long long>(nn) * p.Ho + ho) * p.Wo + wo;
+#pragma unroll
+          for (int j = 0; j < kMy; ++j) {
+            const int c0 = tc.nblk * BLOCK_N + (half + 2 * j) * 32;
+            float* yo = reinterpret_cast<float*>(p.y_f32) + pix * p.y_pix_stride + c0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (c0 + i < p.Cout_store) {
+                const float z = fmaf(acc[j][i] + acc_s[j][i], p.scale ? __ldg(p.scale + c0 + i) : 1.f, p.bias ? __ldg(p.bias + c0 + i) : 0.f);
+                yo[i] = apply_act(z, p.act);
+              }
+            }
+          }
+        }
+        continue;
+      }
       const int as = tl & 1;
       const uint32_t aphase = (tl >> 1) & 1;
       const TileCoord tc = tile_coord(p, tile);
@@ -513,10 +630,10 @@ static void pick_tile(int Wo, int Ho, int N, int* tw, int* th, int* tn) {
   }
 }
 
-template <int BLOCK_N, int BLOCK_K, int kSplit, bool kBf16>
+template <int BLOCK_N, int BLOCK_K, int kSplit, bool kBf16, bool kAcc32 = false>
 static int launch_conv(const ConvTmaps& tm, const ConvKArgs& ka, cudaStream_t stream) {
   using S = ConvSmem<BLOCK_N, BLOCK_K, kSplit>;
-  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, kSplit, kBf16>;
+  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, kSplit, kBf16, kAcc32>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     DYK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
@@ -595,6 +712,7 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
               "dyk_conv2d_fwd: Cout=%d Cout_store=%d (Cout_store must be a multiple of 8, >= Cout)", p->Cout,
               p->Cout_store);
   DYK_REQUIRE(!(p->out_f32 && p->upsample2x), "dyk_conv2d_fwd: out_f32 + upsample2x not supported");
+  DYK_REQUIRE(p->out_f32 >= 0 && p->out_f32 <= 2 && !(p->out_f32 == 2 && p->res), "dyk_conv2d_fwd: out_f32 = %d", p->out_f32);
   DYK_REQUIRE(p->y_pix_stride >= p->Cout_store && p->x_pix_stride >= p->Cin, "dyk_conv2d_fwd: stride < channels");
   DYK_REQUIRE((reinterpret_cast<uintptr_t>(p->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->y) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(p->w) & 15) == 0,
@@ -680,12 +798,15 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   const int taps = pair_w ? 6 : p->kh * p->kw;
   const int cin_eff = pair_w ? 64 : p->Cin;
   const long long m_tiles = (long long)ceil_div(gW, tw) * ceil_div(gH, th) * ceil_div(gN, tn);
-  const int BN = pick_block_n(p->Cout_store, m_tiles, taps * ceil_div(cin_eff, BK), BK);
+  int BN = pick_block_n(p->Cout_store, m_tiles, taps * ceil_div(cin_eff, BK), BK);
+  const bool acc32 = p->out_f32 == 2;
+  if (acc32) BN = 64;      // 2 x 32 register accumulators per epilogue thread
   // 16 epilogue warps when the tile time is the epilogue's: short main loop (<= 16 k-blocks) and an activation that costs
   // MUFU issue slots (Mish).  Measured: dyolov4 (Mish) 8.33 -> 8.09 ms, dyolov3 (leaky) 5.65 -> 5.75 ms, hence the act test.
   static const int force_split = getenv("DYK_EPI_SPLIT") ? atoi(getenv("DYK_EPI_SPLIT")) : 0;
   int split = (taps * ceil_div(cin_eff, BK) <= 16 && BN >= 64 && !p->out_f32 && p->act == DYK_ACT_MISH) ? 4 : 2;
   if (force_split == 2 || (force_split == 4 && BN >= 64)) split = force_split;
+  if (acc32) split = 2;
   if (pair_w) {      // one filter row = 96 contiguous elements [s][c]; a tap's tile is a 64-element window of it
     const cuuint64_t dims[3] = {96, 3, (cuuint64_t)p->Cout};
     const cuuint64_t str[2] = {96 * 2, 288 * 2};
@@ -742,6 +863,7 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   ka.act = p->act;
   ka.upsample2x = p->upsample2x;
   ka.out_f32 = p->out_f32;
+  ka.acc_main_k = acc32 ? p->Cin / 6 : 0;       // the operand is [x1|x2|x3|x1|x2|x1]: the first Cin/6 channels are x1 (* w1)
   ka.y_f32 = p->y;
   ka.y_pix_stride = p->y_pix_stride;
   ka.scale = p->scale; ka.bias = p->bias;
@@ -749,6 +871,11 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   ka.prof = g_conv_prof;
 
   const bool bf = p->dtype == DYK_BF16;
+  if (acc32) {
+    DYK_REQUIRE(BK == 64 && bf, "dyk_conv2d_fwd: out_f32 = 2 (fp32-accurate accumulation) needs bf16 operands and Cin > 32");
+    DYK_REQUIRE(p->Cin % 6 == 0, "dyk_conv2d_fwd: out_f32 = 2 expects the 6-way split operand (Cin %% 6 == 0)");
+    return launch_conv<64, 64, 2, true, true>(tm, ka, stream);
+  }
   if (BK == 64) return bf ? dispatch_n<64, true>(BN, split, tm, ka, stream) : dispatch_n<64, false>(BN, split, tm, ka, stream);
   return bf ? dispatch_n<32, true>(BN, split, tm, ka, stream) : dispatch_n<32, false>(BN, split, tm, ka, stream);
 }

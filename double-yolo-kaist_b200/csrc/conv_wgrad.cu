@@ -12,13 +12,18 @@
 //     out-of-bounds zero fill; stride-2 convolutions read the four parity planes of x like the forward kernel).
 //   * one CTA owns one (128 out-channel block, BLOCK_N in-channel block, group of kTaps taps) and one contiguous range
 //     of the pixel blocks (split-K); accumulators (kTaps x BLOCK_N fp32 columns) stay in TMEM for the whole range.
-//   * partial results go to a workspace [split][tap][Cout_pad][Cin_pad]; a second kernel sums the splits in a fixed
-//     order and writes / accumulates the OIHW gradient -> deterministic, no float atomics.
+//   * the CTAs of one thread-block cluster (2 by default) are consecutive splits of the same tile: after the main loop
+//     every CTA parks its fp32 accumulator tile in its own shared memory (the drained operand pipeline), and each CTA sums
+//     one row slab over all CTAs of the cluster through distributed shared memory, in rank order.  Only that sum goes to
+//     the workspace [split / cluster][tap][Cout_pad][Cin_pad]; with one wave of CTAs and pairs the partial volume of a
+//     128x128x9 layer drops from 58 MB to 14.5 MB.  A second kernel sums the remaining partials in a fixed order and
+//     writes / accumulates the OIHW gradient -> deterministic, no float atomics.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
 #include "common.h"
 #include "ptx.cuh"
 #include "conv_common.cuh"
 #include "vec.cuh"
+#include <cstdlib>
 #include <cstring>
 
 namespace dyk {
@@ -169,16 +174,26 @@ conv_wgrad_kernel(const __grid_constant__ WgradTmaps tm, const WgradKArgs p) {
       }
       umma_commit(done_bar);
     }
-  } else {
-    // epilogue: TMEM lane = out channel; this warp owns lanes q*32 .. q*32+31
-    const int q = warp_idx & 3;
-    const int co = cob * 128 + q * 32 + lane;
+  }
+  // ------------------------------------------------------------------ epilogue: in-cluster reduction of the split-K tiles
+  // Per tap: (1) the four epilogue warps copy the CTA's 128 x BLOCK_N fp32 accumulator tile from TMEM (lane = out channel)
+  // into shared memory (float4 index XOR-swizzled by the row so that the 32 rows of a warp do not collide on banks);
+  // (2) cluster barrier; (3) CTA `rank` sums rows [rank*128/CS, (rank+1)*128/CS) over the CS tiles in rank order (DSMEM
+  // loads) and writes them to the workspace; (4) cluster barrier before the tile buffer is reused for the next tap.
+  __syncwarp();   // the single-thread producer / MMA roles rejoin their warps before the warp-aligned cluster barriers
+  const uint32_t cs = cluster_nctarank(), crank = cluster_ctarank();
+  constexpr int kRowF4 = BLOCK_N / 4;
+  float4* tile = reinterpret_cast<float4*>(smem);
+  if (warp_idx >= 2) {
     mbar_wait(done_bar, 0);
     tc_fence_after_sync();
+  }
+  const int q = warp_idx & 3;
+  const unsigned csplit = split / cs;
 #pragma unroll 1
-    for (int t = 0; t < kTaps; ++t) {
-      const int tap = tg * kTaps + t;
-      float* dst = p.part + (((long long)split * p.taps_total + tap) * p.Cout_pad + co) * p.Cin_pad + cib * BLOCK_N;
+  for (int t = 0; t < kTaps; ++t) {
+    if (warp_idx >= 2) {
+      const int row = q * 32 + lane;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 32) {
         uint32_t v[32];
@@ -190,11 +205,31 @@ conv_wgrad_kernel(const __grid_constant__ WgradTmaps tm, const WgradKArgs p) {
           for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(dst + c + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        for (int j = 0; j < 8; ++j)
+          tile[row * kRowF4 + (((c >> 2) + j) ^ (row & 7))] =
+              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                          __uint_as_float(v[4 * j + 3]));
       }
     }
+    cluster_sync_all();
+    {
+      const int tap = tg * kTaps + t;
+      const int rows_per = 128 / (int)cs;
+      const int row0 = (int)crank * rows_per;
+      float* dst = p.part + (((long long)csplit * p.taps_total + tap) * p.Cout_pad + cob * 128) * p.Cin_pad + cib * BLOCK_N;
+      const uint32_t tile_addr = smem_u32(tile);
+      for (int e = threadIdx.x; e < rows_per * kRowF4; e += kWgThreads) {
+        const int row = row0 + e / kRowF4, c4 = e % kRowF4;
+        const uint32_t off = (uint32_t)(row * kRowF4 + (c4 ^ (row & 7))) * 16u;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (uint32_t r = 0; r < cs; ++r) {
+          const float4 v = ld_shared_cluster_f4(cluster_map_shared(tile_addr + off, r));
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        *reinterpret_cast<float4*>(dst + (long long)row * p.Cin_pad + c4 * 4) = acc;
+      }
+    }
+    cluster_sync_all();
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -306,13 +341,29 @@ static WgradPlan wgrad_plan(int Cin, int Cout, int k) {
   w.G = w.co_blocks * w.ci_blocks * w.tap_groups;
   return w;
 }
-static int wgrad_max_splits(const WgradPlan& w) {
+// Split-K factor and cluster size.  Measured on the dyolov4_fshare bs-16 training step (profiles/r02_wgrad_sweep.txt;
+// DYK_WG_CLUSTER / DYK_WG_WAVES override):  one CTA per SM over the whole grid (one wave) beats two (52.9 -> 49.8 ms per
+// step: half the partial tiles to write and to reduce, one prologue per SM); pairs of splits reduced through DSMEM
+// (cluster of 2) gain a little more (49.5 ms); clusters of 4 / 8 LOSE (53.5 / 54.1 ms): a cluster needs all its SMs free in
+// one GPC at once, the grid then runs in more, emptier waves, and every CTA waits for the slowest of its cluster.
+static void wgrad_splits(const WgradPlan& w, int n_kb, int* splits_out, int* cs_out) {
+  static const int max_cs = getenv("DYK_WG_CLUSTER") ? atoi(getenv("DYK_WG_CLUSTER")) : 2;
+  static const int waves = getenv("DYK_WG_WAVES") ? atoi(getenv("DYK_WG_WAVES")) : 1;
+  int want = (waves * num_sms()) / w.G;
+  if (want > n_kb) want = n_kb;
+  if (want < 1) want = 1;
+  int cs = 1;
+  while (cs * 2 <= want && cs * 2 <= max_cs) cs *= 2;
+  *cs_out = cs;
+  *splits_out = want / cs * cs;
+}
+static int wgrad_max_partials(const WgradPlan& w) {     // upper bound of splits / cluster size over all n_kb
   int s = (2 * num_sms()) / w.G;
   return s < 1 ? 1 : s;
 }
 
 template <int BLOCK_N, int kTaps, bool kBf16>
-static int launch_wgrad(const WgradTmaps& tm, const WgradKArgs& ka, int grid, cudaStream_t stream) {
+static int launch_wgrad(const WgradTmaps& tm, const WgradKArgs& ka, int grid, int cs, cudaStream_t stream) {
   using S = WgradSmem<BLOCK_N, kTaps>;
   auto kern = conv_wgrad_kernel<BLOCK_N, kTaps, kBf16>;
   static bool configured = false;
@@ -320,7 +371,19 @@ static int launch_wgrad(const WgradTmaps& tm, const WgradKArgs& ka, int grid, cu
     DYK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
-  kern<<<grid, kWgThreads, S::kTotal, stream>>>(tm, ka);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kWgThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DYK_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm, ka));
   DYK_LAUNCH_OK("conv_wgrad_kernel");
   return DYK_OK;
 }
@@ -332,7 +395,7 @@ using namespace dyk;
 extern "C" __attribute__((visibility("default"))) int64_t dyk_conv2d_wgrad_workspace_bytes(int32_t Cin, int32_t Cout, int32_t k) {
   if (Cin <= 0 || Cout <= 0 || k <= 0) return 0;
   const WgradPlan w = wgrad_plan(Cin, Cout, k);
-  return (int64_t)wgrad_max_splits(w) * k * k * (w.co_blocks * 128) * (int64_t)(w.ci_blocks * w.BN) * 4;
+  return (int64_t)wgrad_max_partials(w) * k * k * (w.co_blocks * 128) * (int64_t)(w.ci_blocks * w.BN) * 4;
 }
 
 extern "C" __attribute__((visibility("default"))) int dyk_conv2d_wgrad(
@@ -389,11 +452,11 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_wgrad(
   const long long nkb = (long long)ka.tiles_w * ka.tiles_h * N;
   DYK_REQUIRE(nkb < (1ll << 30), "dyk_conv2d_wgrad: too many pixel blocks");
   ka.n_kb = (int)nkb;
-  int splits = wgrad_max_splits(wp);
-  if (splits > ka.n_kb) splits = ka.n_kb;
-  ka.kb_per_split = ceil_div(ka.n_kb, splits);
-  splits = ceil_div(ka.n_kb, ka.kb_per_split);
+  int splits, cs;
+  wgrad_splits(wp, ka.n_kb, &splits, &cs);
+  ka.kb_per_split = ceil_div(ka.n_kb, splits);     // trailing splits may get no pixel block: they contribute zeros
   ka.splits = splits;
+  const int parts = splits / cs;
   ka.co_blocks = wp.co_blocks; ka.ci_blocks = wp.ci_blocks; ka.tap_groups = wp.tap_groups;
   ka.kw = k; ka.stride = stride; ka.pad = pad;
   ka.Cout_pad = wp.co_blocks * 128;
@@ -404,12 +467,12 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_wgrad(
   ka.fd_ci_blocks = make_fastdiv((unsigned)wp.ci_blocks);
   ka.fd_tap_groups = make_fastdiv((unsigned)wp.tap_groups);
   ka.part = reinterpret_cast<float*>(workspace);
-  const int64_t need = (int64_t)splits * ka.taps_total * ka.Cout_pad * (int64_t)ka.Cin_pad * 4;
+  const int64_t need = (int64_t)parts * ka.taps_total * ka.Cout_pad * (int64_t)ka.Cin_pad * 4;
   DYK_REQUIRE(workspace_bytes >= need, "dyk_conv2d_wgrad: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes,
               (long long)need);
   const int grid = wp.G * splits;
   const bool bf = dtype == DYK_BF16;
-#define DYK_WG(BN_, T_) (bf ? launch_wgrad<BN_, T_, true>(tm, ka, grid, stream) : launch_wgrad<BN_, T_, false>(tm, ka, grid, stream))
+#define DYK_WG(BN_, T_) (bf ? launch_wgrad<BN_, T_, true>(tm, ka, grid, cs, stream) : launch_wgrad<BN_, T_, false>(tm, ka, grid, cs, stream))
   if (wp.kTaps == 3) rc = wp.BN == 64 ? DYK_WG(64, 3) : DYK_WG(128, 3);
   else rc = wp.BN == 64 ? DYK_WG(64, 1) : (wp.BN == 128 ? DYK_WG(128, 1) : DYK_WG(256, 1));
 #undef DYK_WG
@@ -417,7 +480,7 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_wgrad(
   const long long total = (long long)Cout_real * ka.taps_total * Cin_real;
   long long g = (total + 255) / 256;
   if (g > num_sms() * 16) g = num_sms() * 16;
-  wgrad_reduce_kernel<<<(int)g, 256, 0, stream>>>(ka.part, splits, ka.taps_total, ka.Cout_pad, ka.Cin_pad, Cout_real, Cin_real,
+  wgrad_reduce_kernel<<<(int)g, 256, 0, stream>>>(ka.part, parts, ka.taps_total, ka.Cout_pad, ka.Cin_pad, Cout_real, Cin_real,
                                                   grad, accumulate);
   DYK_LAUNCH_OK("wgrad_reduce_kernel");
   return DYK_OK;

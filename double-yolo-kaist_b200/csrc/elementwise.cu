@@ -347,8 +347,16 @@ extern "C" __attribute__((visibility("default"))) int dyk_se_gate(const void* x,
   const dim3 grid((C + 63) / 64, slabs, N);
   DYK_DISPATCH_DTYPE(dtype, (se_pool_kernel<kBf16><<<grid, 256, 0, stream>>>((const uint8_t*)x, xs, HW, C, slabs, pooled)));
   DYK_LAUNCH_OK("se_pool_kernel");
+  return dyk_se_mlp(pooled, slabs, N, HW, C, w1, b1, w2, b2, Csq, gate, stream_);
+}
+
+extern "C" __attribute__((visibility("default"))) int dyk_se_mlp(float* pooled, int32_t slabs, int32_t N, int32_t HW, int32_t C, const float* w1,
+                          const float* b1, const float* w2, const float* b2, int32_t Csq, float* gate, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYK_REQUIRE(pooled && w1 && b1 && w2 && b2 && gate, "dyk_se_mlp: null pointer");
+  DYK_REQUIRE((size_t)(C + Csq) * 4 <= 48 * 1024, "dyk_se_mlp: C + Csq too large");
   // hidden activations live behind the per-slab partial sums in the caller's scratch (N * 32 * C floats >= N * (slabs * C + Csq))
-  DYK_REQUIRE(Csq <= C && slabs <= 31, "dyk_se_gate: Csq=%d must not exceed C=%d", Csq, C);
+  DYK_REQUIRE(Csq > 0 && Csq <= C && slabs >= 1 && slabs <= 31, "dyk_se_mlp: Csq=%d must not exceed C=%d (slabs=%d)", Csq, C, slabs);
   float* hid = pooled + (size_t)N * slabs * C;
   se_fc1_kernel<<<dim3(N, (Csq + 7) / 8), 256, C * sizeof(float), stream>>>(pooled, slabs, 1.f / (float)HW, C, Csq, w1, b1, hid);
   DYK_LAUNCH_OK("se_fc1_kernel");

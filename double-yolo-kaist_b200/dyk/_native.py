@@ -56,6 +56,16 @@ SIGNATURES = {
     "dyk_upsample_nearest": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_se_gate": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
     "dyk_scale_channels": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "dyk_se_mlp": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    # ---- fp32-accurate mode
+    "dyk_f32_split6": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp]),
+    "dyk_f32_pack_split6": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "dyk_f32_stem_nchw_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64] + [_i32] * 10 + [_vp]),
+    "dyk_f32_dwconv2d_fwd": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _i64] + [_i32] * 8 + [_vp]),
+    "dyk_f32_fused_add": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp]),
+    "dyk_f32_maxpool2d": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dyk_f32_upsample_nearest": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dyk_f32_se": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "dyk_yolo_decode": (_i32, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _f32, _i32, _i64,
                                _i64, _i32, _vp]),
     "dyk_nms_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
@@ -92,6 +102,9 @@ SIGNATURES = {
     "dyk_frames_to_im2col32": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_pack_weights_multi": (_i32, [_vp, _i32, _i32, _i32, _vp]),
     "dyk_pack_weights_ohwi": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dyk_optim_block_elems": (_i32, []),
+    "dyk_optim_sgd_multi": (_i32, [_vp, _i32, _i64, _f32, _f32, _f32, _f32, _i32, _i32, _vp, _vp, _vp]),
+    "dyk_optim_adam_multi": (_i32, [_vp, _i32, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _vp, _vp, _vp]),
     "dyk_nchw_f32_to_nhwc": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_nhwc_to_nchw_f32": (_i32, [_vp, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
 }

@@ -171,6 +171,72 @@ def nhwc_se(x: View, y: View, w1, b1, w2, b2, pooled, gate) -> None:
     nat.count_launches(4)
 
 
+# ------------------------------------------------------------------------------------------ fp32-accurate mode
+# (include/dyk_b200.h "fp32-accurate mode"; csrc/f32_path.cu).  Views are channel slices of fp32 NHWC buffers.
+def f32_pack_conv_weight(w_oihw: torch.Tensor) -> torch.Tensor:
+    """OIHW fp32 -> [O][kh][kw][6I] bf16 = [w1|w1|w1|w2|w2|w3], w = w1 + w2 + w3 (dyk_f32_pack_split6)."""
+    O, I, kh, kw = w_oihw.shape
+    w = w_oihw.detach().to(torch.float32).contiguous()
+    out = torch.empty((O, kh, kw, 6 * I), dtype=torch.bfloat16, device=w.device)
+    nat.call("dyk_f32_pack_split6", _p(w), _p(out), O, I, kh, kw, _stream())
+    nat.count_launches()
+    return out
+
+
+def f32_conv(x: View, w_split: torch.Tensor, scale, bias, y: View, split_buf: torch.Tensor, *, k, stride, pad, act,
+             cout) -> None:
+    """act(scale * conv(x, w) + bias) with fp32 accuracy on the bf16 tensor-core kernel: x is split into the 6*Cin-channel
+    bf16 operand [x1|x2|x3|x1|x2|x1] (scratch `split_buf`), the convolution accumulates the six partial products in fp32
+    and its epilogue stores fp32."""
+    n = x.npix * 6 * x.C
+    if split_buf.numel() < n:
+        raise nat.NativeError("f32_conv: split scratch too small")
+    sv = View(split_buf[:n].view(x.N, x.H, x.W, 6 * x.C), 0, 6 * x.C)
+    nat.call("dyk_f32_split6", x.ptr, x.stride, sv.ptr, x.npix, x.C, _stream())
+    nat.count_launches()
+    nhwc_conv(sv, w_split, scale, bias, y, k=k, stride=stride, pad=pad, act=act, out_f32=2, cout=cout)
+
+
+def f32_stem(x_nchw: torch.Tensor, w_f32_ohwi, scale, bias, y: View, *, k, stride, pad, act) -> None:
+    N, Cin, H, W = x_nchw.shape
+    kind = {torch.float32: 0, torch.uint8: 1}[x_nchw.dtype]
+    nat.call("dyk_f32_stem_nchw_fwd", _p(x_nchw), _p(w_f32_ohwi), _p(scale), _p(bias), y.ptr, y.stride, N, H, W, Cin, y.C, k,
+             stride, pad, nat.ACT_IDS[act], kind, _stream())
+    nat.count_launches()
+
+
+def f32_dwconv(x: View, w_kkc, scale, bias, y: View, *, k, stride, pad, act) -> None:
+    nat.call("dyk_f32_dwconv2d_fwd", x.ptr, x.stride, _p(w_kkc), _p(scale), _p(bias), y.ptr, y.stride, x.N, x.H, x.W, x.C, k,
+             stride, pad, nat.ACT_IDS[act], _stream())
+    nat.count_launches()
+
+
+def f32_add(a: View, b: View, y: View, wts=None) -> None:
+    nat.call("dyk_f32_fused_add", a.ptr, a.stride, None if b is None else b.ptr, 0 if b is None else b.stride, y.ptr,
+             y.stride, a.npix, y.C, _p(wts), _stream())
+    nat.count_launches()
+
+
+def f32_copy(src: View, dst: View) -> None:
+    f32_add(src, None, dst)
+
+
+def f32_maxpool(x: View, y: View, k, stride) -> None:
+    nat.call("dyk_f32_maxpool2d", x.ptr, x.stride, y.ptr, y.stride, x.N, x.H, x.W, x.C, k, stride, _stream())
+    nat.count_launches()
+
+
+def f32_upsample(x: View, y: View, s) -> None:
+    nat.call("dyk_f32_upsample_nearest", x.ptr, x.stride, y.ptr, y.stride, x.N, x.H, x.W, x.C, s, _stream())
+    nat.count_launches()
+
+
+def f32_se(x: View, y: View, w1, b1, w2, b2, pooled, gate) -> None:
+    nat.call("dyk_f32_se", x.ptr, x.stride, y.ptr, y.stride, x.N, x.H * x.W, x.C, _p(w1), _p(b1), _p(w2), _p(b2), w1.shape[0],
+             _p(pooled), _p(gate), _stream())
+    nat.count_launches(4)
+
+
 def yolo_decode(p_head: torch.Tensor, p_stride, p_out, io_out, *, N, ny, nx, na, no, anchor_vec, stride, v4,
                 rows_total, row_off, in_kind=2) -> None:
     nat.call("dyk_yolo_decode", _p(p_head), p_stride, _p(p_out), _p(io_out), N, ny, nx, na, no, _p(anchor_vec),

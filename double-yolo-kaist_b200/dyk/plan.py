@@ -398,7 +398,7 @@ class WeightBank:
         conv, bn, dtype, flavor = e["conv"], e["bn"], e["dtype"], e["flavor"]
         k = conv.kernel_size[0]
         if flavor == "dense":
-            w = ops.pack_conv_weight(conv.weight, dtype)
+            w = ops.f32_pack_conv_weight(conv.weight) if dtype == torch.float32 else ops.pack_conv_weight(conv.weight, dtype)
         elif flavor == "stem":
             w = conv.weight.detach().float().permute(0, 2, 3, 1).contiguous()
         else:  # depthwise: [k][k][C] fp32
@@ -423,12 +423,15 @@ class Plan:
         self.B, self.dtype, self.device, self.dual = B, dtype, device, dual
         raw, vals, self.img0, self.img1 = build_ops(model, H, W, dual)
         self.layer_vals = vals   # Value visible at every cfg layer index (diagnostics: tools/layer_parity.py)
-        self.ops = fuse(raw)
+        # fp32-accurate mode (compute_dtype = torch.float32, csrc/f32_path.cu): fp32 buffers, split-bf16 tensor-core convs,
+        # no residual / upsample fusion into the conv epilogue (its fp32 store path is the plain one), one lane
+        self.f32 = dtype == torch.float32
+        self.ops = raw if self.f32 else fuse(raw)
         cascade_pools(self.ops)
         mark_heads(self.ops)
         place_concats(self.ops)
         liveness(self.ops)
-        self.two_lanes = os.environ.get("DYK_LANES", "2") != "1"
+        self.two_lanes = os.environ.get("DYK_LANES", "2") != "1" and not self.f32
         self.lanes, self.producer = assign_lanes(self.ops)
         if not self.two_lanes:
             self.lanes = [min(l, 0) for l in self.lanes]
@@ -470,7 +473,7 @@ class Plan:
         self.bytes_allocated = 0
         for rid in sorted(order, key=lambda r: roots[r][1]):
             root, first, last, lanes = roots[rid]
-            dt = torch.float32 if root.f32 else self.dtype
+            dt = torch.float32 if (root.f32 or self.f32) else self.dtype
             shape = (self.B, root.H, root.W, root.C)
             lane = next(iter(lanes)) if len(lanes) == 1 else None
             buf = None
@@ -496,6 +499,11 @@ class Plan:
     # ---- launches -------------------------------------------------------------------------------
     def _bind(self, model, bank):
         self.stem_steps, self.steps = [], []
+        if self.f32:      # one scratch for the split operand [x1|x2|x3|x1|x2|x1] of the widest dense convolution input
+            need = max((self.B * op.src.H * op.src.W * 6 * op.src.C for op in self.ops
+                        if isinstance(op, ConvOp) and op.flavor == "dense"), default=0)
+            self.split_buf = torch.empty(max(need, 1), dtype=torch.bfloat16, device=self.device)
+            self.bytes_allocated += need * 2
         self.yolo = []
         yolos = [op for op in self.ops if isinstance(op, YoloOp)]
         rows_total = sum(op.module.na * op.src.H * op.src.W for op in yolos)
@@ -555,6 +563,13 @@ class Plan:
                 if fl == "stem":
                     which = 0 if op.src is self.img0 else 1
                     self.stem_steps.append((which, e, op.out.view, dict(k=k, stride=s, pad=p, act=op.act)))
+                elif self.f32 and fl == "dense":
+                    self.steps.append(_Call(ops.f32_conv, op.src.view, e["w"], e["scale"], e["bias"], op.out.view, self.split_buf,
+                                            k=k, stride=s, pad=p, act=op.act, cout=op.conv.out_channels))
+                    self.steps[-1].launches = 2
+                elif self.f32:
+                    self.steps.append(_Call(ops.f32_dwconv, op.src.view, e["w"], e["scale"], e["bias"], op.out.view,
+                                            k=k, stride=s, pad=p, act=op.act))
                 elif fl == "dense":
                     kw = dict(k=k, stride=s, pad=p, act=op.act, res=op.res.view if op.res is not None else None,
                               upsample2x=op.upsample2x, out_f32=op.out_f32)
@@ -568,24 +583,25 @@ class Plan:
                 for s, off in op.copies:
                     if s.f32:
                         raise nat.NativeError(f"layer {op.layer}: cannot concatenate an fp32 head tensor")
-                    self.steps.append(_Call(ops.nhwc_copy, s.view, View(op.out.view.buf, op.out.view.c_off + off, s.C)))
+                    self.steps.append(_Call(ops.f32_copy if self.f32 else ops.nhwc_copy, s.view,
+                                            View(op.out.view.buf, op.out.view.c_off + off, s.C)))
             elif isinstance(op, PoolOp):
-                self.steps.append(_Call(ops.nhwc_maxpool, op.src.view, op.out.view, op.k, op.stride))
+                self.steps.append(_Call(ops.f32_maxpool if self.f32 else ops.nhwc_maxpool, op.src.view, op.out.view, op.k, op.stride))
             elif isinstance(op, UpOp):
-                self.steps.append(_Call(ops.nhwc_upsample, op.src.view, op.out.view, op.s))
+                self.steps.append(_Call(ops.f32_upsample if self.f32 else ops.nhwc_upsample, op.src.view, op.out.view, op.s))
             elif isinstance(op, SEOp):
                 w1, b1, w2, b2 = ops.se_weights(op.module.fc1, op.module.fc2)
                 hold = {"w1": w1, "b1": b1, "w2": w2, "b2": b2, "mod": op.module}
                 self._se_holds = getattr(self, "_se_holds", []) + [hold]
                 pooled = torch.empty((self.B, 32, op.src.C), dtype=torch.float32, device=dev)   # DYK_SE_MAX_SLABS partials
                 gate = torch.empty((self.B, op.src.C), dtype=torch.float32, device=dev)
-                self.steps.append(_Call(ops.nhwc_se, op.src.view, op.out.view, w1, b1, w2, b2, pooled, gate))
+                self.steps.append(_Call(ops.f32_se if self.f32 else ops.nhwc_se, op.src.view, op.out.view, w1, b1, w2, b2, pooled, gate))
             elif isinstance(op, YoloOp):
                 m = op.module
                 ny, nx = op.src.H, op.src.W
                 if (m.nx, m.ny) != (nx, ny) or m.grid is None or m.anchor_vec.device != dev:
                     m.create_grids((nx, ny), dev)
-                if not op.src.f32:
+                if not (op.src.f32 or self.f32):
                     raise nat.NativeError(f"layer {op.layer}: [yolo] must follow a linear conv without batch norm")
                 p_out = torch.empty((self.B, m.na, ny, nx, m.no), dtype=torch.float32, device=dev)
                 self.p_outs.append(p_out)
@@ -614,7 +630,7 @@ class Plan:
                     f"layer {op.layer}: channel-mismatched / >2-way weighted shortcut is only available through "
                     "build_utils.layers.WeightedFeatureFusion.forward (no shipped cfg uses it)")
             dst = op.out.view if last else ops.new_view(self.B, x.H, x.W, x.C, self.dtype, self.device)
-            self.steps.append(_Call(ops.nhwc_add, cur, a.view, dst, wall))
+            self.steps.append(_Call(ops.f32_add if self.f32 else ops.nhwc_add, cur, a.view, dst, wall))
             cur = dst
 
     def refresh_se(self):
@@ -624,8 +640,9 @@ class Plan:
 
     # ---- execution ------------------------------------------------------------------------------
     def run_stems(self, x, y):
+        stem = ops.f32_stem if self.f32 else ops.nhwc_stem
         for which, e, out, kw in self.stem_steps:
-            ops.nhwc_stem(x if which == 0 else y, e["w"], e["scale"], e["bias"], out, **kw)
+            stem(x if which == 0 else y, e["w"], e["scale"], e["bias"], out, **kw)
 
     def run_body(self):
         side = self.side_stream
@@ -733,8 +750,8 @@ class PlanCache:
         if y is not None and (y.shape != x.shape or y.device != x.device):
             raise ValueError("visible and LWIR batches must have the same shape and device")
         dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else model.compute_dtype
-        if dtype not in (torch.float16, torch.bfloat16):
-            raise nat.NativeError(f"compute dtype {dtype} is not supported (float16 / bfloat16)")
+        if dtype not in (torch.float16, torch.bfloat16, torch.float32):
+            raise nat.NativeError(f"compute dtype {dtype} is not supported (float16 / bfloat16 / float32)")
 
         def prep(t):
             if t is None:

@@ -177,9 +177,10 @@ def _sub_dgrad_weights(w_dgrad, k, pad, ph, pw, offs_h, offs_w):
     """Sub-kernel of the rotated dgrad weights for output parity (ph, pw): taps ordered by increasing dz offset.
     w_dgrad[ci][r'][s'][co] = W[co][ci][k-1-r'][k-1-s'];  dz offset t_h <-> original tap r = ph + pad - 2*t_h.
     (Not cached: w_dgrad is re-packed every step, and a pointer-keyed cache would alias recycled allocations.)"""
-    rs = [k - 1 - (ph + pad - 2 * t) for t in offs_h]      # index into the rotated tensor
+    rs = [k - 1 - (ph + pad - 2 * t) for t in offs_h]      # index into the rotated tensor: consecutive offsets = every 2nd tap
     ss = [k - 1 - (pw + pad - 2 * t) for t in offs_w]
-    return w_dgrad[:, rs][:, :, ss].contiguous()           # layout-only gather of parameter taps (host-side packing)
+    # strided slices, not index lists: no host->device index copy, so the step stays CUDA-graph capturable
+    return w_dgrad[:, rs[0]:rs[-1] + 1:2, ss[0]:ss[-1] + 1:2].contiguous()   # layout-only gather of parameter taps
 
 
 def conv_wgrad(x: View, dz: View, grad_w: torch.Tensor, *, k: int, stride: int, pad: int, accumulate: bool,

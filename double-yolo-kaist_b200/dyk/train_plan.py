@@ -24,6 +24,8 @@ saved activations (the reference never does that).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -50,8 +52,12 @@ class _Grad:
 
 
 class TrainPlan:
-    def __init__(self, model, B, H, W, dtype, dual, device):
+    def __init__(self, model, B, H, W, dtype, dual, device, in_dtype=torch.float32):
         self.model, self.B, self.dtype, self.device, self.dual = model, B, dtype, device, dual
+        # Static frame buffers: the caller's batches are copied in (31 MB per uint8 bs-16 pair), so every launch of a step
+        # reads fixed addresses and the whole step can be replayed as CUDA graphs.
+        self.in_x = torch.empty((B, 3, H, W), dtype=in_dtype, device=device)
+        self.in_y = torch.empty((B, 3, H, W), dtype=in_dtype, device=device) if dual else None
         self.ops, self.layer_vals, self.img0, self.img1 = P.build_ops(model, H, W, dual)
         for op in self.ops:
             if isinstance(op, P.ConvOp):
@@ -68,6 +74,13 @@ class TrainPlan:
         self._alloc_forward()
         self._bind_forward()
         self._bind_backward()
+        # gradients of a step are produced in this buffer (one view per parameter) and handed out as a copy
+        self.flat = torch.zeros(self.grad_numel, dtype=torch.float32, device=device)
+        self.dps_in = [torch.zeros_like(po) for po in self.p_outs]
+        self._sig = None
+        self._fwd_graph, self._fwd_warm, self._fwd_launches = None, False, 0
+        self._bwd_graphs, self._bwd_key, self._bwd_warm, self._bwd_launches, self._seg_ends = None, None, False, [], []
+        self.graph_failed = False
 
     # ------------------------------------------------------------------------------------------ storage
     def _new(self, Cc, H, W, f32=False):
@@ -163,7 +176,7 @@ class TrainPlan:
 
         def run(x, y):
             if st["stem"]:
-                src = x if op.src is self.img0 else y
+                src = self.in_x if op.src is self.img0 else self.in_y
                 st["x_in"] = src
                 w = conv.weight.detach().float().permute(0, 2, 3, 1).contiguous()
                 ops.nhwc_stem(src, w, None, None, st["z"], k=k, stride=s, pad=p, act="linear")
@@ -197,36 +210,92 @@ class TrainPlan:
         steps.append(lambda x, y, o=op: ops.nhwc_add(o.x.view, o.others[0].view, o.out.view, o.wall))
         return steps
 
-    def _pack_all(self):
-        """One launch re-packs every dense convolution weight into its forward and data-gradient layouts (the optimizer
-        changed them since the last step).  The descriptor table holds raw pointers, so it is rebuilt whenever a
-        parameter's storage moved (.to(), load of a new tensor, ...)."""
+    def _signature(self):
+        """Everything a captured step bakes in that the caller may change between steps: parameter / buffer storage
+        addresses (graphs and the packing table hold raw pointers) and the BatchNorm scalars."""
+        ptrs = tuple(t.data_ptr() for t in self._sig_tensors)
+        return ptrs, tuple((bn.eps, bn.momentum) for bn in self.bns)
+
+    def _prepare(self):
+        """Host-side part of a step (never captured): rebuild the weight-packing table and drop the graphs when a
+        parameter's storage moved (.to(), load of a new tensor, ...) or a BatchNorm's eps / momentum changed."""
+        if not hasattr(self, "_sig_tensors"):
+            self._sig_tensors = list(self.model.parameters()) + list(self.model.buffers())
+        sig = self._signature()
+        if sig == self._sig:
+            return
+        self._sig = sig
+        self._fwd_graph, self._bwd_graphs = None, None
         sts = [st for st in self.convs if st.get("multi")]
+        self._pack_n = len(sts)
         if not sts:
             return
-        sig = tuple(st["conv"].weight.data_ptr() for st in sts)
-        if getattr(self, "_pack_sig", None) != sig:
-            rows, tiles = [], 0
-            for st in sts:
-                wt = st["conv"].weight
-                if not wt.is_contiguous() or wt.dtype != torch.float32:
-                    raise nat.NativeError("convolution weights must be contiguous float32 parameters")
-                O, I, k = wt.shape[0], wt.shape[1], st["k"]
-                if st["wd"].shape[3] < O or st["wd"].shape[0] != I or st["w"].shape[0] != O:
-                    raise nat.NativeError("internal: packed weight buffers do not match the convolution's shape")
-                rows.append([wt.data_ptr(), st["w"].data_ptr(), st["wd"].data_ptr(), O, I, k * k, st["wd"].shape[3], tiles])
-                tiles += ((O + 31) // 32) * ((I + 31) // 32)
-            self._pack_desc = torch.tensor(rows, dtype=torch.int64).to(self.device)
-            self._pack_tiles, self._pack_sig = tiles, sig
-        nat.call("dyk_pack_weights_multi", ops._p(self._pack_desc), len(sts), self._pack_tiles, ops._DT[self.dtype], ops._stream())
+        rows, tiles = [], 0
+        for st in sts:
+            wt = st["conv"].weight
+            if not wt.is_contiguous() or wt.dtype != torch.float32:
+                raise nat.NativeError("convolution weights must be contiguous float32 parameters")
+            O, I, k = wt.shape[0], wt.shape[1], st["k"]
+            if st["wd"].shape[3] < O or st["wd"].shape[0] != I or st["w"].shape[0] != O:
+                raise nat.NativeError("internal: packed weight buffers do not match the convolution's shape")
+            rows.append([wt.data_ptr(), st["w"].data_ptr(), st["wd"].data_ptr(), O, I, k * k, st["wd"].shape[3], tiles])
+            tiles += ((O + 31) // 32) * ((I + 31) // 32)
+        self._pack_desc = torch.tensor(rows, dtype=torch.int64).to(self.device)
+        self._pack_tiles = tiles
+
+    def _pack_all(self):
+        """One launch re-packs every dense convolution weight into its forward and data-gradient layouts (the optimizer
+        changed them since the last step); the descriptor table is maintained by _prepare."""
+        if not self._pack_n:
+            return
+        nat.call("dyk_pack_weights_multi", ops._p(self._pack_desc), self._pack_n, self._pack_tiles, ops._DT[self.dtype], ops._stream())
         nat.count_launches()
 
-    def forward(self, x, y):
+    def _forward_body(self):
         self._pack_all()
         for f in self.fwd:
-            f(x, y)
+            f(self.in_x, self.in_y)
         if self.bns:
             torch._foreach_add_([bn.num_batches_tracked for bn in self.bns], 1)   # counters, not arithmetic of the path
+
+    def _graphs_on(self):
+        return (self.model.use_cuda_graph and not self.graph_failed and self.device.type == "cuda"
+                and os.environ.get("DYK_TRAIN_GRAPH", "1") != "0" and not torch.cuda.is_current_stream_capturing())
+
+    def _capture(self, body):
+        """Capture `body` (native launches only) into a CUDA graph; on failure fall back to eager launches for good."""
+        g = torch.cuda.CUDAGraph()
+        try:
+            # thread_local: the NCCL watchdog thread may query events while this thread captures
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                body()
+            return g
+        except Exception as exc:  # noqa: BLE001 - same native kernels, launched one by one
+            import warnings
+            warnings.warn(f"CUDA graph capture of the training plan failed ({type(exc).__name__}: {exc}); "
+                          "running the same native kernels as individual launches")
+            self.graph_failed = True
+            torch.cuda.synchronize()
+            return None
+
+    def forward(self, x, y):
+        """One training forward: frames are copied into the plan's static buffers, then the ~900 launches (weight packing,
+        convolutions, batch statistics, BN + activation, pools, SE, head permutes) run as ONE graph replay — the first
+        call runs them eagerly (one-time kernel attribute setup), the second captures."""
+        self.in_x.copy_(x)
+        if self.in_y is not None:
+            self.in_y.copy_(y)
+        self._prepare()
+        if self._graphs_on() and self._fwd_warm:
+            if self._fwd_graph is None:
+                self._fwd_graph = self._capture(self._forward_body)
+            if self._fwd_graph is not None:
+                self._fwd_graph.replay()
+                nat.count_launches(self._fwd_launches)
+                return tuple(t.clone() for t in self.p_outs)
+        n0 = nat.launch_count()
+        self._forward_body()
+        self._fwd_launches, self._fwd_warm = nat.launch_count() - n0, True
         return tuple(t.clone() for t in self.p_outs)
 
     # ------------------------------------------------------------------------------------------ backward
@@ -386,22 +455,66 @@ class TrainPlan:
                                                        bn.bias if bn is not None else None) if q is not None]
         self.bwd.append(run)
 
+    def _backward_range(self, lo, hi):
+        if lo == 0:
+            self.flat.zero_()
+        for i in range(lo, hi):
+            self.bwd[i](self.flat, self.dps_in)
+
     def backward(self, dps):
-        flat = torch.zeros(self.grad_numel, dtype=torch.float32, device=self.device)
-        dps = [d.detach().float().contiguous() if d is not None else torch.zeros_like(po)
-               for d, po in zip(dps, self.p_outs)]
+        """The backward launches of one step, as CUDA graph replays.  Without a gradient reducer that is one graph; with
+        dyk.dist_utils.OverlappedAllReduce the list is cut after every backward step at which the first (eager) pass saw
+        a bucket go out, so the all-reduce of a finished bucket is issued between two replays and overlaps the next one.
+        The gradients are returned as views of a COPY of the plan's flat buffer (0.15 ms for 464 MB): the next backward
+        overwrites the buffer, and gradient accumulation over several backward passes must not alias it."""
+        for d, buf in zip(dps, self.dps_in):
+            if d is None:
+                buf.zero_()
+            else:
+                buf.copy_(d.detach())
+        flat, n = self.flat, len(self.bwd)
         reducer = self.reducer
+        active = reducer is not None and reducer._active()
+        key = (id(reducer), getattr(reducer, "bucket_bytes", 0), active)
+        if key != self._bwd_key:
+            self._bwd_key, self._bwd_graphs, self._bwd_warm = key, None, False
         if reducer is not None:
             reducer.begin(flat, self.grad_numel)
             reducer.feed(self.ready_after.get(-1, ()))
-        for i, f in enumerate(self.bwd):
-            f(flat, dps)
-            if reducer is not None:
-                reducer.feed(self.ready_after.get(i, ()))
+        if self._graphs_on() and self._bwd_warm:
+            if self._bwd_graphs is None:
+                cuts = [0] + [e + 1 for e in self._seg_ends if e + 1 < n] + [n]
+                graphs = []
+                for lo, hi in zip(cuts, cuts[1:]):
+                    g = self._capture(lambda lo=lo, hi=hi: self._backward_range(lo, hi))
+                    if g is None:
+                        break
+                    graphs.append((lo, hi, g))
+                self._bwd_graphs = graphs if len(graphs) == len(cuts) - 1 else None
+        if self._graphs_on() and self._bwd_warm and self._bwd_graphs is not None:
+            for lo, hi, g in self._bwd_graphs:
+                g.replay()
+                if reducer is not None:
+                    for i in range(lo, hi):
+                        reducer.feed(self.ready_after.get(i, ()))
+            nat.count_launches(self._bwd_launches)
+        else:
+            n0 = nat.launch_count()
+            self._seg_ends = []
+            self.flat.zero_()
+            for i, f in enumerate(self.bwd):
+                f(flat, self.dps_in)
+                if reducer is not None:
+                    sent = reducer.calls
+                    reducer.feed(self.ready_after.get(i, ()))
+                    if reducer.calls != sent:
+                        self._seg_ends.append(i)
+            self._bwd_launches, self._bwd_warm = nat.launch_count() - n0, True
         if reducer is not None:
             reducer.finish()
-        self.last_flat = flat
-        return [self._pgrad(flat, prm) if prm.requires_grad else None for prm in self.params]
+        out = flat.clone()
+        self.last_flat = out
+        return [self._pgrad(out, prm) if prm.requires_grad else None for prm in self.params]
 
 
 class _TrainFunction(torch.autograd.Function):
@@ -450,13 +563,15 @@ class TrainPlanCache:
 
         x, y = prep(x), prep(y)
         B, _, H, W = x.shape
-        key = (B, H, W, dtype, y is not None, x.device)
+        if y is not None and y.dtype != x.dtype:
+            raise ValueError("visible and LWIR batches must have the same dtype")
+        key = (B, H, W, dtype, y is not None, x.device, x.dtype)
         plan = self.plans.pop(key, None)
         with torch.cuda.device(x.device):
             if plan is None:
                 while len(self.plans) >= self.keep:
                     self.plans.pop(next(iter(self.plans)))
-                plan = TrainPlan(model, B, H, W, dtype, y is not None, x.device)
+                plan = TrainPlan(model, B, H, W, dtype, y is not None, x.device, in_dtype=x.dtype)
             self.plans[key] = plan           # re-insert = most recently used
             self.last_plan = plan
             plan.reducer = getattr(model, "grad_reducer", None)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DYK_ABI_VERSION 2
+#define DYK_ABI_VERSION 3
 
 enum { DYK_F16 = 0, DYK_BF16 = 1 };
 
@@ -76,7 +76,8 @@ typedef struct dyk_conv_params {
   int32_t act;            /* DYK_ACT_*                                           */
   int32_t dtype;          /* DYK_F16 / DYK_BF16                                  */
   int32_t upsample2x;     /* 1: y is the 2x nearest-upsampled map (models.py:100-101 fused) */
-  int32_t out_f32;        /* 1: y is fp32 (y_pix_stride in floats); used by the head convs   */
+  int32_t out_f32;        /* 1: y is fp32 (y_pix_stride in floats); used by the head convs;
+                             2: fp32 y AND fp32-accurate accumulation (fp32 mode, see below)  */
   /* ---- ABI v2 additions (zero = previous behaviour) ---- */
   int32_t out_h, out_w;   /* explicit output size (0 = derive from H, W, pad, k, stride); with pad = 0 this gives
                              "pad only at the bottom / right", which the strided-conv data gradient needs          */
@@ -150,6 +151,40 @@ int dyk_se_gate(const void* x, int64_t x_pix_stride, int32_t N, int32_t HW, int3
                 float* gate, int32_t dtype, void* stream);
 int dyk_scale_channels(const void* x, int64_t x_pix_stride, const float* gate, void* y,
                        int64_t y_pix_stride, int32_t N, int32_t HW, int32_t C, int32_t dtype, void* stream);
+/* the two 1x1 "convolutions" of the block on the pooled vector (fc1 + ReLU, fc2 + hardsigmoid; layers.py:186-189), from
+ * per-slab partial sums pooled[N][slabs][C] (slabs <= 31; the hidden activations are kept behind them in the same scratch) */
+int dyk_se_mlp(float* pooled_scratch, int32_t slabs, int32_t N, int32_t HW, int32_t C, const float* w1, const float* b1,
+               const float* w2, const float* b2, int32_t Csq, float* gate, void* stream);
+
+/* ---- fp32-accurate mode (model.compute_dtype = torch.float32) -------------------------------------
+ * The north-star asks for box / conf / class within 1e-3 of the reference's fp32 path (models.py:279-315 on fp32
+ * tensors).  In this mode activations are fp32 NHWC; dense convolutions still run on dyk_conv2d_fwd (tcgen05, bf16
+ * operands, out_f32 = 2: every 32 MMAs the TMEM accumulator is added into fp32 registers with round-to-nearest, because
+ * the tensor core's own accumulation truncates) as a 3-way bf16 split product with K = 6*Cin:
+ *   dyk_f32_split6:      y[pix][6C]  = [x1|x2|x3|x1|x2|x1] (bf16),  x = x1 + x2 + x3 exactly
+ *   dyk_f32_pack_split6: out[O][kh*kw][6I] = [w1|w1|w1|w2|w2|w3] (bf16) from OIHW fp32
+ * so that x*w = x1w1 + x2w1 + x3w1 + x1w2 + x2w2 + x1w3 up to 2^-24.  The other ops of the graph have fp32 kernels with
+ * the signatures of their 16-bit counterparts (strides in fp32 elements, C a multiple of 4, 16-byte aligned pointers):
+ * stem convolution from NCHW frames (nn.Conv2d + BatchNorm2d + activation, models.py:28-64), depthwise convolution
+ * (layers.py:224-226), WeightedFeatureFusion / concat copy (b = NULL) (layers.py:32-85), nn.MaxPool2d, nn.Upsample,
+ * SqueezeExcitation (pooled_scratch: N * DYK_SE_MAX_SLABS * C floats). */
+int dyk_f32_split6(const float* x, int64_t x_pix_stride, void* y_bf16, int64_t npix, int32_t C, void* stream);
+int dyk_f32_pack_split6(const float* w_oihw, void* out_bf16, int32_t O, int32_t I, int32_t kh, int32_t kw, void* stream);
+int dyk_f32_stem_nchw_fwd(const void* x_nchw, const float* w_ohwi, const float* scale, const float* bias, float* y,
+                          int64_t y_pix_stride, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k,
+                          int32_t stride, int32_t pad, int32_t act, int32_t x_kind, void* stream);
+int dyk_f32_dwconv2d_fwd(const float* x, int64_t x_pix_stride, const float* w_kkc, const float* scale, const float* bias,
+                         float* y, int64_t y_pix_stride, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k,
+                         int32_t stride, int32_t pad, int32_t act, void* stream);
+int dyk_f32_fused_add(const float* a, int64_t a_pix_stride, const float* b, int64_t b_pix_stride, float* y,
+                      int64_t y_pix_stride, int64_t npix, int32_t C, const float* weights, void* stream);
+int dyk_f32_maxpool2d(const float* x, int64_t x_pix_stride, float* y, int64_t y_pix_stride, int32_t N, int32_t H, int32_t W,
+                      int32_t C, int32_t k, int32_t stride, void* stream);
+int dyk_f32_upsample_nearest(const float* x, int64_t x_pix_stride, float* y, int64_t y_pix_stride, int32_t N, int32_t H,
+                             int32_t W, int32_t C, int32_t s, void* stream);
+int dyk_f32_se(const float* x, int64_t x_pix_stride, float* y, int64_t y_pix_stride, int32_t N, int32_t HW, int32_t C,
+               const float* w1, const float* b1, const float* w2, const float* b2, int32_t Csq, float* pooled_scratch,
+               float* gate, void* stream);
 
 /* ---- YOLOLayer.forward, eval + train views (models.py:218-258) ------------------------------------
  * p_nhwc: head conv output [N][ny][nx][p_pix_stride] (channel a*no + o); in_kind 0 = fp16, 1 = bf16,
@@ -323,6 +358,21 @@ int dyk_nchw_f32_to_nhwc(const float* x, void* y, int64_t y_pix_stride, int32_t 
                          int32_t W, int32_t dtype, void* stream);
 int dyk_nhwc_to_nchw_f32(const void* x, int64_t x_pix_stride, float* y, int32_t N, int32_t C, int32_t H,
                          int32_t W, int32_t dtype, void* stream);
+
+/* ---- fused multi-tensor optimizer step (train.py:85-91: optim.SGD(momentum, nesterov=True, weight_decay) or
+ * optim.Adam(betas=(momentum, 0.999), weight_decay); stepped by GradScaler in kaist_train_eval_utils.py:103-108) --------
+ * descs: device int64 [n][6] = (param ptr, grad ptr, state1 ptr, state2 ptr or 0, numel, first block of this tensor);
+ * a tensor occupies ceil(numel / dyk_optim_block_elems()) consecutive blocks; total_blocks = their sum.  All tensors fp32.
+ * grad_scale / found_inf: optional device scalars of torch.amp.GradScaler (gradients are divided by *grad_scale; the
+ * whole step is skipped when *found_inf != 0) — no host synchronisation.
+ * SGD : g += wd*p; buf = first_step ? g : momentum*buf + (1-dampening)*g; g = nesterov ? g + momentum*buf : buf; p -= lr*g
+ * Adam: g += wd*p; m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g^2; p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps) */
+int32_t dyk_optim_block_elems(void);
+int dyk_optim_sgd_multi(const int64_t* descs, int32_t n, int64_t total_blocks, float lr, float momentum, float dampening,
+                        float weight_decay, int32_t nesterov, int32_t first_step, const float* grad_scale,
+                        const float* found_inf, void* stream);
+int dyk_optim_adam_multi(const int64_t* descs, int32_t n, int64_t total_blocks, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, int64_t step, const float* grad_scale, const float* found_inf, void* stream);
 
 #ifdef __cplusplus
 }
