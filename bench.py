@@ -260,7 +260,13 @@ def run_train(args, rank, local, world, dev, cfg=None, dtype=None, steps=None, w
     dual = "second_index" in model.net_info
     B = args.batch
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.SGD(params, lr=1e-4, momentum=0.937, nesterov=True, foreach=True)   # train.py:85-91
+    from dyk import optim as dyk_optim
+    # train.py:85-91: optim.SGD(pg, lr, momentum, weight_decay, nesterov=True) — here its fused multi-tensor replacement
+    # (one native launch for all 568 tensors); DYK_TORCH_OPT=1 times torch.optim.SGD(foreach=True) instead
+    if os.environ.get("DYK_TORCH_OPT", "0") == "1":
+        opt = torch.optim.SGD(params, lr=1e-4, momentum=0.937, weight_decay=5e-4, nesterov=True, foreach=True)
+    else:
+        opt = dyk_optim.FusedSGD(params, lr=1e-4, momentum=0.937, weight_decay=5e-4, nesterov=True)
     ring = 2
     host = [tuple(t.pin_memory() for t in synthetic_frames(B, seed=1000 * rank + i)) for i in range(ring)]
     resident = [(v.to(dev), l.to(dev)) for v, l in host]
@@ -364,7 +370,7 @@ def run_train(args, rank, local, world, dev, cfg=None, dtype=None, steps=None, w
             "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": f"{cfg} {W}x{H} train step, batch {B}/GPU, default-initialised weights, native "
-                                   "compute_loss (CIoU + objectness BCE) on 3 synthetic labels per frame, SGD nesterov", "batch_per_gpu": B, "global_batch": B * world,
+                                   "compute_loss (CIoU + objectness BCE) on 3 synthetic labels per frame, fused SGD (momentum 0.937, nesterov, weight decay 5e-4)", "batch_per_gpu": B, "global_batch": B * world,
                        "parallelism": f"dp{world} (replicas; gradient all-reduce in flat buckets"
                                       + (" overlapped with the backward pass)" if overlap else " after the backward pass)"),
                        "l2": "activations saved for backward (tens of GB) exceed the 126 MB L2; no explicit flush"},

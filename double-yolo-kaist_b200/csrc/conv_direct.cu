@@ -21,7 +21,7 @@ __device__ __forceinline__ float load_frame<float>(const float* p) { return __ld
 template <>
 __device__ __forceinline__ float load_frame<uint8_t>(const uint8_t* p) { return __fdiv_rn((float)__ldg(p), 255.f); }
 
-template <int COUT_T, bool kBf16, typename TIn>
+template <int COUT_T, bool kBf16, typename TIn, int kAct>
 __global__ void __launch_bounds__(128)
 stem_conv_kernel(const TIn* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
                  const float* __restrict__ bias, uint8_t* __restrict__ y, long long ys, int N, int H, int W,
@@ -69,7 +69,7 @@ stem_conv_kernel(const TIn* __restrict__ x, const float* __restrict__ w, const f
         const int co = co0 + c8 * 8 + q;
         const float sc = scale ? __ldg(&scale[co]) : 1.f;
         const float bi = bias ? __ldg(&bias[co]) : 0.f;
-        o[q] = apply_act(fmaf(acc[c8 * 8 + q], sc, bi), act);
+        o[q] = act_apply<kAct>(fmaf(acc[c8 * 8 + q], sc, bi));
       }
       *(reinterpret_cast<uint4*>(yp) + c8) = pack8<kBf16>(o);
     }
@@ -134,7 +134,7 @@ dwconv_kernel(const uint8_t* __restrict__ x, long long xs, const float* __restri
 // unchanged (r outer, s inner).  A vertical-strip variant with the whole filter in registers was measured slower
 // (MobileNetV3 bs64 depthwise total 7.5 ms vs 5.7 ms: 252 registers for 5x5).
 constexpr int kDwStrip = 4;
-template <bool kBf16, int K, int STRIDE>
+template <bool kBf16, int K, int STRIDE, int kAct>
 __global__ void __launch_bounds__(256)
 dwconv_strip_kernel(const uint8_t* __restrict__ x, long long xs, const float* __restrict__ w,
                      const float* __restrict__ scale, const float* __restrict__ bias, uint8_t* __restrict__ y,
@@ -196,7 +196,7 @@ dwconv_strip_kernel(const uint8_t* __restrict__ x, long long xs, const float* __
       if (wo >= Wo) break;
       float o[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) o[q] = apply_act(fmaf(acc[j][q], sc[q], bi[q]), act);
+      for (int q = 0; q < 8; ++q) o[q] = act_apply<kAct>(fmaf(acc[j][q], sc[q], bi[q]));
       const long long opix = ((long long)n * Ho + ho) * Wo + wo;
       *(reinterpret_cast<uint4*>(y + opix * ys * 2) + c) = pack8<kBf16>(o);
     }
@@ -240,9 +240,9 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_stem_nchw_fwd(c
   const dim3 grid((unsigned)gx, (Cout + ct - 1) / ct);
   const size_t smem = (size_t)k * k * Cin * ct * sizeof(float);
 #define DYK_STEM_LAUNCH(CT, TIN)                                                                              \
-  DYK_DISPATCH_DTYPE(dtype, (stem_conv_kernel<CT, kBf16, TIN><<<grid, 128, smem, stream>>>(                     \
+  DYK_DISPATCH_ACT(act, DYK_DISPATCH_DTYPE(dtype, (stem_conv_kernel<CT, kBf16, TIN, kAct><<<grid, 128, smem, stream>>>( \
                                 static_cast<const TIN*>(x), w, scale, bias, (uint8_t*)y, ys, N, H, W, Cin, Cout, \
-                                k, stride, pad, Ho, Wo, act)))
+                                k, stride, pad, Ho, Wo, act))))
   if (ct == 32) {
     if (x_kind == 0) DYK_STEM_LAUNCH(32, float); else DYK_STEM_LAUNCH(32, uint8_t);
   } else {
@@ -273,9 +273,9 @@ extern "C" __attribute__((visibility("default"))) int dyk_dwconv2d_fwd(const voi
       if (gs > (long long)num_sms() * 16) gs = (long long)num_sms() * 16;
       cudaStream_t st = static_cast<cudaStream_t>(stream_);
 #define DYK_DW(KERN, KK, SS)                                                                                        \
-  DYK_DISPATCH_DTYPE(dtype, (KERN<kBf16, KK, SS><<<(unsigned)gs, 256, 0, st>>>(                                         \
+  DYK_DISPATCH_ACT(act, DYK_DISPATCH_DTYPE(dtype, (KERN<kBf16, KK, SS, kAct><<<(unsigned)gs, 256, 0, st>>>(              \
                                 (const uint8_t*)x, xs, w, scale, bias, (uint8_t*)y, ys, N, H, W, cv, pad, Ho, Wo, strips, act, \
-                                (unsigned)tot)))
+                                (unsigned)tot))))
       if (k == 3 && stride == 1) DYK_DW(dwconv_strip_kernel, 3, 1);
       else if (k == 3) DYK_DW(dwconv_strip_kernel, 3, 2);
       else if (stride == 1) DYK_DW(dwconv_strip_kernel, 5, 1);

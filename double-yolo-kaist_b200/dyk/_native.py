@@ -72,10 +72,10 @@ SIGNATURES = {
     "dyk_nms_batched": (_i32, [_vp, _i32, _i32, _i32, _f32, C.c_double, _i32, C.c_uint64, _i32, _i32, _vp, _vp,
                                _vp, _i64, _vp]),
     # ---- training path
-    "dyk_bn_train_stats": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dyk_bn_train_stats": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dyk_bn_act_apply": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _i64, _i64, _i32, _i32, _vp]),
     "dyk_bn_act_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _i64, _vp, _vp,
-                              _vp, _vp]),
+                              _vp, _vp, _vp]),
     "dyk_chan_sum": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _i32, _vp, _vp]),
     "dyk_axpby": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
     "dyk_fusion_weights_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),

@@ -51,6 +51,66 @@ class _Grad:
         self.view, self.written, self.alias_of = view, False, None
 
 
+class _WgradLane:
+    """Weight gradients off the critical path.  In the backward pass only  BN-backward(L) -> dgrad(L) -> BN-backward(L-1) ...
+    is a dependency chain; the weight gradient of layer L (wgrad kernel + its split-K reduction) only needs dz(L).  It is
+    therefore launched on a side stream right after dz(L) exists and runs concurrently with dgrad(L) and the next layers'
+    kernels, filling the SMs that the small late layers leave idle.  dz lives in a ring of `nbuf` buffers: before a
+    buffer is overwritten the main stream waits for the weight-gradient kernel that last read it.  Inside CUDA-graph
+    capture the event record / wait pairs become graph edges (parallel branches).  DYK_WG_SIDE=0 runs everything in order."""
+
+    def __init__(self, device, numel, dtype, nbuf=3):
+        self.on = device.type == "cuda" and os.environ.get("DYK_WG_SIDE", "1") != "0"
+        self.nbuf = nbuf if self.on else 1
+        self.bufs = [torch.empty(numel, dtype=dtype, device=device) for _ in range(self.nbuf)]
+        self.pending = [None] * self.nbuf
+        self.loose = []
+        self.side = torch.cuda.Stream(device=device) if self.on else None
+        self.k, self.slot = 0, None
+
+    def next_dz(self, z: View) -> View:
+        """dz buffer for the layer whose pre-BN tensor is z (called on the main stream)."""
+        i = self.k % self.nbuf
+        self.k += 1
+        if self.pending[i] is not None:
+            torch.cuda.current_stream().wait_event(self.pending[i])
+            self.pending[i] = None
+        self.slot = i
+        return View(self.bufs[i][:z.buf.numel()].view(z.buf.shape), 0, z.C)
+
+    def launch(self, fn, ring=True):
+        """Run fn() (weight-gradient launches) after everything enqueued so far on the main stream, on the side stream."""
+        if not self.on:
+            fn()
+            return
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            fn()
+            done = torch.cuda.Event()
+            done.record(self.side)
+        if ring and self.slot is not None:
+            self.pending[self.slot] = done
+            self.slot = None
+        else:
+            self.loose.append(done)
+
+    def join(self):
+        """Main stream waits for every outstanding weight gradient (end of a graph segment / before gradients are used)."""
+        if not self.on:
+            return
+        main = torch.cuda.current_stream()
+        for i, ev in enumerate(self.pending):
+            if ev is not None:
+                main.wait_event(ev)
+                self.pending[i] = None
+        for ev in self.loose:
+            main.wait_event(ev)
+        self.loose = []
+
+
 class TrainPlan:
     def __init__(self, model, B, H, W, dtype, dual, device, in_dtype=torch.float32):
         self.model, self.B, self.dtype, self.device, self.dual = model, B, dtype, device, dual
@@ -107,6 +167,7 @@ class TrainPlan:
     # ------------------------------------------------------------------------------------------ forward
     def _bind_forward(self):
         self.fwd = []            # callables taking (x, y)
+        self._first_packed_fwd = None
         self.convs = []          # per ConvOp state (packed weights etc.), refreshed every forward
         self.bns = []
         self.p_outs = []
@@ -140,6 +201,8 @@ class TrainPlan:
                     st["multi"] = True
                     self.bytes_allocated += (st["w"].numel() + st["wd"].numel()) * 2
                 self.convs.append(st)
+                if st.get("multi") and self._first_packed_fwd is None:
+                    self._first_packed_fwd = len(self.fwd)      # first launch that reads the packed 16-bit weights
                 self.fwd.append(self._conv_fwd(st))
             elif isinstance(op, P.AddOp):
                 self.fwd.extend(self._add_fwd(op))
@@ -252,8 +315,24 @@ class TrainPlan:
         nat.count_launches()
 
     def _forward_body(self):
-        self._pack_all()
-        for f in self.fwd:
+        packed = None
+        if self.wg.on and self._first_packed_fwd:
+            # the per-step re-packing of all weights (one launch, ~0.9 GB of traffic) runs on the side stream while the
+            # stem convolution — which reads the fp32 parameters directly — and its BatchNorm run on the main stream
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            self.wg.side.wait_event(fork)
+            with torch.cuda.stream(self.wg.side):
+                self._pack_all()
+                packed = torch.cuda.Event()
+                packed.record(self.wg.side)
+        else:
+            self._pack_all()
+        for i, f in enumerate(self.fwd):
+            if packed is not None and i >= self._first_packed_fwd:
+                torch.cuda.current_stream().wait_event(packed)
+                packed = None
             f(self.in_x, self.in_y)
         if self.bns:
             torch._foreach_add_([bn.num_batches_tracked for bn in self.bns], 1)   # counters, not arithmetic of the path
@@ -347,7 +426,7 @@ class TrainPlan:
         self.bwd = []
         self.bwd_writes = {}     # index into self.bwd -> parameters whose gradient that step writes
         max_z = max((st["z"].buf.numel() for st in self.convs if "z" in st), default=0)
-        self.dz_scratch = torch.empty(max_z, dtype=self.dtype, device=self.device)
+        self.wg = _WgradLane(self.device, max_z, self.dtype)
         conv_state = {id(st["op"]): st for st in self.convs}
         yolo_i = len(self.p_outs)
         for op in reversed(self.ops):
@@ -428,9 +507,10 @@ class TrainPlan:
 
         def run(flat, dps):
             gw = self._pgrad(flat, conv.weight)
+            ring = bn is not None
             if bn is not None:
                 z = st["z"]
-                dz = View(self.dz_scratch[:z.buf.numel()].view(z.buf.shape), 0, z.C)
+                dz = self.wg.next_dz(z)
                 T.bn_act_bwd(dy, z, st["scale"], st["shift"], st["mean"], st["invstd"], bn.weight.detach(), op.act, dz,
                              self._pgrad(flat, bn.weight), self._pgrad(flat, bn.bias))
                 cout_real = None
@@ -448,7 +528,8 @@ class TrainPlan:
                 T.dwconv_wgrad(op.src.view, dz, gw, k=k, stride=s, pad=p, accumulate=True)
                 T.dwconv_dgrad(dz, st["w"], gv, k=k, stride=s, pad=p, accumulate=acc)
                 return
-            T.conv_wgrad(op.src.view, dz, gw, k=k, stride=s, pad=p, accumulate=True, cout_real=cout_real)
+            self.wg.launch(lambda: T.conv_wgrad(op.src.view, dz, gw, k=k, stride=s, pad=p, accumulate=True, cout_real=cout_real),
+                           ring=ring)
             wd = st["wd"] if st.get("multi") else T.pack_dgrad_weight(conv.weight, self.dtype, opad=dz.C)
             T.conv_dgrad(dz, wd, gv, k=k, stride=s, pad=p, accumulate=acc)
         self.bwd_writes[len(self.bwd)] = [q for q in (conv.weight, conv.bias, bn.weight if bn is not None else None,
@@ -460,6 +541,7 @@ class TrainPlan:
             self.flat.zero_()
         for i in range(lo, hi):
             self.bwd[i](self.flat, self.dps_in)
+        self.wg.join()
 
     def backward(self, dps):
         """The backward launches of one step, as CUDA graph replays.  Without a gradient reducer that is one graph; with
@@ -505,10 +587,12 @@ class TrainPlan:
             for i, f in enumerate(self.bwd):
                 f(flat, self.dps_in)
                 if reducer is not None:
+                    self.wg.join()          # a bucket may only leave once its weight gradients (side stream) are complete
                     sent = reducer.calls
                     reducer.feed(self.ready_after.get(i, ()))
                     if reducer.calls != sent:
                         self._seg_ends.append(i)
+            self.wg.join()
             self._bwd_launches, self._bwd_warm = nat.launch_count() - n0, True
         if reducer is not None:
             reducer.finish()

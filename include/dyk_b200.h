@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DYK_ABI_VERSION 3
+#define DYK_ABI_VERSION 4
 
 enum { DYK_F16 = 0, DYK_BF16 = 1 };
 
@@ -226,19 +226,24 @@ int dyk_nms_batched(const float* pred, int32_t B, int32_t rows, int32_t nc, floa
 /* nn.BatchNorm2d in training mode (models.py:47), statistics part: per-channel batch mean / biased variance of the
  * 16-bit conv output z -> scale = gamma*invstd, shift = beta - mean*scale (so y = z*scale + shift), saved mean /
  * invstd for backward, and the in-place running_mean / running_var update (momentum, unbiased variance).
- * workspace: DYK_TRAIN_MAX_SLABS * 2 * C floats. */
+ * workspace: DYK_TRAIN_MAX_SLABS * 2 * C floats.
+ * counters: NULL, or C/8 (at least) uint32 that are ZERO on entry and are left zero: the per-channel finalisation then runs
+ * inside the reduction kernel (the block that finishes last does it) instead of as a second launch.  One counter array
+ * may be shared by consecutive calls on one stream, never by concurrent ones. */
 int dyk_bn_train_stats(const void* z, int64_t z_pix_stride, int64_t npix, int32_t C, int32_t dtype, const float* gamma,
                        const float* beta, float eps, float momentum, float* running_mean, float* running_var,
-                       float* scale, float* shift, float* mean, float* invstd, float* workspace, void* stream);
+                       float* scale, float* shift, float* mean, float* invstd, float* workspace, uint32_t* counters,
+                       void* stream);
 /* y = act(z*scale[c] + shift[c])  — BatchNorm normalisation + activation (models.py:47-64) */
 int dyk_bn_act_apply(const void* z, int64_t z_pix_stride, const float* scale, const float* shift, int32_t act, void* y,
                      int64_t y_pix_stride, int64_t npix, int32_t C, int32_t dtype, void* stream);
 /* backward of activation + train-mode BatchNorm: dz (16-bit) from dy and the saved z / statistics; dgamma, dbeta are
- * ACCUMULATED into fp32 vectors (may be NULL).  workspace: (DYK_TRAIN_MAX_SLABS * 2 + 3) * C floats. */
+ * ACCUMULATED into fp32 vectors (may be NULL).  workspace: (DYK_TRAIN_MAX_SLABS * 2 + 3) * C floats; counters as for
+ * dyk_bn_train_stats (NULL = separate finalisation launch). */
 int dyk_bn_act_bwd(const void* dy, int64_t dy_pix_stride, const void* z, int64_t z_pix_stride, const float* scale,
                    const float* shift, const float* mean, const float* invstd, const float* gamma, int32_t act,
                    int64_t npix, int32_t C, int32_t dtype, void* dz, int64_t dz_pix_stride, float* dgamma, float* dbeta,
-                   float* workspace, void* stream);
+                   float* workspace, uint32_t* counters, void* stream);
 /* out[c] (+)= sum over pixels of x[pix][c]  (bias gradient of the head convs).  workspace: DYK_TRAIN_MAX_SLABS*2*C floats */
 int dyk_chan_sum(const void* x, int64_t x_pix_stride, int64_t npix, int32_t C, int32_t dtype, float* out,
                  int32_t accumulate, float* workspace, void* stream);

@@ -84,6 +84,7 @@ def train_one_epoch(model, optimizer, dataloader, device, epoch, accumulate, img
             scaler.update()
             optimizer.zero_grad()
         history.append(float(loss_items[3]))
+    train_one_epoch.last_scale = scaler.get_scale()
     return mloss, history
 
 
@@ -139,13 +140,15 @@ def test_reference_training_loop_over_native_modules(native_lib, name, opt_kind)
     else:
         optimizer = optim.FusedAdam(pg, lr=1e-3, betas=(0.937, 0.999), weight_decay=5e-4)
     before = [p.detach().clone() for p in pg[:8]]
-    data = SyntheticPairs(batches=6, bs=4)
+    data = SyntheticPairs(batches=16, bs=2)      # 8 optimizer steps: room for GradScaler to back off from 65536 under fp16
     # multi-scale on: sizes 96 / 128 / 160 (train.py:143-151 picks grid_min / grid_max around img_size; gs = 32)
     mloss, hist = train_one_epoch(model, optimizer, data, DEV, epoch=0, accumulate=2, img_size=W, grid_min=3, grid_max=5,
                                   gs=32, multi_scale=True, compute_loss=compute_loss)
     torch.cuda.synchronize()
     assert all(math.isfinite(h) for h in hist) and bool(torch.isfinite(mloss).all())
-    assert any(not torch.equal(a, b.detach()) for a, b in zip(before, pg[:8])), "the optimizer never changed the parameters"
+    assert train_one_epoch.last_scale >= 1.0, "GradScaler collapsed: the backward pass produces non-finite gradients at any scale"
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(before, pg[:8])), \
+        f"the optimizer never changed the parameters (final loss scale {train_one_epoch.last_scale})"
     assert all(p.grad is None or bool(torch.isfinite(p.grad).all()) for p in pg)
     # same frames, fixed scale: a second short epoch keeps the loss finite and the BatchNorm statistics have moved
     bn = next(m for m in model.modules() if isinstance(m, torch.nn.BatchNorm2d))

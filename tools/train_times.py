@@ -51,6 +51,49 @@ flat = torch.zeros(plan.grad_numel, device="cuda")
 dps = [torch.randn_like(t) for t in plan.p_outs]
 bt = timed(plan.bwd, lambda f: f(flat, dps))
 print(f"forward {sum(ft):.2f} ms in {len(ft)} steps, backward {sum(bt):.2f} ms in {len(bt)} steps")
+
+
+def conv_info(f):
+    """(pixels_out, Cin, Cout, k, stride) of the convolution block behind a forward / backward step, or None"""
+    for o in list(f.__defaults__ or ()) + [c.cell_contents for c in (getattr(f, "__closure__", None) or ())]:
+        if isinstance(o, dict) and "op" in o:
+            op, conv = o["op"], o["conv"]
+            return dict(layer=op.layer, cin=conv.in_channels, cout=conv.out_channels, k=o["k"], s=o["s"], groups=conv.groups,
+                        Ho=op.out.H, Wo=op.out.W, Hi=op.src.H, Wi=op.src.W, act=op.act)
+    return None
+
+
+import json, os
+rows = []
+for name, ts, fns in (("fwd", ft, plan.fwd), ("bwd", bt, plan.bwd)):
+    for t, f in zip(ts, fns):
+        ci = conv_info(f)
+        row = dict(phase=name, ms=t, what=describe(f))
+        if ci:
+            eo = B * ci["Ho"] * ci["Wo"] * ci["cout"] * 2 / 1e9          # GB of one 16-bit pass over the output
+            ei = B * ci["Hi"] * ci["Wi"] * ci["cin"] * 2 / 1e9
+            gf = 2.0 * B * ci["Ho"] * ci["Wo"] * ci["cout"] * ci["cin"] // ci["groups"] * ci["k"] ** 2 / 1e9
+            if name == "fwd":     # conv (in + z) + stats (z) + apply (z + y)
+                gb, fl = ei + 4 * eo, gf
+            else:                 # BN bwd reduce (dy, z [+ g]) + apply (g, z, dz) + wgrad (x, dz) + dgrad (dz, dx)
+                gb, fl = (6 if ci["act"] == "mish" else 5) * eo + (ei + eo) + (eo + ei), 2 * gf
+            row.update(ci, gb=gb, gflop=fl, ideal_ms=max(gb / 6.4, fl / 1400.0))
+        rows.append(row)
+out = os.environ.get("DYK_TRAIN_TIMES_JSON")
+if out:
+    json.dump(rows, open(out, "w"))
+tot = sum(r["ms"] for r in rows if "ideal_ms" in r)
+ideal = sum(r["ideal_ms"] for r in rows if "ideal_ms" in r)
+print(f"conv blocks: measured {tot:.2f} ms, per-layer roofline (max of 6.4 TB/s HBM passes as launched, 1400 TF/s) {ideal:.2f} ms")
+by_res = {}
+for r in rows:
+    if "ideal_ms" in r:
+        k = (r["phase"], r["Ho"], r["Wo"])
+        a = by_res.setdefault(k, [0.0, 0.0, 0])
+        a[0] += r["ms"]; a[1] += r["ideal_ms"]; a[2] += 1
+for k in sorted(by_res):
+    a = by_res[k]
+    print(f"  {k[0]} {k[1]:4d}x{k[2]:<4d} n={a[2]:3d}  measured {a[0]:7.3f} ms  roofline {a[1]:7.3f} ms  x{a[0] / a[1]:.2f}")
 for name, ts, fns in (("fwd", ft, plan.fwd), ("bwd", bt, plan.bwd)):
     rows = sorted(zip(ts, [describe(f) for f in fns]), reverse=True)[:18]
     for t, d in rows:
