@@ -28,7 +28,8 @@ static inline int grid_for_t(long long work, int block) {
 }
 // enough slabs that (C / 64) x slabs blocks fill the GPU a few times over, capped by the workspace contract
 static inline int slabs_for(long long npix) {
-  long long s = npix / 512;
+  static const int slab_pix = getenv("DYK_SLAB_PIX") ? atoi(getenv("DYK_SLAB_PIX")) : 256;
+  long long s = npix / slab_pix;
   if (s < 1) s = 1;
   if (s > kMaxSlabs) s = kMaxSlabs;
   return (int)s;
@@ -552,48 +553,63 @@ __global__ void fusion_weights_bwd_kernel(const float* __restrict__ w_raw, const
 }
 
 // ------------------------------------------------------------------ MaxPool2d backward
-// (1) idx[n][ho][wo][c] = position (hi*W + wi) of the first maximum of the window (scan order, strict '>')
+// (1) idx[n][ho][wo][c] = position (hi*W + wi) of the first maximum of the window (scan order, strict '>').
+//     One thread = one output pixel x 8 channels (16-byte loads; the scalar version issued one 2-byte load per element
+//     and tap: 169 per element for the 13x13 SPP pool).
 template <bool kBf16>
 __global__ void maxpool_argmax_kernel(const uint8_t* __restrict__ x, long long xs, int N, int H, int W, int C, int k,
                                       int stride, int pad, int Ho, int Wo, int* __restrict__ idx) {
-  const long long total = (long long)N * Ho * Wo * C;
+  const int cv = C / 8;
+  const long long total = (long long)N * Ho * Wo * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    long long t = i / C;
+    const int c = (int)(i % cv);
+    long long t = i / cv;
     const int wo = (int)(t % Wo); t /= Wo;
     const int ho = (int)(t % Ho);
     const int n = (int)(t / Ho);
-    float best = -INFINITY;
-    int bi = -1;
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { best[q] = -INFINITY; bi[q] = -1; }
     for (int r = 0; r < k; ++r) {
       const int hi = ho * stride - pad + r;
       if (hi < 0 || hi >= H) continue;
-      for (int s = 0; s < k; ++s) {
-        const int wi = wo * stride - pad + s;
+      for (int s_ = 0; s_ < k; ++s_) {
+        const int wi = wo * stride - pad + s_;
         if (wi < 0 || wi >= W) continue;
-        const float v = load1<kBf16>(x, (((long long)n * H + hi) * W + wi) * xs + c);
-        if (v > best || bi < 0) { best = v; bi = hi * W + wi; }
+        float f[8];
+        unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + hi) * W + wi) * xs * 2) + c), f);
+        const int pos = hi * W + wi;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (f[q] > best[q] || bi[q] < 0) { best[q] = f[q]; bi[q] = pos; }
       }
     }
-    idx[i] = bi;
+    int4* o = reinterpret_cast<int4*>(idx + ((((long long)n * Ho + ho) * Wo + wo) * C + c * 8));
+    o[0] = make_int4(bi[0], bi[1], bi[2], bi[3]);
+    o[1] = make_int4(bi[4], bi[5], bi[6], bi[7]);
   }
 }
-// (2) dx[n][hi][wi][c] (+)= sum of dy over the windows whose argmax is this pixel (fixed order -> deterministic)
+// (2) dx[n][hi][wi][c] (+)= sum of dy over the windows whose argmax is this pixel (fixed order -> deterministic);
+//     one thread = one input pixel x 8 channels
 template <bool kBf16>
 __global__ void maxpool_bwd_kernel(const uint8_t* __restrict__ dy, long long dys, const int* __restrict__ idx, int N, int H,
                                    int W, int C, int k, int stride, int pad, int Ho, int Wo, uint8_t* __restrict__ dx,
                                    long long dxs, int accumulate) {
-  const long long total = (long long)N * H * W * C;
+  const int cv = C / 8;
+  const long long total = (long long)N * H * W * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    long long t = i / C;
+    const int c = (int)(i % cv);
+    long long t = i / cv;
     const int wi = (int)(t % W); t /= W;
     const int hi = (int)(t % H);
     const int n = (int)(t / H);
     const int me = hi * W + wi;
-    float s = 0.f;
+    float s[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] = 0.f;
     // outputs whose window covers (hi, wi): ho*stride - pad <= hi <= ho*stride - pad + k - 1
     int ho_lo = (hi + pad - k + 1 + stride - 1) / stride; if (hi + pad - k + 1 < 0) ho_lo = 0;
     int wo_lo = (wi + pad - k + 1 + stride - 1) / stride; if (wi + pad - k + 1 < 0) wo_lo = 0;
@@ -601,11 +617,26 @@ __global__ void maxpool_bwd_kernel(const uint8_t* __restrict__ dy, long long dys
     for (int ho = ho_lo; ho <= ho_hi; ++ho)
       for (int wo = wo_lo; wo <= wo_hi; ++wo) {
         const long long o = (((long long)n * Ho + ho) * Wo + wo);
-        if (idx[o * C + c] == me) s += load1<kBf16>(dy, o * dys + c);
+        const int4* ip = reinterpret_cast<const int4*>(idx + o * C + c * 8);
+        const int4 i0 = __ldg(ip), i1 = __ldg(ip + 1);
+        const int id[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) any |= id[q] == me;
+        if (!any) continue;
+        float f[8];
+        unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(dy + o * dys * 2) + c), f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s[q] += id[q] == me ? f[q] : 0.f;
       }
-    const long long di = (((long long)n * H + hi) * W + wi) * dxs + c;
-    if (accumulate) s += load1<kBf16>(dx, di);
-    store1<kBf16>(dx, di, s);
+    uint4* dp = reinterpret_cast<uint4*>(dx + (((long long)n * H + hi) * W + wi) * dxs * 2) + c;
+    if (accumulate) {
+      float d[8];
+      unpack8<kBf16>(*dp, d);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s[q] += d[q];
+    }
+    *dp = pack8<kBf16>(s);
   }
 }
 
@@ -1043,14 +1074,16 @@ DYK_EXPORT int dyk_maxpool2d_bwd(const void* x, int64_t xs, const void* dy, int6
                                  int32_t* idx_workspace, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DYK_REQUIRE(x && dy && dx && idx_workspace, "dyk_maxpool2d_bwd: null pointer");
-  DYK_REQUIRE(C > 0 && k >= 1 && stride >= 1, "dyk_maxpool2d_bwd: bad shape");
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && xs % 8 == 0 && dys % 8 == 0 && dxs % 8 == 0 && k >= 1 && stride >= 1,
+              "dyk_maxpool2d_bwd: C and the pixel strides must be multiples of 8");
+  DYK_REQUIRE(DYK_AL16(x) && DYK_AL16(dy) && DYK_AL16(dx) && DYK_AL16(idx_workspace), "dyk_maxpool2d_bwd: 16-byte alignment");
   const int pad = (k - 1) / 2;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   DYK_REQUIRE(Ho > 0 && Wo > 0, "dyk_maxpool2d_bwd: empty output");
-  DYK_DISPATCH_DTYPE(dtype, (maxpool_argmax_kernel<kBf16><<<grid_for_t((long long)N * Ho * Wo * C, 256), 256, 0, stream>>>(
+  DYK_DISPATCH_DTYPE(dtype, (maxpool_argmax_kernel<kBf16><<<grid_for_t((long long)N * Ho * Wo * (C / 8), 128), 128, 0, stream>>>(
                                 (const uint8_t*)x, xs, N, H, W, C, k, stride, pad, Ho, Wo, idx_workspace)));
   DYK_LAUNCH_OK("maxpool_argmax_kernel");
-  DYK_DISPATCH_DTYPE(dtype, (maxpool_bwd_kernel<kBf16><<<grid_for_t((long long)N * H * W * C, 256), 256, 0, stream>>>(
+  DYK_DISPATCH_DTYPE(dtype, (maxpool_bwd_kernel<kBf16><<<grid_for_t((long long)N * H * W * (C / 8), 128), 128, 0, stream>>>(
                                 (const uint8_t*)dy, dys, idx_workspace, N, H, W, C, k, stride, pad, Ho, Wo, (uint8_t*)dx, dxs,
                                 accumulate)));
   DYK_LAUNCH_OK("maxpool_bwd_kernel");

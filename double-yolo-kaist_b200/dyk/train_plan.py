@@ -51,6 +51,41 @@ class _Grad:
         self.view, self.written, self.alias_of = view, False, None
 
 
+def assign_train_lanes(ops_):
+    """Two-lane schedule of a training plan (forward and, mirrored, backward).  The dual-stream models are two independent
+    backbones between fusion points; their mid / late layers (64x80 and smaller) are far too small to fill 148 SMs, and
+    a layer is a chain of 4 (forward) to 6 (backward) dependent launches, so running the LWIR backbone on a second stream
+    lets the two chains interleave.  Same greedy rule as dyk.plan.assign_lanes, with the stems as ordinary ops: an op
+    follows the lane of the most recent op it depends on, joins on lane 0, and the first op without any ancestor after
+    lane 0 has started (the LWIR stem) opens lane 1.  Returns (lane per op, producer op index per Value id)."""
+    producer, anc, lanes, last = {}, [], [], [None, None]
+    for k, op in enumerate(ops_):
+        a = 0
+        for v in op.inputs():
+            p_ = producer.get(id(v))
+            if p_ is not None:
+                a |= (1 << p_) | anc[p_]
+        anc.append(a)
+        out = getattr(op, "out", None)
+        if out is not None:
+            producer[id(out)] = k
+        d0 = last[0] is not None and (a >> last[0]) & 1
+        d1 = last[1] is not None and (a >> last[1]) & 1
+        if d0 and not d1:
+            lane = 0
+        elif d1 and not d0:
+            lane = 1
+        elif d0 and d1:
+            lane = 0
+        elif a:
+            lane = lanes[a.bit_length() - 1]
+        else:
+            lane = 0 if last[0] is None else 1
+        lanes.append(lane)
+        last[lane] = k
+    return lanes, producer
+
+
 class _WgradLane:
     """Weight gradients off the critical path.  In the backward pass only  BN-backward(L) -> dgrad(L) -> BN-backward(L-1) ...
     is a dependency chain; the weight gradient of layer L (wgrad kernel + its split-K reduction) only needs dz(L).  It is
@@ -131,8 +166,14 @@ class TrainPlan:
             off += (prm.numel() + 31) // 32 * 32          # padded so vector kernels may write whole 32-float groups
         self.grad_numel = off
         self.reducer = None      # set by TrainPlanCache from model.grad_reducer (dyk.dist_utils.OverlappedAllReduce)
+        self.lanes, self.producer = assign_train_lanes(self.ops)
+        self.two_lanes = (device.type == "cuda" and os.environ.get("DYK_TRAIN_LANES", "2") != "1" and 1 in self.lanes)
+        if not self.two_lanes:
+            self.lanes = [0] * len(self.ops)
+        self.lane1 = torch.cuda.Stream(device=device) if self.two_lanes else None
         self._alloc_forward()
         self._bind_forward()
+        self._finish_forward_schedule()
         self._bind_backward()
         # gradients of a step are produced in this buffer (one view per parameter) and handed out as a copy
         self.flat = torch.zeros(self.grad_numel, dtype=torch.float32, device=device)
@@ -167,13 +208,17 @@ class TrainPlan:
     # ------------------------------------------------------------------------------------------ forward
     def _bind_forward(self):
         self.fwd = []            # callables taking (x, y)
-        self._first_packed_fwd = None
+        self._packed_ops = set()
         self.convs = []          # per ConvOp state (packed weights etc.), refreshed every forward
         self.bns = []
         self.p_outs = []
         self.yolo = []
         dev = self.device
-        for op in self.ops:
+        self.fwd_groups = []     # (op index, first fwd step, one past the last) — the unit of the two-lane schedule
+        for op_index, op in enumerate(self.ops):
+            if self.fwd_groups:
+                self.fwd_groups[-1][2] = len(self.fwd)
+            self.fwd_groups.append([op_index, len(self.fwd), len(self.fwd)])
             if isinstance(op, P.ConvOp):
                 conv, bn = op.conv, op.bn
                 k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
@@ -201,8 +246,8 @@ class TrainPlan:
                     st["multi"] = True
                     self.bytes_allocated += (st["w"].numel() + st["wd"].numel()) * 2
                 self.convs.append(st)
-                if st.get("multi") and self._first_packed_fwd is None:
-                    self._first_packed_fwd = len(self.fwd)      # first launch that reads the packed 16-bit weights
+                if st.get("multi"):
+                    self._packed_ops.add(op_index)              # reads the packed 16-bit weights (_pack_all)
                 self.fwd.append(self._conv_fwd(st))
             elif isinstance(op, P.AddOp):
                 self.fwd.extend(self._add_fwd(op))
@@ -232,6 +277,19 @@ class TrainPlan:
                 self.fwd.append(lambda x, y, o=op, po=p_out, an=anchor, mm=m: ops.yolo_decode(
                     o.src.view.buf, o.src.view.stride, po, None, N=self.B, ny=o.src.H, nx=o.src.W, na=mm.na, no=mm.no,
                     anchor_vec=an, stride=mm.stride, v4=mm.bf_type == "yolov4", rows_total=0, row_off=0, in_kind=2))
+
+    def _finish_forward_schedule(self):
+        """Cross-lane dependencies of the forward groups: group k waits for the event recorded after group p for every
+        input produced on the other lane."""
+        if self.fwd_groups:
+            self.fwd_groups[-1][2] = len(self.fwd)
+        self.fwd_waits, self.fwd_records = {}, set()
+        for k, op in enumerate(self.ops):
+            for v in op.inputs():
+                p_ = self.producer.get(id(v))
+                if p_ is not None and self.lanes[p_] != self.lanes[k]:
+                    self.fwd_waits.setdefault(k, set()).add(p_)
+                    self.fwd_records.add(p_)
 
     def _conv_fwd(self, st):
         op, conv, bn = st["op"], st["conv"], st["bn"]
@@ -315,25 +373,53 @@ class TrainPlan:
         nat.count_launches()
 
     def _forward_body(self):
+        main = torch.cuda.current_stream()
         packed = None
-        if self.wg.on and self._first_packed_fwd:
-            # the per-step re-packing of all weights (one launch, ~0.9 GB of traffic) runs on the side stream while the
-            # stem convolution — which reads the fp32 parameters directly — and its BatchNorm run on the main stream
-            main = torch.cuda.current_stream()
+        wg0 = self.wgs[0]
+        if wg0.on:
+            # the per-step re-packing of all weights (one launch, ~0.9 GB of traffic) runs on a side stream while the
+            # stem convolutions — which read the fp32 parameters directly — and their BatchNorm run on the lanes
             fork = torch.cuda.Event()
             fork.record(main)
-            self.wg.side.wait_event(fork)
-            with torch.cuda.stream(self.wg.side):
+            wg0.side.wait_event(fork)
+            with torch.cuda.stream(wg0.side):
                 self._pack_all()
                 packed = torch.cuda.Event()
-                packed.record(self.wg.side)
+                packed.record(wg0.side)
         else:
             self._pack_all()
-        for i, f in enumerate(self.fwd):
-            if packed is not None and i >= self._first_packed_fwd:
-                torch.cuda.current_stream().wait_event(packed)
-                packed = None
-            f(self.in_x, self.in_y)
+        if self.two_lanes:
+            fork1 = torch.cuda.Event()
+            fork1.record(main)
+            self.lane1.wait_event(fork1)
+        streams = (main, self.lane1)
+        pack_seen = [packed is None, packed is None]
+        events = {}
+        for k, lo, hi in self.fwd_groups:
+            lane = self.lanes[k]
+            st = streams[lane]
+            if not pack_seen[lane] and k in self._packed_ops:
+                st.wait_event(packed)
+                pack_seen[lane] = True
+            for p_ in self.fwd_waits.get(k, ()):
+                st.wait_event(events[p_])
+            if lane == 0:
+                for i in range(lo, hi):
+                    self.fwd[i](self.in_x, self.in_y)
+            else:
+                with torch.cuda.stream(st):
+                    for i in range(lo, hi):
+                        self.fwd[i](self.in_x, self.in_y)
+            if k in self.fwd_records:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                events[k] = ev
+        if self.two_lanes:
+            join = torch.cuda.Event()
+            join.record(self.lane1)
+            main.wait_event(join)
+        if not pack_seen[0] and packed is not None:
+            main.wait_event(packed)
         if self.bns:
             torch._foreach_add_([bn.num_batches_tracked for bn in self.bns], 1)   # counters, not arithmetic of the path
 
@@ -415,21 +501,39 @@ class TrainPlan:
         def is_written(g):
             return g.written or (g.alias_of is not None and is_written(g.alias_of))
 
+        def root(g):
+            while g.alias_of is not None:
+                g = g.alias_of
+            return g
+
+        cur = {"writes": set(), "reads": set()}      # gradient buffers the group being bound touches (two-lane schedule)
+
         def claim(v):
             """Returns (grad view of v, accumulate?) and marks it written."""
             g = gslot(v)
             acc = is_written(g)
             g.written = True
+            cur["writes"].add(id(root(g)))
             return g.view, acc
 
         self.grads, self.consumers = grads, consumers
         self.bwd = []
         self.bwd_writes = {}     # index into self.bwd -> parameters whose gradient that step writes
         max_z = max((st["z"].buf.numel() for st in self.convs if "z" in st), default=0)
-        self.wg = _WgradLane(self.device, max_z, self.dtype)
+        self.wgs = [_WgradLane(self.device, max_z, self.dtype) for _ in range(2 if self.two_lanes else 1)]
+        self.wg = self.wgs[0]           # the lane the step being executed uses (set per group by _backward_range)
         conv_state = {id(st["op"]): st for st in self.convs}
         yolo_i = len(self.p_outs)
-        for op in reversed(self.ops):
+        self.bwd_groups = []            # dict(op, lo, hi, reads, writes): the backward steps of one op, in execution order
+
+        def close_group():
+            if cur.get("op") is not None and len(self.bwd) > cur["lo"]:
+                self.bwd_groups.append(dict(op=cur["op"], lo=cur["lo"], hi=len(self.bwd), reads=cur["reads"], writes=cur["writes"]))
+
+        for op_index in range(len(self.ops) - 1, -1, -1):
+            op = self.ops[op_index]
+            close_group()
+            cur.update(op=op_index, lo=len(self.bwd), reads=set(), writes=set())
             if isinstance(op, P.YoloOp):
                 yolo_i -= 1
                 gv, acc = claim(op.src)
@@ -444,6 +548,7 @@ class TrainPlan:
             if gout is None or not is_written(gout):
                 continue      # nothing downstream depends on this tensor
             dy = gout.view
+            cur["reads"].add(id(root(gout)))
             if isinstance(op, P.ConvOp):
                 st = conv_state[id(op)]
                 self._conv_bwd(st, dy, claim if not st["stem"] else None)
@@ -483,7 +588,29 @@ class TrainPlan:
                              self._pgrad(flat, m.fc2.weight).view(w2.shape), self._pgrad(flat, m.fc2.bias), a)
                 self.bwd_writes[len(self.bwd)] = [op.module.fc1.weight, op.module.fc1.bias, op.module.fc2.weight, op.module.fc2.bias]
                 self.bwd.append(se)
+        close_group()
+        self._schedule_lanes_backward()
         self._schedule_ready()
+
+    def _schedule_lanes_backward(self):
+        """Cross-lane ordering of the backward groups.  A group runs on the lane of its op.  Every gradient buffer it reads
+        (dy) or writes (first writer overwrites, later ones accumulate: the order fixed when the plan was bound must hold)
+        may last have been written by a group of the other lane: it then waits for the event recorded after that group."""
+        last = {}                        # gradient buffer -> {lane: index of the last group that wrote it}
+        self.bwd_waits, self.bwd_records = {}, set()
+        for gi, g in enumerate(self.bwd_groups):
+            lane = self.lanes[g["op"]]
+            for r in g["reads"] | g["writes"]:
+                other = last.get(r, {}).get(1 - lane)
+                if other is not None:
+                    self.bwd_waits.setdefault(gi, set()).add(other)
+                    self.bwd_records.add(other)
+            for r in g["writes"]:
+                last.setdefault(r, {})[lane] = gi
+        self._step_group = {}
+        for gi, g in enumerate(self.bwd_groups):
+            for i in range(g["lo"], g["hi"]):
+                self._step_group[i] = gi
 
     def _schedule_ready(self):
         """ready_after[i] = flat ranges (lo, hi) whose gradients are final once bwd step i has been enqueued; ranges of
@@ -536,12 +663,53 @@ class TrainPlan:
                                                        bn.bias if bn is not None else None) if q is not None]
         self.bwd.append(run)
 
-    def _backward_range(self, lo, hi):
-        if lo == 0:
+    def _backward_range(self, glo, ghi, reducer=None, record_sends=False):
+        """Backward groups [glo, ghi) on their lanes; every forked stream has re-joined the main stream on return."""
+        main = torch.cuda.current_stream()
+        if glo == 0:
             self.flat.zero_()
-        for i in range(lo, hi):
-            self.bwd[i](self.flat, self.dps_in)
-        self.wg.join()
+        if self.two_lanes:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            self.lane1.wait_event(fork)
+        streams = (main, self.lane1)
+        events = {}
+        for gi in range(glo, ghi):
+            g = self.bwd_groups[gi]
+            lane = self.lanes[g["op"]]
+            st = streams[lane]
+            for w in self.bwd_waits.get(gi, ()):
+                if w >= glo:                       # earlier ranges were joined when they ended
+                    st.wait_event(events[w])
+            self.wg = self.wgs[lane]
+            if lane == 0:
+                for i in range(g["lo"], g["hi"]):
+                    self.bwd[i](self.flat, self.dps_in)
+            else:
+                with torch.cuda.stream(st):
+                    for i in range(g["lo"], g["hi"]):
+                        self.bwd[i](self.flat, self.dps_in)
+            if gi in self.bwd_records:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                events[gi] = ev
+            if reducer is not None:                # eager pass with a gradient reducer: feed it group by group
+                self._join_lanes(main)
+                sent = reducer.calls
+                for i in range(g["lo"], g["hi"]):
+                    reducer.feed(self.ready_after.get(i, ()))
+                if record_sends and reducer.calls != sent:
+                    self._seg_ends.append(gi)
+        self._join_lanes(main)
+
+    def _join_lanes(self, main):
+        if self.two_lanes:
+            with torch.cuda.stream(self.lane1):
+                self.wgs[1].join()                 # lane 1's weight gradients re-join lane 1 ...
+            j = torch.cuda.Event()
+            j.record(self.lane1)
+            main.wait_event(j)                     # ... and lane 1 re-joins the main stream
+        self.wgs[0].join()
 
     def backward(self, dps):
         """The backward launches of one step, as CUDA graph replays.  Without a gradient reducer that is one graph; with
@@ -563,9 +731,10 @@ class TrainPlan:
         if reducer is not None:
             reducer.begin(flat, self.grad_numel)
             reducer.feed(self.ready_after.get(-1, ()))
+        ng = len(self.bwd_groups)
         if self._graphs_on() and self._bwd_warm:
             if self._bwd_graphs is None:
-                cuts = [0] + [e + 1 for e in self._seg_ends if e + 1 < n] + [n]
+                cuts = [0] + [e + 1 for e in self._seg_ends if e + 1 < ng] + [ng]
                 graphs = []
                 for lo, hi in zip(cuts, cuts[1:]):
                     g = self._capture(lambda lo=lo, hi=hi: self._backward_range(lo, hi))
@@ -577,22 +746,14 @@ class TrainPlan:
             for lo, hi, g in self._bwd_graphs:
                 g.replay()
                 if reducer is not None:
-                    for i in range(lo, hi):
-                        reducer.feed(self.ready_after.get(i, ()))
+                    for gi in range(lo, hi):
+                        for i in range(self.bwd_groups[gi]["lo"], self.bwd_groups[gi]["hi"]):
+                            reducer.feed(self.ready_after.get(i, ()))
             nat.count_launches(self._bwd_launches)
         else:
             n0 = nat.launch_count()
             self._seg_ends = []
-            self.flat.zero_()
-            for i, f in enumerate(self.bwd):
-                f(flat, self.dps_in)
-                if reducer is not None:
-                    self.wg.join()          # a bucket may only leave once its weight gradients (side stream) are complete
-                    sent = reducer.calls
-                    reducer.feed(self.ready_after.get(i, ()))
-                    if reducer.calls != sent:
-                        self._seg_ends.append(i)
-            self.wg.join()
+            self._backward_range(0, ng, reducer=reducer, record_sends=True)
             self._bwd_launches, self._bwd_warm = nat.launch_count() - n0, True
         if reducer is not None:
             reducer.finish()
