@@ -42,9 +42,9 @@ __device__ __forceinline__ float act_grad(float x, int act) {
     case DYK_ACT_MISH: {
       // mish'(x) = t + x*sigmoid(x)*(1 - t^2), t = tanh(softplus(x)) = n/(n+2), n = e^x (e^x + 2).  With n + 1 = (e^x + 1)^2
       // this is (n (n+2) + 4 x e^x (e^x + 1)) / (n+2)^2: one exponential and one reciprocal per element.
-      const float e = __expf(fminf(x, 20.f));
+      const float e = ex2_approx(fminf(x, 20.f) * 1.4426950408889634f);    // bare MUFU ops, see mish_f (act.cuh)
       const float n = e * (e + 2.f);
-      const float r = __fdividef(1.f, n + 2.f);
+      const float r = rcp_approx(n + 2.f);
       return x > 20.f ? 1.f : fmaf(n, n + 2.f, 4.f * x * e * (e + 1.f)) * r * r;
     }
     case DYK_ACT_RELU: return x > 0.f ? 1.f : 0.f;

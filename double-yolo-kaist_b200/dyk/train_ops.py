@@ -15,16 +15,39 @@ from . import _native as nat
 from . import ops
 from .ops import View, _p, _stream
 
-_scratch = {}
+_scratch = {}            # default registry (direct, eager use of the wrappers below)
+_active = [_scratch]     # innermost registry in use; TrainPlan installs its own for the duration of a step
+
+
+class use_scratch:
+    """Context manager: scratch buffers requested inside belong to `registry` (a dict owned by the caller).
+
+    A training plan captures its launches into CUDA graphs, which bake the scratch addresses in.  A buffer that a later,
+    larger request replaces must therefore stay allocated for as long as the plan lives — with one process-wide registry
+    a bigger plan (multi-scale training) or another model freed the old buffer, the allocator handed the memory to
+    something else, and the next replay of the first plan's graph scribbled over it.  Each plan now owns its registry;
+    replaced buffers are parked in registry['_keep'] and die with the plan."""
+
+    def __init__(self, registry: dict):
+        self.registry = registry
+
+    def __enter__(self):
+        _active.append(self.registry)
+
+    def __exit__(self, *exc):
+        _active.pop()
 
 
 def scratch(nbytes: int, device, tag="f") -> torch.Tensor:
-    """Device scratch of at least nbytes (uint8), cached per (device, stream, tag)."""
+    """Device scratch of at least nbytes (uint8), cached per (device, stream, tag) in the active registry."""
+    reg = _active[-1]
     key = (device, torch.cuda.current_stream().cuda_stream, tag)
-    t = _scratch.get(key)
+    t = reg.get(key)
     if t is None or t.numel() < nbytes:
+        if t is not None and reg is not _scratch:
+            reg.setdefault("_keep", []).append(t)
         t = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
-        _scratch[key] = t
+        reg[key] = t
     return t
 
 

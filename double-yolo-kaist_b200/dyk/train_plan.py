@@ -176,6 +176,7 @@ class TrainPlan:
         self._finish_forward_schedule()
         self._bind_backward()
         # gradients of a step are produced in this buffer (one view per parameter) and handed out as a copy
+        self._scratch = {}       # kernel workspaces of this plan (addresses are baked into its CUDA graphs)
         self.flat = torch.zeros(self.grad_numel, dtype=torch.float32, device=device)
         self.dps_in = [torch.zeros_like(po) for po in self.p_outs]
         self._sig = None
@@ -447,6 +448,10 @@ class TrainPlan:
         """One training forward: frames are copied into the plan's static buffers, then the ~900 launches (weight packing,
         convolutions, batch statistics, BN + activation, pools, SE, head permutes) run as ONE graph replay — the first
         call runs them eagerly (one-time kernel attribute setup), the second captures."""
+        with T.use_scratch(self._scratch):
+            return self._forward(x, y)
+
+    def _forward(self, x, y):
         self.in_x.copy_(x)
         if self.in_y is not None:
             self.in_y.copy_(y)
@@ -717,6 +722,10 @@ class TrainPlan:
         a bucket go out, so the all-reduce of a finished bucket is issued between two replays and overlaps the next one.
         The gradients are returned as views of a COPY of the plan's flat buffer (0.15 ms for 464 MB): the next backward
         overwrites the buffer, and gradient accumulation over several backward passes must not alias it."""
+        with T.use_scratch(self._scratch):
+            return self._backward(dps)
+
+    def _backward(self, dps):
         for d, buf in zip(dps, self.dps_in):
             if d is None:
                 buf.zero_()

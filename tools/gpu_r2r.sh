@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name"; timeout "$@" > gpurun_out/$name.log 2>&1; echo "exit $?" | tee -a gpurun_out/$name.log; tail -n ${TAILN:-25} gpurun_out/$name.log; }
+TAILN=5 run r2r_tests 1800 python -m pytest tests -q -m gpu --timeout 600 -p no:cacheprovider
+bench() { timeout 600 python bench.py "$@" 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(' fps', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'ms', round(d['ms_per_step'],3), 'roofline', d.get('roofline',{}).get('frac'), 'clocks', d.get('clocks'))"; }
+echo "dyolov4 fp16 bs16"; bench --cfg kaist_dyolov4_fshare_global_concat_se3.cfg --steps 100 --warmup 5 --no-cpu-baseline --no-train-leg --sustain-s 0
+echo "dyolov4 fp16 bs16 again"; bench --cfg kaist_dyolov4_fshare_global_concat_se3.cfg --steps 100 --warmup 5 --no-cpu-baseline --no-train-leg --sustain-s 0
+echo "dyolov4 bf16 bs16"; bench --cfg kaist_dyolov4_fshare_global_concat_se3.cfg --dtype bf16 --steps 100 --warmup 5 --no-cpu-baseline --no-train-leg --sustain-s 0
+python tools/layer_times.py kaist_dyolov4_fshare_global_concat_se3.cfg 16 gpurun_out/r2r_layers_v4.json 2>&1 | grep -v Summary | head -30
