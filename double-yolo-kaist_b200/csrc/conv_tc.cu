@@ -25,6 +25,7 @@
 #include "common.h"
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include "ptx.cuh"
 #include "act.cuh"
 #include "conv_common.cuh"
@@ -124,27 +125,40 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvKArgs& p, int tile) {
 // column chunks half, half+2, ... of kColsW channels.  Per chunk: tcgen05.ld -> scale/bias/activation
 // (+ residual) in fp32 -> 16-bit -> swizzled warp-private staging -> one TMA store of the 32-row sub-box issued
 // by lane 0.  kAct is a compile-time activation so that only one code path is resident in the instruction cache.
+// Per-thread geometry of the epilogue that does not change from tile to tile (hoisted out of the tile loop: on the
+// short-main-loop 1x1 layers a warp handles only 16 - 32 elements per thread and tile, and ncu showed ~290 of its 448
+// instructions per tile were this bookkeeping, not arithmetic).
+struct EpiRow {
+  int wi, hi, ni;          // offset of this thread's row (pixel) inside the tile
+  int sw, sh, sn;          // offset of this warp's 32-row sub-box inside the tile
+};
+__device__ __forceinline__ EpiRow epi_row(const ConvKArgs& p, int q, int lane) {
+  EpiRow r;
+  const int row = q * 32 + lane, r0 = q * 32;
+  r.wi = row & (p.tw - 1);
+  r.hi = (row >> p.tw_log2) & (p.th - 1);
+  r.ni = row >> (p.tw_log2 + p.th_log2);
+  r.sw = r0 & (p.tw - 1);
+  r.sh = (r0 >> p.tw_log2) & (p.th - 1);
+  r.sn = r0 >> (p.tw_log2 + p.th_log2);
+  return r;
+}
+
 template <int BLOCK_N, int BLOCK_K, int kSplit, bool kBf16, int kAct>
-__device__ __forceinline__ void epilogue_tile(const ConvTmaps& tm, const ConvKArgs& p, const TileCoord& tc,
-                                              uint32_t t_row, uint8_t* wstage, float* wvec, int& sbuf,
-                                              uint64_t* tempty, int q, int lane, int half) {
+__device__ __forceinline__ void epilogue_tile(const ConvTmaps& tm, const ConvKArgs& p, const TileCoord& tc, const EpiRow& er,
+                                              uint32_t t_row, uint8_t* wstage, float* wvec, int& sbuf, int& staged_nblk,
+                                              uint64_t* tempty, int lane, int half) {
   using S = ConvSmem<BLOCK_N, BLOCK_K, kSplit>;
   constexpr int kCols = S::kColsW;                  // 32 or 16
   constexpr int kRowBytes = kCols * 2;              // 64 or 32 (== TMA store swizzle span)
   constexpr int kChunks = BLOCK_N / kCols;          // column chunks per tile
-  const int row = q * 32 + lane;
-  const int wi = row & (p.tw - 1);
-  const int hi = (row >> p.tw_log2) & (p.th - 1);
-  const int ni = row >> (p.tw_log2 + p.th_log2);
-  const int wo = tc.w0 + wi, ho = tc.h0 + hi, nn = tc.n0 + ni;
+  const int wo = tc.w0 + er.wi, ho = tc.h0 + er.hi, nn = tc.n0 + er.ni;
   const bool pix_ok = (wo < p.Wo) && (ho < p.Ho) && (nn < p.N);
   const long long pix = (static_cast<long long>(nn) * p.Ho + ho) * p.Wo + wo;
   const int n_base = tc.nblk * BLOCK_N;
   const bool has_res = p.res != nullptr;
   // origin of this warp's 32-row sub-box inside the tile (warp-uniform)
-  const int r0 = q * 32;
-  const int sw0 = tc.w0 + (r0 & (p.tw - 1)), sh0 = tc.h0 + ((r0 >> p.tw_log2) & (p.th - 1)),
-            sn0 = tc.n0 + (r0 >> (p.tw_log2 + p.th_log2));
+  const int sw0 = tc.w0 + er.sw, sh0 = tc.h0 + er.sh, sn0 = tc.n0 + er.sn;
 
   uint4 rres[kCols / 8];
   auto load_res = [&](int c) {
@@ -156,17 +170,21 @@ __device__ __forceinline__ void epilogue_tile(const ConvTmaps& tm, const ConvKAr
       if (has_res && pix_ok && c0 + j * 8 < p.Cout_store) rres[j] = __ldg(reinterpret_cast<const uint4*>(rp) + j);
     }
   };
-  // this warp's scale / bias values -> warp-private shared memory: wvec[2*(j*kCols + col) + {0,1}] for its j-th chunk
-  __syncwarp();   // the previous tile's reads of wvec are complete
-  if (lane < kCols) {
+  // this warp's scale / bias values -> warp-private shared memory: wvec[2*(j*kCols + col) + {0,1}] for its j-th chunk;
+  // only when the output-channel block differs from the one staged last (never again on layers with one channel block)
+  if (tc.nblk != staged_nblk) {
+    staged_nblk = tc.nblk;
+    __syncwarp();   // the previous tile's reads of wvec are complete
+    if (lane < kCols) {
 #pragma unroll
-    for (int j = 0; j < kChunks / kSplit; ++j) {
-      const int col = n_base + (half + kSplit * j) * kCols + lane;
-      wvec[j * kCols + lane] = p.scale ? __ldg(p.scale + col) : 1.f;
-      wvec[(kChunks / kSplit) * kCols + j * kCols + lane] = p.bias ? __ldg(p.bias + col) : 0.f;
+      for (int j = 0; j < kChunks / kSplit; ++j) {
+        const int col = n_base + (half + kSplit * j) * kCols + lane;
+        wvec[j * kCols + lane] = p.scale ? __ldg(p.scale + col) : 1.f;
+        wvec[(kChunks / kSplit) * kCols + j * kCols + lane] = p.bias ? __ldg(p.bias + col) : 0.f;
+      }
     }
+    __syncwarp();
   }
-  __syncwarp();
   const float* wscale = wvec;
   const float* wbias = wvec + (kChunks / kSplit) * kCols;
 
@@ -543,30 +561,35 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
         }
         continue;
       }
-      const int as = tl & 1;
-      const uint32_t aphase = (tl >> 1) & 1;
-      const TileCoord tc = tile_coord(p, tile);
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
-      // The accumulator wait sits inside the activation-specialised body's caller so that residual / vector
-      // prefetches of the *next* tile are not hoisted above it by accident.
-      {
-        const long long t0 = (kProf && p.prof) ? clock64() : 0;
-        mbar_wait(&tfull_bar[as], aphase);
-        if (kProf && p.prof) t_wtfull += clock64() - t0;
-      }
-      tc_fence_after_sync();
-#define DYK_EPI(ACT)                                                                                         \
-  epilogue_tile<BLOCK_N, BLOCK_K, kSplit, kBf16, ACT>(tm, p, tc, t_row, wstage, wvec, sbuf, &tempty_bar[as], q, lane, half)
+      // 16-bit / fp32-head path: one specialised tile loop per activation (the switch is taken once per kernel, the
+      // per-thread row geometry and the staged scale / bias survive from tile to tile)
+      const EpiRow er = epi_row(p, q, lane);
+      int staged_nblk = -1;
+      auto tile_loop = [&](auto act_tag) {
+        constexpr int kActC = decltype(act_tag)::value;
+        for (; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+          const int as = tl & 1;
+          const TileCoord tc = tile_coord(p, tile);
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
+          {
+            const long long t0 = (kProf && p.prof) ? clock64() : 0;
+            mbar_wait(&tfull_bar[as], (tl >> 1) & 1);
+            if (kProf && p.prof) t_wtfull += clock64() - t0;
+          }
+          tc_fence_after_sync();
+          epilogue_tile<BLOCK_N, BLOCK_K, kSplit, kBf16, kActC>(tm, p, tc, er, t_row, wstage, wvec, sbuf, staged_nblk,
+                                                                 &tempty_bar[as], lane, half);
+        }
+      };
       switch (p.act) {
-        case DYK_ACT_LEAKY: DYK_EPI(DYK_ACT_LEAKY); break;
-        case DYK_ACT_MISH: DYK_EPI(DYK_ACT_MISH); break;
-        case DYK_ACT_RELU: DYK_EPI(DYK_ACT_RELU); break;
-        case DYK_ACT_RELU6: DYK_EPI(DYK_ACT_RELU6); break;
-        case DYK_ACT_HARDSWISH: DYK_EPI(DYK_ACT_HARDSWISH); break;
-        case DYK_ACT_HARDSIGMOID: DYK_EPI(DYK_ACT_HARDSIGMOID); break;
-        default: DYK_EPI(DYK_ACT_LINEAR); break;
+        case DYK_ACT_LEAKY: tile_loop(std::integral_constant<int, DYK_ACT_LEAKY>{}); break;
+        case DYK_ACT_MISH: tile_loop(std::integral_constant<int, DYK_ACT_MISH>{}); break;
+        case DYK_ACT_RELU: tile_loop(std::integral_constant<int, DYK_ACT_RELU>{}); break;
+        case DYK_ACT_RELU6: tile_loop(std::integral_constant<int, DYK_ACT_RELU6>{}); break;
+        case DYK_ACT_HARDSWISH: tile_loop(std::integral_constant<int, DYK_ACT_HARDSWISH>{}); break;
+        case DYK_ACT_HARDSIGMOID: tile_loop(std::integral_constant<int, DYK_ACT_HARDSIGMOID>{}); break;
+        default: tile_loop(std::integral_constant<int, DYK_ACT_LINEAR>{}); break;
       }
-#undef DYK_EPI
     }
     if (lane == 0) tma_store_wait_all<0>();
     if (kProf && p.prof && ew == 0 && lane == 0) {
