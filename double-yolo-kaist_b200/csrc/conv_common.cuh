@@ -42,5 +42,20 @@ __device__ __forceinline__ float2 unpack2(uint32_t v) {
   }
 }
 
+// Residual rows of the tiles a CTA will reach a few iterations from now, requested into L2 ahead of time.  The epilogue
+// loads the residual of a tile when it gets there; on layers with a short main loop (few input channels, large maps) that
+// load's DRAM latency (2 - 3 us under load) used to be exposed once per tile or even per column chunk and set the whole
+// tile period (4.3 us per 128 x 128 tile on 64->128 3x3 @128x160, three times the HBM time).  bytes % 16 == 0, 16-byte aligned.
+constexpr int kResPrefetchTiles = 4;
+// mode (DYK_RES_PF, read once on the host): 0 = off, 1 = one prefetch.global.L2 per 128-byte line, 2 = one bulk prefetch per row
+__device__ __forceinline__ void l2_prefetch_row(const void* gptr, unsigned bytes, int mode) {
+  if (mode == 2) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+  } else {
+    const char* c = reinterpret_cast<const char*>(gptr);
+    for (unsigned o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
+  }
+}
+int res_prefetch_mode();   // conv_tc.cu
 
 }  // namespace dyk

@@ -41,6 +41,7 @@ struct HaloKArgs {
   int num_subs;                 // subs_w * subs_h * N
   int n_blocks, num_tiles;      // tiles = ceil(num_subs / kSub) * n_blocks, n-block fastest
   int k_chunks;                 // ceil(Cin / 64)
+  int k_last_steps;             // K = 16 MMA steps of the last chunk (Cin = 32: 2 — the zero-filled half of the box is skipped)
   int Cout_store;
   int act;
   FastDiv fd_nblocks, fd_subs_w, fd_subs_h;
@@ -49,6 +50,7 @@ struct HaloKArgs {
   const void* res;              // may be null
   long long res_pix_stride;
   unsigned long long* prof;     // role-cycle counters (-DDYK_CONV_PROFILE builds only), may be null
+  int res_pf;                   // residual L2 prefetch mode (conv_common.cuh)
 };
 
 #ifdef DYK_CONV_PROFILE
@@ -276,8 +278,9 @@ conv3x3_halo_kernel(const __grid_constant__ HaloTmaps tm, const HaloKArgs p) {
       }
     }
   } else if (warp_idx == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer: whole warp in the loop, one elected
+    // lane per tcgen05 instruction (uniform-register operands; see conv_halo2.cu)
+    {
       constexpr uint32_t idesc = umma_idesc_f16(128, BLOCK_N, kBf16 ? 1 : 0);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
@@ -298,6 +301,8 @@ conv3x3_halo_kernel(const __grid_constant__ HaloTmaps tm, const HaloKArgs p) {
             tc_fence_after_sync();
             const uint64_t bdesc = umma_desc_kmajor<128>(smem_u32(b_base + bs * S::kBSlot));
             const int r = tap / 3, s = tap - 3 * r;
+            const int ksteps = kc == p.k_chunks - 1 ? p.k_last_steps : 4;
+            const bool el = elect_one();
 #pragma unroll
             for (int j = 0; j < kSub; ++j) {
               // shifted view of the halo tile: first row r*10 + s, 10 rows between 8-row groups
@@ -309,17 +314,22 @@ conv3x3_halo_kernel(const __grid_constant__ HaloTmaps tm, const HaloKArgs p) {
               adesc |= static_cast<uint64_t>(2) << 61;
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_f16_ss(d_tmem + j * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                if (el && k < ksteps)
+                  umma_f16_ss(d_tmem + j * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
             }
-            umma_commit(&b_empty[bs]);
+            if (el) umma_commit(&b_empty[bs]);
+            __syncwarp();
             if (++bs == kBStages) { bs = 0; bph ^= 1; }
           }
-          umma_commit(&a_empty[as]);
+          if (elect_one()) {
+            umma_commit(&a_empty[as]);
+            if (kc == p.k_chunks - 1) umma_commit(&tfull[acc]);
+          }
+          __syncwarp();
           if (++as == kAStages) { as = 0; aph ^= 1; }
         }
-        umma_commit(&tfull[acc]);
       }
-      if (kHProf && p.prof) {
+      if (kHProf && p.prof && lane == 0) {
         atomicAdd(p.prof + 2, (unsigned long long)t_wdata);
         atomicAdd(p.prof + 3, (unsigned long long)t_wacc);
         atomicAdd(p.prof + 4, (unsigned long long)(clock64() - t_begin));
@@ -338,7 +348,24 @@ conv3x3_halo_kernel(const __grid_constant__ HaloTmaps tm, const HaloKArgs p) {
     int tl = 0, sbuf = 0;
     long long t_wtfull = 0;
     const long long t_begin = HPROF_T0();
+    // residual rows of the tiles this CTA reaches kResPrefetchTiles iterations from now -> L2 (conv_common.cuh)
+    auto prefetch_res = [&](int t) {
+      if (p.res_pf && p.res != nullptr && t < p.num_tiles && (kSub == 2 || grp == 0)) {
+        const unsigned mt = fd_div((unsigned)t, p.fd_nblocks);
+        const int nb = (t - (int)(mt * p.fd_nblocks.div)) * BLOCK_N;
+        const SubCoord f = sub_coord(p, mt * kSub + j);
+        const int row = q * 32 + lane;
+        const int wo = f.w0 + (row & (kSubW - 1)), ho = f.h0 + (row >> 3);
+        if (f.n < p.N && wo < p.W && ho < p.H) {
+          const long long pix = (static_cast<long long>(f.n) * p.H + ho) * p.W + wo;
+          const int cols = p.Cout_store - nb < BLOCK_N ? p.Cout_store - nb : BLOCK_N;
+          l2_prefetch_row(reinterpret_cast<const uint8_t*>(p.res) + (pix * p.res_pix_stride + nb) * 2, (unsigned)cols * 2u, p.res_pf);
+        }
+      }
+    };
+    for (int d = 1; d < kResPrefetchTiles; ++d) prefetch_res((int)blockIdx.x + d * (int)gridDim.x);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+      prefetch_res(tile + kResPrefetchTiles * (int)gridDim.x);
       const int acc = tl & 1;
       const unsigned mt = fd_div((unsigned)tile, p.fd_nblocks);
       const int nblk = tile - (int)(mt * p.fd_nblocks.div);
@@ -451,6 +478,7 @@ int conv3x3_halo_try(const dyk_conv_params* p, cudaStream_t stream) {
   ka.n_blocks = n_blocks;
   ka.num_tiles = (int)(ceil_div64(num_subs, kSub) * n_blocks);
   ka.k_chunks = k_chunks;
+  ka.k_last_steps = ceil_div(p->Cin - (k_chunks - 1) * 64, 16);
   ka.Cout_store = p->Cout_store;
   ka.act = p->act;
   ka.fd_nblocks = make_fastdiv((unsigned)n_blocks);
@@ -459,6 +487,7 @@ int conv3x3_halo_try(const dyk_conv_params* p, cudaStream_t stream) {
   ka.scale = p->scale; ka.bias = p->bias;
   ka.res = p->res; ka.res_pix_stride = p->res_pix_stride;
   ka.prof = g_conv_prof;
+  ka.res_pf = res_prefetch_mode();
 
   const bool bf = p->dtype == DYK_BF16;
   if (BN == 256) return bf ? launch_halo<256, 1, true>(tm, ka, stream) : launch_halo<256, 1, false>(tm, ka, stream);

@@ -15,10 +15,27 @@
 //
 // Warp roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner (+ MMA issuer in the leader),
 // warps 2..9 = epilogue.
+//
+// Dual-source variant (kDual; WeightedFeatureFusion, build_utils/layers.py:63-85, fused into the convolution that
+// consumes it): the A operand is w0 * x + w1 * x2, formed in shared memory.  Each CTA's producer loads the halo windows
+// of BOTH tensors (same box, same swizzle, so element i of one slot corresponds to element i of the other) and four extra
+// "combiner" warps overwrite the x slot with the rounded weighted sum — once per 64-channel chunk, for all nine taps —
+// then publish it to the MMA issuer (fence.proxy.async + arrive on the leader's "full" barrier).  The fused sum is never
+// written to memory: both modality tensors are read once.  The two extra halo slots are paid for with three weight stages.
+//
+// Resident-weights variant (kResB; the early high-resolution layers: Cin <= 64, 64..128 output channels, e.g. 32->64 @256x320
+// and 64->128 @128x160): these layers are HBM-bound (Cin + 2 Cout bytes per pixel against 18 Cin Cout FLOPs) and were
+// running at 40 % of the HBM rate for two reasons measured with the role counters / ncu: (1) the generic kernel re-fetches
+// the input tile for each of the nine taps and the weight tile for every pixel tile, 288 KB of L2 -> SM traffic per 128
+// pixels, which is bound by the ~50 B/clk/SM L2 delivery rate, not by HBM; (2) with two input slots only one tile's load is
+// in flight per SM, too few bytes to cover the HBM latency.  Here the whole filter (9 taps x Cout x 128 B, half per CTA of
+// the pair: <= 72 KB) is loaded ONCE per CTA and stays in shared memory, the input halo window is the only operand
+// traffic (23 KB per 128 pixels), and the freed shared memory holds a ring of four input windows (three loads in flight).
 #include "common.h"
 #include "ptx.cuh"
 #include "act.cuh"
 #include "conv_common.cuh"
+#include "vec.cuh"
 #include <cstdlib>
 #include <cstring>
 
@@ -33,6 +50,7 @@ struct Halo2Tmaps {
   CUtensorMap b;  // packed weights (Cin, 9, Cout), box {64, 1, 128}
   CUtensorMap bs; // the same tensor with box {64, 1, 128 / tail_split} for the split items of the last round
   CUtensorMap y;  // output (Cout_store, W, H, N), box {32, 8, 4, 1}
+  CUtensorMap a2; // second source of the dual-source variant (same geometry as a)
 };
 
 #ifdef DYK_CONV_PROFILE
@@ -45,6 +63,7 @@ constexpr bool kH2Prof = false;
 // staging buffer (TMA store read), 7 clusters
 struct Halo2KArgs {
   unsigned long long* prof;
+  int res_pf;                   // residual L2 prefetch mode (conv_common.cuh)
   int H, W, N;
   int num_subs;
   int n_blocks, num_tiles;      // pair tiles = ceil(num_subs / 2) * n_blocks, n-block fastest
@@ -60,6 +79,9 @@ struct Halo2KArgs {
   const float* bias;
   const void* res;
   long long res_pix_stride;
+  const float* x_wts_raw;       // dual source: the fusion module's raw parameter w[2]; A = sigmoid(w)[0] * x + sigmoid(w)[1] * x2
+  int res_cols;                 // resident-weights variant: output channels (MMA N), multiple of 32, <= 128
+  int k_last_steps;             // K = 16 MMA steps of the last 64-channel chunk (Cin = 32: 2)
 };
 
 constexpr int kH2EpiWarps = 8;
@@ -75,6 +97,14 @@ constexpr int kH2VecFloats = 2 * kH2BlockN;
 constexpr int kH2VecBytes = kH2EpiWarps * kH2VecFloats * 4;
 constexpr int kH2Total = kH2AStages * kH2ASlot + kH2BStages * kH2BSlot + kH2StagingBytes + kH2VecBytes + 1024 + 1024;
 static_assert(kH2Total <= 227 * 1024, "halo2 shared memory budget");
+constexpr int kH2CombWarps = 4;                                // dual-source variant: combiner warps per CTA
+constexpr int kH2BStagesDual = 5;
+constexpr int kH2TotalDual = 2 * kH2AStages * kH2ASlot + kH2BStagesDual * kH2BSlot + kH2StagingBytes + kH2VecBytes + 1024 + 1024;
+static_assert(kH2TotalDual <= 227 * 1024, "halo2 (dual source) shared memory budget");
+constexpr int kH2AStagesRes = 4, kH2BSlotRes = 64 * 128;       // resident weights: 9 taps x (<= 64 rows per CTA) x 128 B
+constexpr int kH2TotalRes = kH2AStagesRes * kH2ASlot + 9 * kH2BSlotRes + kH2StagingBytes + kH2VecBytes + 1024 + 1024;
+static_assert(kH2TotalRes <= 227 * 1024, "halo2 (resident weights) shared memory budget");
+constexpr int kH2MaxAStages = 4, kH2MaxBStages = 9;
 
 struct Sub2 {
   int w0, h0, n;
@@ -83,6 +113,7 @@ struct Item2 {
   int tile, ncol0, ncols;
 };
 __device__ __forceinline__ Item2 item2_decode(const Halo2KArgs& p, int item) {
+  if (p.res_cols) return Item2{item, 0, p.res_cols};
   if (item < p.full_items) return Item2{item, 0, kH2BlockN};
   const int j = item - p.full_items;
   const int ncols = kH2BlockN >> p.tail_lg;
@@ -100,16 +131,15 @@ __device__ __forceinline__ Sub2 sub2_coord(const Halo2KArgs& p, unsigned sub) {
   return c;
 }
 
-template <bool kBf16, int kAct>
+template <bool kBf16, int kAct, bool kNoRes>
 __device__ __forceinline__ void halo2_epilogue(const Halo2Tmaps& tm, const Halo2KArgs& p, const Sub2& sc, int n_base,
                                                int nchunks, uint32_t t_row, uint8_t* wstage, float* wvec, int& sbuf,
                                                uint32_t tempty_leader, int q, int lane, int half, bool prof_warp,
                                                long long& prof_ld, long long& prof_st, const uint4 (&rres_all)[4][4]) {
   constexpr int kCols = 32;
   constexpr int kChunks = kH2BlockN / kCols;   // up to 8 (nchunks of them in this item); this warp handles chunks half, half+2, ...
-  const int row = q * 32 + lane;
   const bool sub_ok = sc.n < p.N;
-  const bool has_res = p.res != nullptr;
+  const bool has_res = !kNoRes && p.res != nullptr;   // (the dual-source variant never carries a residual)
 
   __syncwarp();
 #pragma unroll
@@ -132,7 +162,7 @@ __device__ __forceinline__ void halo2_epilogue(const Halo2Tmaps& tm, const Halo2
     if (beyond) {
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty_leader);
+      if (lane == 0) mbar_arrive_remote(tempty_leader);
       break;
     }
     uint32_t v[kCols];
@@ -143,7 +173,7 @@ __device__ __forceinline__ void halo2_epilogue(const Halo2Tmaps& tm, const Halo2
     if (last) {
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty_leader);
+      if (lane == 0) mbar_arrive_remote(tempty_leader);
     }
     uint8_t* sbase = wstage + sbuf * 2048;
     const long long t_st0 = (kH2Prof && p.prof) ? clock64() : 0;
@@ -191,9 +221,13 @@ __device__ __forceinline__ void halo2_epilogue(const Halo2Tmaps& tm, const Halo2
   }
 }
 
-template <bool kBf16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kH2Threads, 1)
+template <bool kBf16, bool kDual, bool kResB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kH2Threads + (kDual ? 32 * kH2CombWarps : 0), 1)
 conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) {
+  static_assert(!(kDual && kResB), "variants are exclusive");
+  constexpr int kBStages = kResB ? 9 : (kDual ? kH2BStagesDual : kH2BStages);
+  constexpr int kAStg = kResB ? kH2AStagesRes : kH2AStages;
+  constexpr int kBSlotBytes = kResB ? kH2BSlotRes : kH2BSlot;
   griddep_launch_dependents();
   // profile build: wall-clock (globaltimer, ns) of kernel entry / prologue end / role-loop end / exit, min and max over CTAs
   auto stamp = [&](int lo, int hi) {
@@ -208,17 +242,19 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_base = smem;
-  uint8_t* b_base = a_base + kH2AStages * kH2ASlot;
-  uint8_t* staging = b_base + kH2BStages * kH2BSlot;
+  uint8_t* a2_base = a_base + kAStg * kH2ASlot;                             // dual source only
+  uint8_t* b_base = a_base + (kDual ? 2 : 1) * kAStg * kH2ASlot;
+  uint8_t* staging = b_base + kBStages * kBSlotBytes;
   float* vecs = reinterpret_cast<float*>(staging + kH2StagingBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(vecs) + kH2VecBytes);
   uint64_t* a_full = bars;                          // [2]  (used in the leader)
-  uint64_t* a_empty = a_full + kH2AStages;          // [2]  (per CTA, multicast arrivals)
-  uint64_t* b_full = a_empty + kH2AStages;          // [8]  (leader)
-  uint64_t* b_empty = b_full + kH2BStages;          // [8]  (per CTA)
-  uint64_t* tfull = b_empty + kH2BStages;           // [2]  (per CTA, multicast arrivals)
+  uint64_t* a_empty = a_full + kH2MaxAStages;       // [2]  (per CTA, multicast arrivals)
+  uint64_t* b_full = a_empty + kH2MaxAStages;       // [8]  (leader)
+  uint64_t* b_empty = b_full + kH2MaxBStages;       // [8]  (per CTA)
+  uint64_t* tfull = b_empty + kH2MaxBStages;        // [2]  (per CTA, multicast arrivals)
   uint64_t* tempty = tfull + 2;                     // [2]  (leader; 16 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* a_raw = tempty + 2;                     // [2]  (per CTA; dual source: both halo windows landed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_raw + kH2MaxAStages);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -232,13 +268,20 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
     tma_prefetch_desc(&tm.b);
     tma_prefetch_desc(&tm.bs);
     tma_prefetch_desc(&tm.y);
-    for (int i = 0; i < kH2AStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < kH2BStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    if (kDual) tma_prefetch_desc(&tm.a2);
+    // dual source: "full" = the combiner warps of both CTAs have published the weighted sum (no TMA bytes credited)
+    for (int i = 0; i < kAStg; ++i) {
+      mbar_init(&a_full[i], kDual ? 2 * kH2CombWarps : 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&a_raw[i], 1);
+    }
+    for (int i = 0; i < kBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * kH2EpiWarps); }
     fence_mbar_init();
   }
   if (warp_idx == 1) tmem_alloc_2sm<512>(tmem_slot);
   tc_fence_before_sync();
+  __syncthreads();         // (the cluster barrier below already orders the CTA; this one is what compute-sanitizer models)
   cluster_sync_all();      // barriers of both CTAs initialised before any remote arrive / TMA credit
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
@@ -250,6 +293,14 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
     if (lane == 0) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
+      if constexpr (kResB) {
+        // the whole filter, once: tap t -> slot t (this CTA's half of the output channels)
+        const uint32_t b_bytes = (uint32_t)p.res_cols * 128u;
+        for (int tap = 0; tap < 9; ++tap) {
+          if (leader) mbar_arrive_expect_tx(&b_full[tap], b_bytes);
+          tma_load_3d_2sm(b_base + tap * kBSlotBytes, &tm.bs, leader_smem_addr(&b_full[tap]), 0, tap, (int)rank * (p.res_cols >> 1));
+        }
+      }
       for (int item = cluster_id; item < p.num_items; item += num_clusters) {
         const Item2 it = item2_decode(p, item);
         const int tile = it.tile;
@@ -262,23 +313,36 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
         const int b_row = nblk * kH2BlockN + it.ncol0 + (int)rank * (it.ncols >> 1);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(&a_empty[as], aph ^ 1);
-          if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * kH2HaloBytes);
-          tma_load_4d_2sm(a_base + as * kH2ASlot, &tm.a, leader_smem_addr(&a_full[as]), kc * 64, sc.w0 - 1, sc.h0 - 1, sc.n);
-          if (++as == kH2AStages) { as = 0; aph ^= 1; }
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&b_empty[bs], bph ^ 1);
-            if (leader) mbar_arrive_expect_tx(&b_full[bs], b_bytes);
-            tma_load_3d_2sm(b_base + bs * kH2BSlot, bmap, leader_smem_addr(&b_full[bs]), kc * 64, tap, b_row);
-            if (++bs == kH2BStages) { bs = 0; bph ^= 1; }
+          if constexpr (kDual) {
+            mbar_arrive_expect_tx(&a_raw[as], 2 * kH2HaloBytes);
+            tma_load_4d(a_base + as * kH2ASlot, &tm.a, &a_raw[as], kc * 64, sc.w0 - 1, sc.h0 - 1, sc.n);
+            tma_load_4d(a2_base + as * kH2ASlot, &tm.a2, &a_raw[as], kc * 64, sc.w0 - 1, sc.h0 - 1, sc.n);
+          } else {
+            if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * kH2HaloBytes);
+            tma_load_4d_2sm(a_base + as * kH2ASlot, &tm.a, leader_smem_addr(&a_full[as]), kc * 64, sc.w0 - 1, sc.h0 - 1, sc.n);
+          }
+          if (++as == kAStg) { as = 0; aph ^= 1; }
+          if constexpr (!kResB) {
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              if (leader) mbar_arrive_expect_tx(&b_full[bs], b_bytes);
+              tma_load_3d_2sm(b_base + bs * kBSlotBytes, bmap, leader_smem_addr(&b_full[bs]), kc * 64, tap, b_row);
+              if (++bs == kBStages) { bs = 0; bph ^= 1; }
+            }
           }
         }
       }
     }
   } else if (warp_idx == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
-    if (leader && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    // The WHOLE warp walks the loop (waits included) and one elected lane issues each tcgen05 instruction.  With a single
+    // thread inside `if (lane == 0)` every operand reached the MMA through a per-lane loop (ELECT + 5 R2UR.BROADCAST +
+    // BRA.U.ANY, ~24 SASS instructions per MMA, ncu source view): the issue loop itself ran at ~150 cycles per MMA and
+    // paced the tensor pipe (128 cycles per 256x256x16 pair MMA).  Warp-uniform control flow keeps descriptors and
+    // barrier addresses in uniform registers.
+    if (leader) {
       const uint32_t idesc_whole = umma_idesc_f16(256, kH2BlockN, kBf16 ? 1 : 0);
-      const uint32_t idesc_split = umma_idesc_f16(256, kH2BlockN >> p.tail_lg, kBf16 ? 1 : 0);
+      const uint32_t idesc_split = umma_idesc_f16(256, kResB ? p.res_cols : (kH2BlockN >> p.tail_lg), kBf16 ? 1 : 0);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int tl = 0;
@@ -287,7 +351,7 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
 #define H2WAIT(bar, ph, var) do { const long long t0 = (kH2Prof && p.prof) ? clock64() : 0; mbar_wait(bar, ph); \
                                   if (kH2Prof && p.prof) var += clock64() - t0; } while (0)
       for (int item = cluster_id; item < p.num_items; item += num_clusters, ++tl) {
-        const uint32_t idesc = item < p.full_items ? idesc_whole : idesc_split;
+        const uint32_t idesc = (!kResB && item < p.full_items) ? idesc_whole : idesc_split;
         const int acc = tl & 1;
         H2WAIT(&tempty[acc], ((tl >> 1) & 1) ^ 1, w_acc);
         tc_fence_after_sync();
@@ -296,10 +360,16 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
           H2WAIT(&a_full[as], aph, w_data);
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(a_base + as * kH2ASlot);
+          const int ksteps = kc == p.k_chunks - 1 ? p.k_last_steps : 4;
           for (int tap = 0; tap < 9; ++tap) {
-            H2WAIT(&b_full[bs], bph, w_data);
-            tc_fence_after_sync();
-            const uint64_t bdesc = umma_desc_kmajor<128>(smem_u32(b_base + bs * kH2BSlot));
+            if constexpr (kResB) {
+              if (tl == 0) { H2WAIT(&b_full[tap], 0, w_data); tc_fence_after_sync(); }     // the filter arrives once
+              bs = tap;
+            } else {
+              H2WAIT(&b_full[bs], bph, w_data);
+              tc_fence_after_sync();
+            }
+            const uint64_t bdesc = umma_desc_kmajor<128>(smem_u32(b_base + bs * kBSlotBytes));
             const int r = tap / 3, s = tap - 3 * r;
             uint64_t adesc = 0;
             adesc |= static_cast<uint64_t>(((sa + (r * kH2HaloW + s) * 128) & 0x3FFFF) >> 4);
@@ -307,22 +377,58 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
             adesc |= static_cast<uint64_t>((kH2HaloW * 128) >> 4) << 32;
             adesc |= static_cast<uint64_t>(1) << 46;
             adesc |= static_cast<uint64_t>(2) << 61;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_ss_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
-            umma_commit_2sm(&b_empty[bs]);
-            if (++bs == kH2BStages) { bs = 0; bph ^= 1; }
+              for (int k = 0; k < 4; ++k)
+                if (k < ksteps) umma_f16_ss_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              if constexpr (!kResB) umma_commit_2sm(&b_empty[bs]);
+            }
+            __syncwarp();
+            if constexpr (!kResB) {
+              if (++bs == kBStages) { bs = 0; bph ^= 1; }
+            }
           }
-          umma_commit_2sm(&a_empty[as]);
-          if (++as == kH2AStages) { as = 0; aph ^= 1; }
+          if (elect_one()) {
+            umma_commit_2sm(&a_empty[as]);
+            if (kc == p.k_chunks - 1) umma_commit_2sm(&tfull[acc]);
+          }
+          __syncwarp();
+          if (++as == kAStg) { as = 0; aph ^= 1; }
         }
-        umma_commit_2sm(&tfull[acc]);
       }
 #undef H2WAIT
-      if (kH2Prof && p.prof) {
+      if (kH2Prof && p.prof && lane == 0) {
         atomicAdd(p.prof + 0, (unsigned long long)w_data);
         atomicAdd(p.prof + 1, (unsigned long long)w_acc);
         atomicAdd(p.prof + 2, (unsigned long long)(clock64() - t_begin));
+      }
+    }
+  } else if (kDual && warp_idx >= 2 + kH2EpiWarps) {
+    // ------------------------------------------------------------------ combiner (dual source): A = w0 * x + w1 * x2
+    const int ct = threadIdx.x - kH2Threads;
+    // fusion_weights_kernel's arithmetic (elementwise.cu): sigmoid(w) * (2 / n), n = 2
+    const float w0 = (1.f / (1.f + expf(-__ldg(p.x_wts_raw)))) * (2.f / 2);
+    const float w1 = (1.f / (1.f + expf(-__ldg(p.x_wts_raw + 1)))) * (2.f / 2);
+    int as = 0;
+    uint32_t aph = 0;
+    for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        mbar_wait(&a_raw[as], aph);
+        uint4* pa = reinterpret_cast<uint4*>(a_base + as * kH2ASlot);
+        const uint4* pb = reinterpret_cast<const uint4*>(a2_base + as * kH2ASlot);
+#pragma unroll 4
+        for (int i = ct; i < kH2HaloBytes / 16; i += 32 * kH2CombWarps) {
+          float fa[8], fb[8], fo[8];
+          unpack8<kBf16>(pa[i], fa);
+          unpack8<kBf16>(pb[i], fb);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) fo[k] = fuse2(fa[k], fb[k], w0, w1);
+          pa[i] = pack8<kBf16>(fo);
+        }
+        fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_smem_addr(&a_full[as]));
+        if (++as == kAStg) { as = 0; aph ^= 1; }
       }
     }
   } else {
@@ -336,7 +442,25 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
     const bool prof_warp = leader && ew == 0;
     long long prof_ld = 0, prof_st = 0, prof_wait = 0;
     const long long t_begin = (kH2Prof && p.prof) ? clock64() : 0;
+    // residual rows of the items this CTA reaches kResPrefetchTiles iterations from now -> L2 (conv_common.cuh)
+    auto prefetch_res = [&](int item_f) {
+      if (!kDual && p.res_pf && p.res != nullptr && half == 0 && item_f < p.num_items) {
+        const Item2 f = item2_decode(p, item_f);
+        const unsigned mt = fd_div((unsigned)f.tile, p.fd_nblocks);
+        const int nb = (f.tile - (int)(mt * p.fd_nblocks.div)) * kH2BlockN + f.ncol0;
+        const Sub2 fs = sub2_coord(p, mt * 2 + rank);
+        const int row = q * 32 + lane;
+        const int wo = fs.w0 + (row & 7), ho = fs.h0 + (row >> 3);
+        if (fs.n < p.N && wo < p.W && ho < p.H && nb < p.Cout_store) {
+          const long long pix = (static_cast<long long>(fs.n) * p.H + ho) * p.W + wo;
+          const int cols = p.Cout_store - nb < f.ncols ? p.Cout_store - nb : f.ncols;
+          l2_prefetch_row(reinterpret_cast<const uint8_t*>(p.res) + (pix * p.res_pix_stride + nb) * 2, (unsigned)cols * 2u, p.res_pf);
+        }
+      }
+    };
+    for (int d = 1; d < kResPrefetchTiles; ++d) prefetch_res(cluster_id + d * num_clusters);
     for (int item = cluster_id; item < p.num_items; item += num_clusters, ++tl) {
+      prefetch_res(item + kResPrefetchTiles * num_clusters);
       const Item2 it = item2_decode(p, item);
       const int tile = it.tile;
       const int nchunks = it.ncols >> 5;
@@ -349,7 +473,7 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
       // residual operand of this thread's row: all four column chunks are requested before the accumulator wait, so
       // their global-memory latency hides behind the main loop instead of being paid inside the epilogue
       uint4 rres_all[4][4];
-      if (p.res != nullptr) {
+      if (!kDual && p.res != nullptr) {
         const int row = q * 32 + lane;
         const int wo = sc.w0 + (row & 7), ho = sc.h0 + (row >> 3);
         const bool pix_ok = sc.n < p.N && wo < p.W && ho < p.H;
@@ -373,7 +497,7 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
       }
       tc_fence_after_sync();
 #define DYK_H2EPI(ACT) \
-  halo2_epilogue<kBf16, ACT>(tm, p, sc, nblk * kH2BlockN + it.ncol0, nchunks, t_row, wstage, wvec, sbuf, tempty_leader, q, lane, half, \
+  halo2_epilogue<kBf16, ACT, kDual>(tm, p, sc, nblk * kH2BlockN + it.ncol0, nchunks, t_row, wstage, wvec, sbuf, tempty_leader, q, lane, half, \
                              prof_warp, prof_ld, prof_st, rres_all)
       switch (p.act) {
         case DYK_ACT_LEAKY: DYK_H2EPI(DYK_ACT_LEAKY); break;
@@ -403,36 +527,59 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
   stamp(-1, 13);
 }
 
-template <bool kBf16>
+template <bool kBf16, bool kDual, bool kResB>
 static int launch_halo2(const Halo2Tmaps& tm, const Halo2KArgs& ka, cudaStream_t stream) {
-  auto kern = conv3x3_halo2_kernel<kBf16>;
+  auto kern = conv3x3_halo2_kernel<kBf16, kDual, kResB>;
+  constexpr int kSmem = kResB ? kH2TotalRes : (kDual ? kH2TotalDual : kH2Total);
   static bool configured = false;
   if (!configured) {
-    DYK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kH2Total));
+    DYK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
   int clusters = num_sms() / 2;
   if (ka.num_items < clusters) clusters = ka.num_items;
-  DYK_CUDA_OK(launch_pdl(kern, dim3(2 * clusters), dim3(kH2Threads), (size_t)kH2Total, stream, tm, ka));
+  DYK_CUDA_OK(launch_pdl(kern, dim3(2 * clusters), dim3(kH2Threads + (kDual ? 32 * kH2CombWarps : 0)), (size_t)kSmem, stream, tm, ka));
   DYK_LAUNCH_OK("conv3x3_halo2_kernel");
   return DYK_OK;
 }
 
-// Returns DYK_OK after launching, 1 when the layer is not eligible, < 0 on error.
-int conv3x3_halo2_try(const dyk_conv_params* p, cudaStream_t stream) {
+// Resident-weights variant: 3x3 / stride 1 / pad 1 with one 64-channel K chunk and 64..128 output channels.
+static bool halo2_resident_eligible(const dyk_conv_params* p) {
+  static const bool off = getenv("DYK_HALO2_RES") != nullptr && getenv("DYK_HALO2_RES")[0] == '0';
+  if (off) return false;
+  if (!(p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && !p->upsample2x && !p->out_f32 && !p->y_plane &&
+        p->out_h == 0 && p->out_w == 0 && !p->x2))
+    return false;
+  if (p->Cin > 64 || p->Cin < 16 || p->Cout_store < 64 || p->Cout_store > 128 || p->Cout_store % 32 != 0) return false;
+  const int subs_w = ceil_div(p->W, kH2SubW), subs_h = ceil_div(p->H, kH2SubH);
+  const long long num_subs = (long long)subs_w * subs_h * p->N;
+  if (num_subs >= (1ll << 30) || num_subs < num_sms()) return false;      // at least one tile per SM, or the one-off filter load dominates
+  const double eff = (double)p->W * p->H / ((double)subs_w * kH2SubW * subs_h * kH2SubH);
+  return eff >= 0.6;
+}
+
+bool conv3x3_halo2_eligible(const dyk_conv_params* p) {
   static const bool off = getenv("DYK_HALO2") != nullptr && getenv("DYK_HALO2")[0] == '0';
-  if (off) return 1;
+  if (off) return false;
   if (!(p->kh == 3 && p->kw == 3 && p->stride == 1 && p->pad == 1 && !p->upsample2x && !p->out_f32 && !p->y_plane &&
         p->out_h == 0 && p->out_w == 0))
-    return 1;
-  if (p->Cout_store < 256 || p->Cin < 64) return 1;
+    return false;
+  if (p->Cout_store < 256 || p->Cin < 64) return false;
+  const int subs_w = ceil_div(p->W, kH2SubW), subs_h = ceil_div(p->H, kH2SubH);
+  const long long num_subs = (long long)subs_w * subs_h * p->N;
+  if (num_subs >= (1ll << 30)) return false;
+  const double eff = (double)p->W * p->H / ((double)subs_w * kH2SubW * subs_h * kH2SubH);
+  return eff >= 0.6;
+}
+
+int conv3x3_halo2_try(const dyk_conv_params* p, cudaStream_t stream) {
+  const bool resident = halo2_resident_eligible(p);
+  if (!resident && !conv3x3_halo2_eligible(p)) return 1;
   const int H = p->H, W = p->W, N = p->N;
   const int subs_w = ceil_div(W, kH2SubW), subs_h = ceil_div(H, kH2SubH);
   const long long num_subs = (long long)subs_w * subs_h * N;
-  if (num_subs >= (1ll << 30)) return 1;
-  const double eff = (double)W * H / ((double)subs_w * kH2SubW * subs_h * kH2SubH);
-  if (eff < 0.6) return 1;
   const int n_blocks = ceil_div(p->Cout_store, kH2BlockN);
+  const bool dual = p->x2 != nullptr;
 
   Halo2Tmaps tm;
   Halo2KArgs ka;
@@ -445,6 +592,11 @@ int conv3x3_halo2_try(const dyk_conv_params* p, cudaStream_t stream) {
     const cuuint64_t str[3] = {(cuuint64_t)xs, (cuuint64_t)xs * W, (cuuint64_t)xs * W * H};
     const cuuint32_t box[4] = {64, kH2HaloW, kH2HaloH, 1};
     if ((rc = encode_map_generic(&tm.a, p->x, 4, dims, str, box, 128, "halo2 A"))) return rc;
+    if (dual) {
+      const long long xs2 = p->x2_pix_stride * 2;
+      const cuuint64_t str2[3] = {(cuuint64_t)xs2, (cuuint64_t)xs2 * W, (cuuint64_t)xs2 * W * H};
+      if ((rc = encode_map_generic(&tm.a2, p->x2, 4, dims, str2, box, 128, "halo2 A (second source)"))) return rc;
+    }
   }
   {
     const cuuint64_t dims[3] = {(cuuint64_t)p->Cin, 9, (cuuint64_t)p->Cout};
@@ -471,7 +623,7 @@ int conv3x3_halo2_try(const dyk_conv_params* p, cudaStream_t stream) {
     // layers (256->512 @32x40: 57.3 -> 55.3 us); the real fix for the partial round is a split along K.
     static const int force = getenv("DYK_H2_TAIL") ? atoi(getenv("DYK_H2_TAIL")) : 0;   // 1, 2, 4 force; 0 = cost model
     const int clusters = num_sms() / 2;
-    const int tail = ka.num_tiles % clusters;
+    const int tail = resident ? 0 : ka.num_tiles % clusters;
     int lg = 0;
     if (tail > 0) {
       const double cost[3] = {1.0, 0.9, 1.2};
@@ -487,7 +639,7 @@ int conv3x3_halo2_try(const dyk_conv_params* p, cudaStream_t stream) {
     ka.num_items = ka.full_items + (tail << lg);
     const cuuint64_t dims[3] = {(cuuint64_t)p->Cin, 9, (cuuint64_t)p->Cout};
     const cuuint64_t str[2] = {(cuuint64_t)p->Cin * 2, (cuuint64_t)p->Cin * 2 * 9};
-    const cuuint32_t box[3] = {64, 1, (cuuint32_t)(128 >> lg)};
+    const cuuint32_t box[3] = {64, 1, (cuuint32_t)(resident ? p->Cout_store / 2 : (128 >> lg))};
     if ((rc = encode_map_generic(&tm.bs, p->w, 3, dims, str, box, 128, "halo2 B (split)"))) return rc;
   }
   ka.k_chunks = ceil_div(p->Cin, 64);
@@ -499,7 +651,16 @@ int conv3x3_halo2_try(const dyk_conv_params* p, cudaStream_t stream) {
   ka.scale = p->scale; ka.bias = p->bias;
   ka.res = p->res; ka.res_pix_stride = p->res_pix_stride;
   ka.prof = g_conv_prof;
-  return p->dtype == DYK_BF16 ? launch_halo2<true>(tm, ka, stream) : launch_halo2<false>(tm, ka, stream);
+  ka.res_pf = res_prefetch_mode();
+  ka.x_wts_raw = p->x_wts_raw;
+  ka.k_last_steps = ceil_div(p->Cin - (ka.k_chunks - 1) * 64, 16);
+  if (resident) {
+    ka.res_cols = p->Cout_store;
+    return p->dtype == DYK_BF16 ? launch_halo2<true, false, true>(tm, ka, stream) : launch_halo2<false, false, true>(tm, ka, stream);
+  }
+  if (dual)
+    return p->dtype == DYK_BF16 ? launch_halo2<true, true, false>(tm, ka, stream) : launch_halo2<false, true, false>(tm, ka, stream);
+  return p->dtype == DYK_BF16 ? launch_halo2<true, false, false>(tm, ka, stream) : launch_halo2<false, false, false>(tm, ka, stream);
 }
 
 }  // namespace dyk

@@ -61,6 +61,7 @@ struct ConvKArgs {
   const void* res;                 // may be null
   long long res_pix_stride;
   unsigned long long* prof;        // optional role-cycle counters (dyk_conv_set_profile), may be null
+  int res_pf;                      // residual L2 prefetch mode (conv_common.cuh)
 };
 
 // Role-cycle counters (diagnostics): where the three pipelines of the kernel wait.
@@ -320,6 +321,17 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
   static_assert(BLOCK_K == 64 || BLOCK_K == 32, "BLOCK_K");
 
   griddep_launch_dependents();
+  // profile build: wall-clock (globaltimer, ns) of kernel entry / prologue end / role-loop end / exit, min and max over CTAs
+  // (slots 8..13 of the counter array, as in conv3x3_halo2_kernel)
+  auto stamp = [&](int lo, int hi) {
+    if (kProf && p.prof && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (lo >= 0) atomicMin(p.prof + lo, t);
+      if (hi >= 0) atomicMax(p.prof + hi, t);
+    }
+  };
+  stamp(8, 9);
   extern __shared__ uint8_t smem_raw[];
   // align by *offset* (not by casting through an integer) so the compiler keeps the shared state space
   // and emits LDS/STS instead of generic LD/ST for the staging buffer and the scale/bias vectors
@@ -359,6 +371,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   griddep_wait();   // PDL: everything above overlapped the previous kernel's tail; its results are visible from here on
+  stamp(-1, 10);
 
   if (warp_idx == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -414,8 +427,10 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
       }
     }
   } else if (warp_idx == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer: the whole warp walks the loop and
+    // one elected lane issues each tcgen05 instruction (warp-uniform control flow keeps descriptors / barrier addresses in
+    // uniform registers; a lone thread under `if (lane == 0)` needed ~24 SASS instructions per MMA, see conv_halo2.cu)
+    {
       constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BLOCK_N, kBf16 ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -439,20 +454,23 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
               const uint64_t bdesc = umma_desc_kmajor<kSwz>(sa + S::kABytes);
 #pragma unroll
               const int k0 = (kb % p.k_chunks) * BLOCK_K;
+              const bool el = elect_one();
 #pragma unroll
               for (int k = 0; k < BLOCK_K / 16; ++k) {
                 if (k0 + 16 * k < p.acc_main_k) {
-                  umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, first_m ? 0u : 1u);
+                  if (el) umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, first_m ? 0u : 1u);
                   first_m = false;
                 } else {
-                  umma_f16_ss(d_tmem + BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, first_s ? 0u : 1u);
+                  if (el) umma_f16_ss(d_tmem + BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, first_s ? 0u : 1u);
                   first_s = false;
                 }
               }
-              umma_commit(&empty_bar[stage]);
+              if (el) umma_commit(&empty_bar[stage]);
+              __syncwarp();
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&tfull_bar[as]);
+            if (elect_one()) umma_commit(&tfull_bar[as]);
+            __syncwarp();
           }
           --tl;      // the tile loop's own increment
           continue;
@@ -476,17 +494,20 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
           const uint32_t sa = smem_u32(stage_base + stage * S::kStageBytes);
           const uint64_t adesc = umma_desc_kmajor<kSwz>(sa);
           const uint64_t bdesc = umma_desc_kmajor<kSwz>(sa + S::kABytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address field
-            umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address field
+              umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            if (kb == num_kb - 1) umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
       }
-      if (kProf && p.prof) {
+      if (kProf && p.prof && lane == 0) {
         atomicAdd(p.prof + PROF_MMA_WAIT_FULL, (unsigned long long)t_wfull);
         atomicAdd(p.prof + PROF_MMA_WAIT_TEMPTY, (unsigned long long)t_wtempty);
         atomicAdd(p.prof + PROF_MMA_TOTAL, (unsigned long long)(clock64() - t_begin));
@@ -565,9 +586,26 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
       // per-thread row geometry and the staged scale / bias survive from tile to tile)
       const EpiRow er = epi_row(p, q, lane);
       int staged_nblk = -1;
+      // residual rows of the tiles this CTA reaches kResPrefetchTiles iterations from now -> L2 (conv_common.cuh)
+      auto prefetch_res = [&](int t) {
+        if (p.res_pf && p.res != nullptr && half == 0 && t < p.num_tiles) {
+          const TileCoord f = tile_coord(p, t);
+          const int wo = f.w0 + er.wi, ho = f.h0 + er.hi, nn = f.n0 + er.ni;
+          if (wo < p.Wo && ho < p.Ho && nn < p.N) {
+            const long long pix = (static_cast<long long>(nn) * p.Ho + ho) * p.Wo + wo;
+            const int nb = f.nblk * BLOCK_N;
+            const int cols = p.Cout_store - nb < BLOCK_N ? p.Cout_store - nb : BLOCK_N;
+            l2_prefetch_row(reinterpret_cast<const uint8_t*>(p.res) + (pix * p.res_pix_stride + nb) * 2, (unsigned)cols * 2u, p.res_pf);
+          }
+        }
+      };
+      if (tl == 0) {
+        for (int d = 1; d < kResPrefetchTiles; ++d) prefetch_res(tile + d * (int)gridDim.x);
+      }
       auto tile_loop = [&](auto act_tag) {
         constexpr int kActC = decltype(act_tag)::value;
         for (; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+          prefetch_res(tile + kResPrefetchTiles * (int)gridDim.x);
           const int as = tl & 1;
           const TileCoord tc = tile_coord(p, tile);
           const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
@@ -600,7 +638,9 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
 
   tc_fence_before_sync();
   __syncthreads();
+  stamp(12, 11);
   if (warp_idx == 1) tmem_dealloc<kTmemCols>(tmem_base);
+  stamp(-1, 13);
 }
 
 // ---------------------------------------------------------------------------------------------- host
@@ -636,6 +676,17 @@ static inline int encode_map(CUtensorMap* map, const void* base, int rank, const
 
 int conv3x3_halo_try(const dyk_conv_params* p, cudaStream_t stream);   // conv_halo.cu
 int conv3x3_halo2_try(const dyk_conv_params* p, cudaStream_t stream);  // conv_halo2.cu (CTA pairs)
+bool conv3x3_halo2_eligible(const dyk_conv_params* p);
+
+int res_prefetch_mode() {
+  static const int mode = getenv("DYK_RES_PF") ? atoi(getenv("DYK_RES_PF")) : 0;
+  return mode;
+}
+
+static bool dual_source_ok(const dyk_conv_params* p) {
+  static const bool no_halo = getenv("DYK_NO_HALO") != nullptr && getenv("DYK_NO_HALO")[0] == '1';
+  return !no_halo && p->Cin % 64 == 0 && !p->res && (p->dtype == DYK_F16 || p->dtype == DYK_BF16) && conv3x3_halo2_eligible(p);
+}
 
 // Spatial box (tw, th, tn) with tw*th*tn == 128 that wastes the fewest output pixels.
 static void pick_tile(int Wo, int Ho, int N, int* tw, int* th, int* tn) {
@@ -721,6 +772,10 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv_set_profile(uint6
   return DYK_OK;
 }
 
+extern "C" __attribute__((visibility("default"))) int dyk_conv2d_dual_source_supported(const dyk_conv_params* p) {
+  return (p != nullptr && dual_source_ok(p)) ? 1 : 0;
+}
+
 extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_conv_params* p, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DYK_REQUIRE(p != nullptr, "dyk_conv2d_fwd: null params");
@@ -752,6 +807,14 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   DYK_REQUIRE(!(p->y_plane && (p->res || p->upsample2x || p->out_f32)),
               "dyk_conv2d_fwd: y_plane cannot be combined with residual / upsample2x / out_f32");
 
+  if (p->x2) {
+    DYK_REQUIRE(p->x_wts_raw != nullptr, "dyk_conv2d_fwd: x2 without x_wts_raw");
+    DYK_REQUIRE(p->x2_pix_stride % 8 == 0 && p->x2_pix_stride >= p->Cin && (reinterpret_cast<uintptr_t>(p->x2) & 15) == 0,
+                "dyk_conv2d_fwd: x2 must be 16-byte aligned with stride %% 8 == 0");
+    DYK_REQUIRE(dual_source_ok(p), "dyk_conv2d_fwd: the dual-source input is not available for this layer "
+                "(see dyk_conv2d_dual_source_supported)");
+    return conv3x3_halo2_try(p, stream);
+  }
   // 3x3 stride-1 layers: halo kernel (every input pixel loaded once per tile instead of once per tap)
   static const bool no_halo = getenv("DYK_NO_HALO") != nullptr && getenv("DYK_NO_HALO")[0] == '1';
   if (!no_halo) {
@@ -892,6 +955,7 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   ka.scale = p->scale; ka.bias = p->bias;
   ka.res = p->res; ka.res_pix_stride = p->res_pix_stride;
   ka.prof = g_conv_prof;
+  ka.res_pf = res_prefetch_mode();
 
   const bool bf = p->dtype == DYK_BF16;
   if (acc32) {

@@ -35,7 +35,7 @@ __global__ void fused_add_kernel(const uint8_t* __restrict__ a, long long as, co
     if (wts) {
       // reference order: x = x * w0 (rounded to the tensor dtype), a = a * w1 (rounded), then x + a
 #pragma unroll
-      for (int k = 0; k < 8; ++k) fo[k] = fa[k] * w0 + fb[k] * w1;
+      for (int k = 0; k < 8; ++k) fo[k] = fuse2(fa[k], fb[k], w0, w1);
     } else {
 #pragma unroll
       for (int k = 0; k < 8; ++k) fo[k] = fa[k] + fb[k];
@@ -231,6 +231,36 @@ __global__ void pack_ohwi_kernel(const float* __restrict__ w, void* __restrict__
   }
 }
 
+// Eval-mode BatchNorm folded into per-channel (scale, bias) for every convolution of a model in ONE launch (one block per
+// layer).  descs: device int64 [n][10] = (gamma or 0, beta or 0, running_mean, running_var or 0 when the layer has no BN,
+// conv bias or 0, scale_out or 0, bias_out or 0, C, Cpad, float bits of eps).  Entries C..Cpad of the outputs are zeroed.
+__global__ void __launch_bounds__(256) fold_bn_multi_kernel(const long long* __restrict__ descs) {
+  const long long* d = descs + (long long)blockIdx.x * 10;
+  const float* gamma = reinterpret_cast<const float*>(d[0]);
+  const float* beta = reinterpret_cast<const float*>(d[1]);
+  const float* mean = reinterpret_cast<const float*>(d[2]);
+  const float* var = reinterpret_cast<const float*>(d[3]);
+  const float* cbias = reinterpret_cast<const float*>(d[4]);
+  float* scale_out = reinterpret_cast<float*>(d[5]);
+  float* bias_out = reinterpret_cast<float*>(d[6]);
+  const int C = (int)d[7], Cpad = (int)d[8];
+  const float eps = __int_as_float((int)d[9]);
+  for (int c = threadIdx.x; c < Cpad; c += blockDim.x) {
+    float sc = 0.f, bi = 0.f;
+    if (c < C) {
+      if (var != nullptr) {
+        sc = (gamma ? gamma[c] : 1.f) * __frsqrt_rn(var[c] + eps);
+        bi = (beta ? beta[c] : 0.f) - mean[c] * sc;
+      } else {
+        sc = 1.f;
+        bi = cbias ? cbias[c] : 0.f;
+      }
+    }
+    if (scale_out) scale_out[c] = sc;
+    if (bias_out) bias_out[c] = bi;
+  }
+}
+
 // [N][C][HW] fp32 -> [N][HW][ys] dtype through a 32x32 smem transpose
 template <bool kBf16>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, void* __restrict__ y, long long ys, int C, int HW) {
@@ -402,5 +432,12 @@ extern "C" __attribute__((visibility("default"))) int dyk_nhwc_to_nchw_f32(const
   const dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
   DYK_DISPATCH_DTYPE(dtype, (nhwc_to_nchw_kernel<kBf16><<<grid, block, 0, static_cast<cudaStream_t>(stream_)>>>(x, xs, y, C, HW)));
   DYK_LAUNCH_OK("nhwc_to_nchw_kernel");
+  return DYK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dyk_fold_bn_multi(const int64_t* descs, int32_t n, void* stream_) {
+  DYK_REQUIRE(descs && n > 0, "dyk_fold_bn_multi: bad arguments");
+  fold_bn_multi_kernel<<<n, 256, 0, static_cast<cudaStream_t>(stream_)>>>(reinterpret_cast<const long long*>(descs));
+  DYK_LAUNCH_OK("fold_bn_multi_kernel");
   return DYK_OK;
 }

@@ -67,7 +67,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #else
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 10)) {  // every try_wait sleeps up to 10 ms in HW; this is >> any legitimate wait
+    if (++spins > (1u << 12)) {  // every try_wait sleeps up to 10 ms in HW; this is >> any legitimate wait (also under compute-sanitizer)
       printf("dyk: mbarrier watchdog: block %d thread %d bar %p parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, (void*)bar, parity);
       __trap();
@@ -256,6 +256,14 @@ __device__ __forceinline__ uint32_t leader_smem_addr(const void* p) { return sme
 
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Arrive on a (possibly remote) barrier of the cluster with the default .release.cta semantics — what CUTLASS'
+// ClusterBarrier::arrive(cta_id) emits.  The .release.cluster form above compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR,
+// which waits for every outstanding global access of the thread (~1000+ cycles; 15 % of all warp-stall samples of the
+// pair kernel on short tiles, ncu).  Handing a TMEM accumulator back needs no memory ordering at all: the TMEM reads are
+// complete (tcgen05.wait::ld) and ordered by tcgen05.fence::before_thread_sync.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads issued by either CTA of a pair; the transaction bytes are credited to the LEADER CTA's mbarrier
 __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1,

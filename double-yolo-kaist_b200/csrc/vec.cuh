@@ -35,6 +35,10 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// WeightedFeatureFusion arithmetic (build_utils/layers.py:82-84: x * w[0] + a * w[1]) with one fixed evaluation order, so
+// that the stand-alone kernel and the convolution that forms the sum while staging its operand give the same bits.
+__device__ __forceinline__ float fuse2(float x, float a, float w0, float w1) { return __fmaf_rn(x, w0, __fmul_rn(a, w1)); }
+
 template <bool kBf16>
 __device__ __forceinline__ float load1(const void* p, long long idx) {
   if constexpr (kBf16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[idx]);

@@ -36,6 +36,7 @@ class ConvParams(C.Structure):
         ("kh", _i32), ("kw", _i32), ("stride", _i32), ("pad", _i32),
         ("act", _i32), ("dtype", _i32), ("upsample2x", _i32), ("out_f32", _i32),
         ("out_h", _i32), ("out_w", _i32), ("y_plane", _i32),
+        ("x2", _vp), ("x2_pix_stride", _i64), ("x_wts_raw", _vp),
     ]
 
 
@@ -45,6 +46,7 @@ SIGNATURES = {
     "dyk_last_error": (C.c_char_p, []),
     "dyk_check_device": (_i32, []),
     "dyk_conv2d_fwd": (_i32, [C.POINTER(ConvParams), _vp]),
+    "dyk_conv2d_dual_source_supported": (_i32, [C.POINTER(ConvParams)]),
     "dyk_conv_set_profile": (_i32, [_vp]),
     "dyk_conv2d_stem_nchw_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64] + [_i32] * 11 + [_vp]),
     "dyk_dwconv2d_fwd": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
@@ -101,6 +103,7 @@ SIGNATURES = {
     "dyk_yolo_loss_scale_grad": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "dyk_frames_to_im2col32": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_pack_weights_multi": (_i32, [_vp, _i32, _i32, _i32, _vp]),
+    "dyk_fold_bn_multi": (_i32, [_vp, _i32, _vp]),
     "dyk_pack_weights_ohwi": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dyk_optim_block_elems": (_i32, []),
     "dyk_optim_sgd_multi": (_i32, [_vp, _i32, _i64, _f32, _f32, _f32, _f32, _i32, _i32, _vp, _vp, _vp]),

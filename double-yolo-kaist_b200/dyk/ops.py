@@ -99,19 +99,83 @@ def fold_bn(conv, bn):
     return None, None
 
 
+def fold_bn_alloc(conv, bn, mult: int = 256):
+    """Uninitialised (scale, bias) buffers of the shapes fold_bn returns; filled by fold_bn_multi."""
+    dev = conv.weight.device
+    npad = (conv.out_channels + mult - 1) // mult * mult
+    if bn is not None:
+        return (torch.empty(npad, dtype=torch.float32, device=dev), torch.empty(npad, dtype=torch.float32, device=dev))
+    if conv.bias is not None:
+        return None, torch.empty(npad, dtype=torch.float32, device=dev)
+    return None, None
+
+
+def _f32c(t, what):
+    if t is None:
+        return 0
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise nat.NativeError(f"{what} must be a contiguous float32 tensor")
+    return t.data_ptr()
+
+
+def fold_bn_multi(items) -> None:
+    """items: (conv, bn, scale_out, bias_out) — fold_bn for all of them in one launch (dyk_fold_bn_multi)."""
+    import struct
+    rows = []
+    for conv, bn, scale, bias in items:
+        if scale is None and bias is None:
+            continue
+        Cc = conv.out_channels
+        npad = (bias if bias is not None else scale).numel()
+        if bn is not None:
+            eps = struct.unpack("<i", struct.pack("<f", float(bn.eps)))[0]
+            rows.append([_f32c(bn.weight, "BatchNorm weight"), _f32c(bn.bias, "BatchNorm bias"),
+                         _f32c(bn.running_mean, "running_mean"), _f32c(bn.running_var, "running_var"), 0,
+                         scale.data_ptr(), bias.data_ptr(), Cc, npad, eps])
+        else:
+            rows.append([0, 0, 0, 0, _f32c(conv.bias, "conv bias"), 0, bias.data_ptr(), Cc, npad, 0])
+    if not rows:
+        return
+    dev = items[0][0].weight.device
+    desc = torch.tensor(rows, dtype=torch.int64).to(dev)
+    nat.call("dyk_fold_bn_multi", _p(desc), len(rows), _stream())
+    nat.count_launches()
+
+
+def pack_conv_weights_multi(items, dtype) -> None:
+    """items: (weight OIHW fp32 parameter, packed [O][k][k][I] buffer) — all re-laid out by one dyk_pack_weights_multi."""
+    rows, tiles = [], 0
+    for w, out in items:
+        O, I, kh, kw = w.shape
+        if kh * kw > 9:
+            raise nat.NativeError("pack_conv_weights_multi: kernels larger than 3x3 are packed one by one")
+        rows.append([_f32c(w, "convolution weight"), out.data_ptr(), 0, O, I, kh * kw, 0, tiles])
+        tiles += ((O + 31) // 32) * ((I + 31) // 32)
+    if not rows:
+        return
+    desc = torch.tensor(rows, dtype=torch.int64).to(items[0][0].device)
+    nat.call("dyk_pack_weights_multi", _p(desc), len(rows), tiles, _DT[dtype], _stream())
+    nat.count_launches()
+
+
 # ------------------------------------------------------------------------------------------ NHWC launches
-def nhwc_conv(x: View, w_packed: torch.Tensor, scale, bias, y: View, *, k, stride, pad, act, res: View = None,
-              upsample2x=False, out_f32=False, cout=None) -> None:
+def _conv_params(x: View, w_packed, scale, bias, y: View, *, k, stride, pad, act, res: View = None, upsample2x=False,
+                 out_f32=False, cout=None, x2: View = None, x_wts_raw=None):
     p = nat.ConvParams()
     p.x, p.x_pix_stride = x.ptr, x.stride
-    p.w = w_packed.data_ptr()
+    p.w = None if w_packed is None else w_packed.data_ptr()
     p.scale = None if scale is None else scale.data_ptr()
     p.bias = None if bias is None else bias.data_ptr()
     p.y, p.y_pix_stride = y.ptr, y.stride
     if res is not None:
         p.res, p.res_pix_stride = res.ptr, res.stride
+    if x2 is not None:
+        if (x2.N, x2.H, x2.W, x2.C, x2.dt) != (x.N, x.H, x.W, x.C, x.dt):
+            raise ValueError("dual-source convolution: the two inputs must have the same shape and dtype")
+        p.x2, p.x2_pix_stride = x2.ptr, x2.stride
+        p.x_wts_raw = x_wts_raw.data_ptr()
     p.N, p.H, p.W, p.Cin = x.N, x.H, x.W, x.C
-    p.Cout = w_packed.shape[0] if cout is None else cout
+    p.Cout = (w_packed.shape[0] if cout is None else cout)
     p.Cout_store = y.C
     p.kh = p.kw = k
     p.stride, p.pad = stride, pad
@@ -119,8 +183,28 @@ def nhwc_conv(x: View, w_packed: torch.Tensor, scale, bias, y: View, *, k, strid
     p.dtype = x.dt
     p.upsample2x = int(upsample2x)
     p.out_f32 = int(out_f32)
+    return p
+
+
+def nhwc_conv(x: View, w_packed: torch.Tensor, scale, bias, y: View, *, k, stride, pad, act, res: View = None,
+              upsample2x=False, out_f32=False, cout=None, x2: View = None, x_wts_raw=None) -> None:
+    """x2 / x_wts_raw: the convolution's input is sigmoid(w)[0] * x + sigmoid(w)[1] * x2 (WeightedFeatureFusion fused into
+    its consumer, build_utils/layers.py:63-85); see conv_dual_source_supported."""
+    p = _conv_params(x, w_packed, scale, bias, y, k=k, stride=stride, pad=pad, act=act, res=res, upsample2x=upsample2x,
+                     out_f32=out_f32, cout=cout, x2=x2, x_wts_raw=x_wts_raw)
     nat.call("dyk_conv2d_fwd", C.byref(p), _stream())
     nat.count_launches()
+
+
+def conv_dual_source_supported(N, H, W, Cin, cout, cout_store, dtype, *, k, stride, pad, upsample2x=False, out_f32=False) -> bool:
+    """dyk_conv2d_dual_source_supported for a layer shape (no tensors needed)."""
+    p = nat.ConvParams()
+    p.N, p.H, p.W, p.Cin, p.Cout, p.Cout_store = N, H, W, Cin, cout, cout_store
+    p.kh = p.kw = k
+    p.stride, p.pad = stride, pad
+    p.dtype = _DT[dtype]
+    p.upsample2x, p.out_f32 = int(upsample2x), int(out_f32)
+    return bool(nat.load().dyk_conv2d_dual_source_supported(C.byref(p)))
 
 
 def nhwc_stem(x_nchw: torch.Tensor, w_f32_ohwi, scale, bias, y: View, *, k, stride, pad, act) -> None:

@@ -32,7 +32,7 @@ from .ops import View
 
 class Value:
     """One logical activation tensor (N, H, W, C) produced by one op."""
-    __slots__ = ("C", "H", "W", "uses", "ext", "f32", "place", "view", "kind", "first", "last", "name")
+    __slots__ = ("C", "H", "W", "uses", "ext", "f32", "place", "view", "kind", "first", "last", "name", "virtual")
 
     def __init__(self, C_, H, W, kind, name="", ext=False, f32=False):
         self.C, self.H, self.W = C_, H, W
@@ -45,6 +45,7 @@ class Value:
         self.first = None
         self.last = None
         self.name = name
+        self.virtual = False   # never materialised: formed (and rounded to the storage type) inside its consumer
 
 
 class Op:
@@ -63,6 +64,8 @@ class ConvOp(Op):
         self.upsample2x = False
         self.out_f32 = False
         self.tag = tag
+        self.src2 = None        # dual-source input: src = w0 * src + w1 * src2 (fused WeightedFeatureFusion)
+        self.fusion = None      # ... and the module that owns the raw weights
 
     @property
     def flavor(self):
@@ -75,7 +78,7 @@ class ConvOp(Op):
                               f"({c.in_channels}->{c.out_channels}) has no native kernel")
 
     def inputs(self):
-        return [self.src] + ([self.res] if self.res is not None else [])
+        return [self.src] + ([self.src2] if self.src2 is not None else []) + ([self.res] if self.res is not None else [])
 
 
 class AddOp(Op):
@@ -268,6 +271,39 @@ def fuse(ops_):
     return out
 
 
+def fuse_weighted_adds(ops_, B, dtype):
+    """Weighted [shortcut] (the modality fusion `x * w[0] + a * w[1]`, build_utils/layers.py:63-85) whose only consumer is
+    a convolution with a dual-source operand path (dyk_conv2d_dual_source_supported): the sum is formed inside that
+    convolution while its operand is staged, so the add launch, the write of the sum and its re-read all disappear."""
+    if os.environ.get("DYK_FUSE_ADD", "1") == "0":
+        return ops_
+    consumers = {}
+    for op in ops_:
+        for v in op.inputs():
+            consumers.setdefault(id(v), []).append(op)
+    drop = set()
+    for op in ops_:
+        if not (isinstance(op, AddOp) and op.module.weight and len(op.others) == 1):
+            continue
+        a, b, out = op.x, op.others[0], op.out
+        cons = consumers.get(id(out), [])
+        if len(cons) != 1 or out.uses != 1 or a.ext or b.ext or a.f32 or b.f32:
+            continue
+        c = cons[0]
+        if not (isinstance(c, ConvOp) and c.flavor == "dense" and c.src is out and c.res is None and c.src2 is None):
+            continue
+        if (a.C, a.H, a.W) != (b.C, b.H, b.W) or a.C != out.C:
+            continue
+        k, s, p = c.conv.kernel_size[0], c.conv.stride[0], c.conv.padding[0]
+        if not ops.conv_dual_source_supported(B, a.H, a.W, a.C, c.conv.out_channels, c.out.C, dtype, k=k, stride=s, pad=p,
+                                              upsample2x=c.upsample2x, out_f32=c.out_f32):
+            continue
+        c.src, c.src2, c.fusion = a, b, op.module
+        out.virtual = True
+        drop.add(id(op))
+    return [op for op in ops_ if id(op) not in drop]
+
+
 def cascade_pools(ops_):
     """SPP (models.py:91-94): the 5x5, 9x9 and 13x13 stride-1 max pools of one tensor.  Max pooling with -inf padding
     composes — mp5(mp5(x)) = mp9(x), mp5(mp9(x)) = mp13(x), bit for bit — so the larger windows are computed from the
@@ -379,6 +415,7 @@ class WeightBank:
 
     def __init__(self):
         self.entries = {}     # (id(conv), dtype, flavor) -> dict
+        self.pending = []     # entries allocated by get() and not yet filled
         self.signature = None
 
     @staticmethod
@@ -386,36 +423,70 @@ class WeightBank:
         return tuple(t._version for t in tensors)
 
     def get(self, conv, bn, dtype, flavor):
+        """Entry with its device buffers allocated; the contents are written by the next flush()."""
         key = (id(conv), dtype, flavor)
         e = self.entries.get(key)
         if e is None:
             e = {"conv": conv, "bn": bn, "dtype": dtype, "flavor": flavor}
-            self._fill(e, first=True)
+            k = conv.kernel_size[0]
+            dev = conv.weight.device
+            wt = conv.weight
+            if flavor == "dense" and dtype != torch.float32 and k * k <= 9 and wt.dtype == torch.float32 and wt.is_contiguous():
+                e["w"] = torch.empty((conv.out_channels, k, k, conv.in_channels), dtype=dtype, device=dev)
+                e["multi"] = True
+            else:
+                e["w"] = self._pack_single(e)
+                e["multi"] = False
+            e["scale"], e["bias"] = ops.fold_bn_alloc(conv, bn)
             self.entries[key] = e
+            self.pending.append(e)
         return e
 
-    def _fill(self, e, first):
-        conv, bn, dtype, flavor = e["conv"], e["bn"], e["dtype"], e["flavor"]
+    @staticmethod
+    def _pack_single(e):
+        conv, dtype, flavor = e["conv"], e["dtype"], e["flavor"]
         k = conv.kernel_size[0]
         if flavor == "dense":
-            w = ops.f32_pack_conv_weight(conv.weight) if dtype == torch.float32 else ops.pack_conv_weight(conv.weight, dtype)
-        elif flavor == "stem":
-            w = conv.weight.detach().float().permute(0, 2, 3, 1).contiguous()
-        else:  # depthwise: [k][k][C] fp32
-            w = conv.weight.detach().float().reshape(conv.out_channels, k, k).permute(1, 2, 0).contiguous()
-        scale, bias = ops.fold_bn(conv, bn)
-        if first:
-            e["w"], e["scale"], e["bias"] = w, scale, bias
-        else:  # keep device addresses stable: captured graphs hold them
-            e["w"].copy_(w)
-            if scale is not None:
-                e["scale"].copy_(scale)
-            if bias is not None:
-                e["bias"].copy_(bias)
+            return ops.f32_pack_conv_weight(conv.weight) if dtype == torch.float32 else ops.pack_conv_weight(conv.weight, dtype)
+        if flavor == "stem":
+            return conv.weight.detach().float().permute(0, 2, 3, 1).contiguous()
+        # depthwise: [k][k][C] fp32
+        return conv.weight.detach().float().reshape(conv.out_channels, k, k).permute(1, 2, 0).contiguous()
+
+    def _fill(self, entries, first):
+        """Two native launches for the whole list: every dense 16-bit weight re-laid out (dyk_pack_weights_multi) and
+        every BatchNorm folded (dyk_fold_bn_multi); the few stem / depthwise / fp32-mode weights are permuted one by one.
+        Device addresses never change: captured graphs hold them."""
+        by_dtype = {}
+        for e in entries:
+            if e["multi"]:
+                by_dtype.setdefault(e["dtype"], []).append((e["conv"].weight.detach(), e["w"]))
+            elif not first:
+                e["w"].copy_(self._pack_single(e))
+        for dtype, items in by_dtype.items():
+            ops.pack_conv_weights_multi(items, dtype)
+        native = []
+        for e in entries:
+            conv, bn = e["conv"], e["bn"]
+            ts = [bn.weight, bn.bias, bn.running_mean, bn.running_var] if bn is not None else [conv.bias]
+            if all(t is None or (t.dtype == torch.float32 and t.is_contiguous()) for t in ts):
+                native.append((conv, bn, e["scale"], e["bias"]))
+            else:                                   # .half() models: fold with torch ops in fp32
+                scale, bias = ops.fold_bn(conv, bn)
+                if scale is not None:
+                    e["scale"].copy_(scale)
+                if bias is not None:
+                    e["bias"].copy_(bias)
+        ops.fold_bn_multi(native)
+
+    def flush(self):
+        if self.pending:
+            self._fill(self.pending, first=True)
+            self.pending = []
 
     def refresh(self):
-        for e in self.entries.values():
-            self._fill(e, first=False)
+        self.pending = []
+        self._fill(list(self.entries.values()), first=False)
 
 
 class Plan:
@@ -426,7 +497,7 @@ class Plan:
         # fp32-accurate mode (compute_dtype = torch.float32, csrc/f32_path.cu): fp32 buffers, split-bf16 tensor-core convs,
         # no residual / upsample fusion into the conv epilogue (its fp32 store path is the plain one), one lane
         self.f32 = dtype == torch.float32
-        self.ops = raw if self.f32 else fuse(raw)
+        self.ops = raw if self.f32 else fuse_weighted_adds(fuse(raw), B, dtype)
         cascade_pools(self.ops)
         mark_heads(self.ops)
         place_concats(self.ops)
@@ -437,6 +508,7 @@ class Plan:
             self.lanes = [min(l, 0) for l in self.lanes]
         self._allocate()
         self._bind(model, bank)
+        bank.flush()
         self.graph = None
         self.graph_failed = False
 
@@ -573,6 +645,8 @@ class Plan:
                 elif fl == "dense":
                     kw = dict(k=k, stride=s, pad=p, act=op.act, res=op.res.view if op.res is not None else None,
                               upsample2x=op.upsample2x, out_f32=op.out_f32)
+                    if op.src2 is not None:
+                        kw.update(x2=op.src2.view, x_wts_raw=op.fusion.w)
                     self.steps.append(_ConvStep(op.src.view, e, op.out.view, kw))
                 else:
                     self.steps.append(_Call(ops.nhwc_dwconv, op.src.view, e["w"], e["scale"], e["bias"], op.out.view,

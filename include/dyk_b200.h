@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DYK_ABI_VERSION 4
+#define DYK_ABI_VERSION 5
 
 enum { DYK_F16 = 0, DYK_BF16 = 1 };
 
@@ -83,8 +83,21 @@ typedef struct dyk_conv_params {
                              "pad only at the bottom / right", which the strided-conv data gradient needs          */
   int32_t y_plane;        /* 1 + (row parity*2 + col parity): y is that parity plane of a tensor of size
                              (2*out_h, 2*out_w) and pixel stride y_pix_stride (0 = dense output)                   */
+  /* ---- ABI v5 additions (zero = previous behaviour): dual-source input ----
+   * WeightedFeatureFusion (build_utils/layers.py:63-85, the modality-fusion add `x * w[0] + a * w[1]` with
+   * w = sigmoid(self.w) * (2 / n), n = 2) fused into the convolution that consumes it: the input of the convolution is
+   *   w0 * x + w1 * x2   (rounded once to the storage type, exactly what dyk_fused_add would have stored)
+   * formed in shared memory while the operand is staged, so neither modality tensor is read twice and the sum is never
+   * written.  x2 has the geometry of x; x_wts_raw points to the module's raw parameter `w` (2 floats, device memory).
+   * Available where dyk_conv2d_dual_source_supported() says so; dyk_conv2d_fwd fails with DYK_EINVAL elsewhere.   */
+  const void* x2;
+  int64_t x2_pix_stride;
+  const float* x_wts_raw;
 } dyk_conv_params;
 int dyk_conv2d_fwd(const dyk_conv_params* p, void* stream);
+/* 1 when dyk_conv2d_fwd accepts x2 != NULL for this layer (3x3, stride 1, pad 1, >= 256 output channels, Cin % 64 == 0:
+ * the CTA-pair halo kernel), else 0.  Only the shape / flag fields of p are read. */
+int dyk_conv2d_dual_source_supported(const dyk_conv_params* p);
 
 /* Diagnostics (no reference counterpart): when dev_counters != NULL, every later dyk_conv2d_fwd launch adds
  * its role-cycle counters into dev_counters[0..7] (device memory, 8 x uint64, caller zeroes them):
@@ -359,6 +372,12 @@ int dyk_yolo_loss_scale_grad(const float* dp, float* out, int64_t n, int32_t no,
  */
 int dyk_pack_weights_ohwi(const float* w_oihw, void* w_packed, int32_t O, int32_t I, int32_t kh, int32_t kw,
                           int32_t dtype, void* stream);
+/* eval-mode nn.BatchNorm2d folded into the convolution epilogue's per-channel (scale, bias) (models.py:44-47: the
+ * reference runs conv -> BatchNorm2d -> activation as three library calls), for every layer of a model in one launch:
+ * scale = gamma * rsqrt(running_var + eps), bias = beta - running_mean * scale; a layer without BN gets its conv bias.
+ * descs: DEVICE int64 [n][10] = (gamma or 0, beta or 0, running_mean, running_var or 0 = no BN, conv bias or 0,
+ * scale_out or 0, bias_out or 0, C, Cpad, float bits of eps); outputs are Cpad floats, zero beyond C. */
+int dyk_fold_bn_multi(const int64_t* descs, int32_t n, void* stream);
 int dyk_nchw_f32_to_nhwc(const float* x, void* y, int64_t y_pix_stride, int32_t N, int32_t C, int32_t H,
                          int32_t W, int32_t dtype, void* stream);
 int dyk_nhwc_to_nchw_f32(const void* x, int64_t x_pix_stride, float* y, int32_t N, int32_t C, int32_t H,

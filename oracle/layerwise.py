@@ -22,8 +22,8 @@ def native_layers(model):
     for i, v in enumerate(plan.layer_vals):
         if v is None or v.ext:
             continue
-        if v.view is None or v.f32:
-            unrounded.add(i)
+        if (v.view is None and not getattr(v, "virtual", False)) or v.f32:
+            unrounded.add(i)      # (a `virtual` value is formed inside its consumer but IS rounded to the storage type there)
         if v.view is None:
             continue
         vw = v.view

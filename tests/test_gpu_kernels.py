@@ -61,6 +61,11 @@ CONV_CASES = [
     (2, 2048, 8, 10, 512, 1, 1, "leaky", False, False, True),
     (1, 8, 64, 80, 32, 3, 1, "mish", False, False, True),
     (2, 64, 12, 12, 64, 5, 1, "relu", False, False, True),
+    # early high-resolution 3x3 layers: CTA-pair kernel with the whole filter resident in shared memory
+    (4, 32, 64, 80, 64, 3, 1, "leaky", True, False, True),
+    (2, 64, 96, 80, 128, 3, 1, "mish", True, False, True),
+    (3, 48, 70, 83, 96, 3, 1, "leaky", False, False, True),     # ragged tiles, 3 K steps, 96 output channels
+    (5, 16, 50, 64, 64, 3, 1, "relu", False, False, True),
 ]
 
 
@@ -215,3 +220,73 @@ def test_yolo_decode(v4):
     layer.train()
     assert torch.equal(layer(p).cpu(), p_ref)
     assert (layer.nx, layer.ny) == (10, 8)
+
+
+def test_batched_weight_bind_matches_per_layer_ops():
+    """dyk_fold_bn_multi / dyk_pack_weights_multi (one launch per model at bind time) against the per-layer torch fold
+    of eval-mode BatchNorm2d (models.py:44-47) and the per-layer re-layout: scale / bias to 2 ulp, weights bit-equal."""
+    from dyk import ops
+    torch.manual_seed(5)
+    layers = []
+    for cin, cout, k, has_bn in ((16, 24, 3, True), (24, 18, 1, False), (40, 300, 3, True), (8, 8, 1, True)):
+        conv = nn.Conv2d(cin, cout, k, bias=not has_bn).to(DEV)
+        bn = nn.BatchNorm2d(cout, eps=1e-4).to(DEV) if has_bn else None
+        if bn is not None:
+            bn.weight.data.uniform_(0.5, 2.0); bn.bias.data.normal_()
+            bn.running_mean.normal_(); bn.running_var.uniform_(0.01, 3.0)
+        layers.append((conv, bn))
+    outs = [ops.fold_bn_alloc(c, b) for c, b in layers]
+    ops.fold_bn_multi([(c, b, s, t) for (c, b), (s, t) in zip(layers, outs)])
+    for (c, b), (s, t) in zip(layers, outs):
+        ws, wt = ops.fold_bn(c, b)
+        assert (s is None) == (ws is None)
+        if s is not None:
+            torch.testing.assert_close(s, ws, rtol=3e-7, atol=0)
+        torch.testing.assert_close(t, wt, rtol=3e-7, atol=1e-7)
+    for dtype in (torch.float16, torch.bfloat16):
+        bufs = [torch.empty((c.out_channels, c.kernel_size[0], c.kernel_size[0], c.in_channels), dtype=dtype, device=DEV)
+                for c, _ in layers]
+        ops.pack_conv_weights_multi([(c.weight.detach(), o) for (c, _), o in zip(layers, bufs)], dtype)
+        for (c, _), o in zip(layers, bufs):
+            assert torch.equal(o, ops.pack_conv_weight(c.weight, dtype))
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 256, 16, 24, 256), (3, 128, 30, 41, 512), (1, 512, 16, 20, 320)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_weighted_fusion_fused_into_consumer_conv(shape, dtype):
+    """WeightedFeatureFusion (layers.py:63-85) formed inside the consuming 3x3 convolution (dual-source operand of the
+    CTA-pair halo kernel): bit-identical to the stand-alone add kernel followed by the same convolution, and within
+    storage precision of conv(x * w0 + a * w1) in fp32."""
+    from dyk import ops
+    from dyk.ops import View
+    N, Cin, H, W, Cout = shape
+    g = torch.Generator().manual_seed(Cin + Cout)
+    assert ops.conv_dual_source_supported(N, H, W, Cin, Cout, Cout, dtype, k=3, stride=1, pad=1)
+    assert not ops.conv_dual_source_supported(N, H, W, Cin, Cout, Cout, dtype, k=3, stride=2, pad=1)
+    assert not ops.conv_dual_source_supported(N, H, W, Cin, 64, 64, dtype, k=3, stride=1, pad=1)
+    x = _q(torch.randn((N, Cin, H, W), generator=g), dtype).to(DEV)
+    a = _q(torch.randn((N, Cin, H, W), generator=g), dtype).to(DEV)
+    w_raw = torch.tensor([0.4, -1.1], device=DEV)
+    weight = _q(torch.randn((Cout, Cin, 3, 3), generator=g) / (Cin * 9) ** 0.5, dtype).to(DEV)
+    scale = torch.rand(1024, generator=g).to(DEV) + 0.5
+    bias = torch.randn(1024, generator=g).to(DEV) * 0.1
+    xv, av = ops.to_nhwc(x, dtype), ops.to_nhwc(a, dtype)
+    wp = ops.pack_conv_weight(weight, dtype)
+    # fused
+    y1 = ops.new_view(N, H, W, Cout, dtype, DEV)
+    ops.nhwc_conv(xv, wp, scale, bias, y1, k=3, stride=1, pad=1, act="leaky", x2=av, x_wts_raw=w_raw)
+    # stand-alone add, then the same convolution
+    wall = torch.empty(2, dtype=torch.float32, device=DEV)
+    ops.fusion_weights(w_raw, wall)
+    s = ops.new_view(N, H, W, Cin, dtype, DEV)
+    ops.nhwc_add(xv, av, s, wall)
+    y2 = ops.new_view(N, H, W, Cout, dtype, DEV)
+    ops.nhwc_conv(s, wp, scale, bias, y2, k=3, stride=1, pad=1, act="leaky")
+    torch.cuda.synchronize()
+    assert torch.equal(y1.buf, y2.buf), "fused and stand-alone weighted fusion differ"
+    ww = torch.sigmoid(w_raw)
+    want = F.leaky_relu(F.conv2d((x * ww[0] + a * ww[1]).to(dtype).float(), weight, padding=1)
+                        * scale[:Cout].view(1, -1, 1, 1) + bias[:Cout].view(1, -1, 1, 1), 0.1)
+    eps = 2e-3 if dtype == torch.float16 else 1.6e-2
+    _close(ops.to_nchw(y1), want, rtol=eps, atol=eps, what=f"dual-source conv {shape} {dtype}")

@@ -67,7 +67,7 @@ for i in sel:
     by = 2.0 * (N * H * W * Cin + N * Ho * Wo * Cout * (2 if res else 1) + Cout * Cin * k * k)
     role = ""
     if PROFILE:
-        prof = torch.zeros(8, dtype=torch.int64, device="cuda")
+        prof = torch.zeros(16, dtype=torch.int64, device="cuda"); prof[8] = 1 << 62; prof[12] = 1 << 62   # 8..13: globaltimer stamps
         nat.call("dyk_conv_set_profile", C.c_void_p(prof.data_ptr()))
         ops.nhwc_conv(x, w, scale, bias, y, k=k, stride=s, pad=pad, act=act, res=r)
         torch.cuda.synchronize()

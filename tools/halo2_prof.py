@@ -9,7 +9,7 @@ import torch
 from dyk import ops, _native as nat
 from dyk.ops import View
 dt = torch.float16
-for (N, Cin, H, W, Cout, res) in [(16, 128, 64, 80, 256, True), (16, 256, 32, 40, 512, True), (16, 512, 16, 20, 1024, True),
+for (N, Cin, H, W, Cout, res) in [(16, 32, 256, 320, 64, True), (16, 32, 256, 320, 64, False), (16, 64, 128, 160, 128, True), (16, 128, 64, 80, 256, True), (16, 256, 32, 40, 512, True), (16, 512, 16, 20, 1024, True),
                                   (16, 512, 32, 40, 512, False), (16, 256, 32, 40, 512, False)]:
     x = View(torch.randn((N, H, W, Cin), device="cuda").to(dt), 0, Cin)
     y = View(torch.empty((N, H, W, Cout), device="cuda", dtype=dt), 0, Cout)
@@ -27,6 +27,7 @@ for (N, Cin, H, W, Cout, res) in [(16, 128, 64, 80, 256, True), (16, 256, 32, 40
     p = prof.tolist(); n = max(p[7], 1)
     subs = ((W + 7) // 8) * ((H + 15) // 16) * N
     tiles = (subs + 1) // 2 * ((Cout + 255) // 256)
+    n = min(n, 74) if n > 74 else n
     tpc = tiles / n
     print(f"{Cin}->{Cout} {H}x{W} res={int(res)}: {a.elapsed_time(b) * 1e3:7.1f} us  clusters {n} tiles/cluster {tpc:.2f} | MMA loop {p[2] / n:8.0f} cyc "
           f"(wait data {p[0] / max(p[2], 1):4.0%}, wait acc {p[1] / max(p[2], 1):4.0%}) | epilogue total {p[4] / n:8.0f} cyc: wait acc {p[3] / max(p[4], 1):4.0%}, "
