@@ -102,7 +102,7 @@ __device__ __forceinline__ SubCoord sub_coord(const HaloKArgs& p, unsigned sub) 
 template <int BLOCK_N, int kSub, bool kBf16, int kAct>
 __device__ __forceinline__ void halo_epilogue(const HaloTmaps& tm, const HaloKArgs& p, const SubCoord& sc, int n_base,
                                               uint32_t t_row, uint8_t* wstage, float* wvec, int& sbuf,
-                                              uint64_t* tempty, int q, int lane, int c_begin, int c_step) {
+                                              uint64_t* tempty, int q, int lane, int c_begin, int c_step, int& staged_base) {
   constexpr int kCols = 32;
   constexpr int kChunks = BLOCK_N / kCols;
   const int row = q * 32 + lane;
@@ -122,15 +122,18 @@ __device__ __forceinline__ void halo_epilogue(const HaloTmaps& tm, const HaloKAr
       if (pix_ok && c0 + j * 8 < p.Cout_store) rres[j] = __ldg(reinterpret_cast<const uint4*>(rp) + j);
     }
   };
-  // scale / bias of the whole n-block -> warp-private shared memory
-  __syncwarp();
+  // scale / bias of the whole n-block -> warp-private shared memory (only when the channel block changes)
+  if (n_base != staged_base) {
+    staged_base = n_base;
+    __syncwarp();
 #pragma unroll
-  for (int j = 0; j < BLOCK_N / 32; ++j) {
-    const int col = n_base + j * 32 + lane;
-    wvec[j * 32 + lane] = p.scale ? __ldg(p.scale + col) : 1.f;
-    wvec[BLOCK_N + j * 32 + lane] = p.bias ? __ldg(p.bias + col) : 0.f;
+    for (int j = 0; j < BLOCK_N / 32; ++j) {
+      const int col = n_base + j * 32 + lane;
+      wvec[j * 32 + lane] = p.scale ? __ldg(p.scale + col) : 1.f;
+      wvec[BLOCK_N + j * 32 + lane] = p.bias ? __ldg(p.bias + col) : 0.f;
+    }
+    __syncwarp();
   }
-  __syncwarp();
 
 #pragma unroll 1
   for (int c = c_begin; c < kChunks; c += c_step) {
@@ -243,8 +246,8 @@ conv3x3_halo_kernel(const __grid_constant__ HaloTmaps tm, const HaloKArgs p) {
   griddep_wait();   // PDL: everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp_idx == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
+    {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       long long t_wait = 0;
@@ -258,20 +261,26 @@ conv3x3_halo_kernel(const __grid_constant__ HaloTmaps tm, const HaloKArgs p) {
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           { const long long t0 = HPROF_T0(); mbar_wait(&a_empty[as], aph ^ 1); HPROF_ADD(t_wait, t0); }
           uint8_t* sa = a_base + as * S::kASlot;
-          mbar_arrive_expect_tx(&a_full[as], kSub * kHaloRows * 128);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&a_full[as], kSub * kHaloRows * 128);
 #pragma unroll
-          for (int j = 0; j < kSub; ++j)
-            tma_load_4d(sa + j * kSubBytes, &tm.a, &a_full[as], kc * 64, sc[j].w0 - 1, sc[j].h0 - 1, sc[j].n);
+            for (int j = 0; j < kSub; ++j)
+              tma_load_4d(sa + j * kSubBytes, &tm.a, &a_full[as], kc * 64, sc[j].w0 - 1, sc[j].h0 - 1, sc[j].n);
+          }
+          __syncwarp();
           if (++as == kAStages) { as = 0; aph ^= 1; }
           for (int tap = 0; tap < 9; ++tap) {
             { const long long t0 = HPROF_T0(); mbar_wait(&b_empty[bs], bph ^ 1); HPROF_ADD(t_wait, t0); }
-            mbar_arrive_expect_tx(&b_full[bs], S::kBSlot);
-            tma_load_3d(b_base + bs * S::kBSlot, &tm.b, &b_full[bs], kc * 64, tap, nblk * BLOCK_N);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&b_full[bs], S::kBSlot);
+              tma_load_3d(b_base + bs * S::kBSlot, &tm.b, &b_full[bs], kc * 64, tap, nblk * BLOCK_N);
+            }
+            __syncwarp();
             if (++bs == kBStages) { bs = 0; bph ^= 1; }
           }
         }
       }
-      if (kHProf && p.prof) {
+      if (kHProf && p.prof && lane == 0) {
         atomicAdd(p.prof + 0, (unsigned long long)t_wait);
         atomicAdd(p.prof + 1, (unsigned long long)(clock64() - t_begin));
         atomicAdd(p.prof + 7, 1ull);
@@ -346,6 +355,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloTmaps tm, const HaloKArgs p) {
     uint8_t* wstage = staging + ew * 4096;
     float* wvec = vecs + ew * S::kVecFloats;
     int tl = 0, sbuf = 0;
+    int staged_base = -1;
     long long t_wtfull = 0;
     const long long t_begin = HPROF_T0();
     // residual rows of the tiles this CTA reaches kResPrefetchTiles iterations from now -> L2 (conv_common.cuh)
@@ -375,7 +385,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloTmaps tm, const HaloKArgs p) {
       tc_fence_after_sync();
 #define DYK_HEPI(ACT)                                                                                          \
   halo_epilogue<BLOCK_N, kSub, kBf16, ACT>(tm, p, sc, nblk * BLOCK_N, t_row, wstage, wvec, sbuf, &tempty[acc], q, \
-                                           lane, c_begin, c_step)
+                                           lane, c_begin, c_step, staged_base)
       switch (p.act) {
         case DYK_ACT_LEAKY: DYK_HEPI(DYK_ACT_LEAKY); break;
         case DYK_ACT_MISH: DYK_HEPI(DYK_ACT_MISH); break;

@@ -135,22 +135,29 @@ template <bool kBf16, int kAct, bool kNoRes>
 __device__ __forceinline__ void halo2_epilogue(const Halo2Tmaps& tm, const Halo2KArgs& p, const Sub2& sc, int n_base,
                                                int nchunks, uint32_t t_row, uint8_t* wstage, float* wvec, int& sbuf,
                                                uint32_t tempty_leader, int q, int lane, int half, bool prof_warp,
-                                               long long& prof_ld, long long& prof_st, const uint4 (&rres_all)[4][4]) {
+                                               long long& prof_ld, long long& prof_st, const uint4 (&rres_all)[4][4],
+                                               int& staged_base) {
   constexpr int kCols = 32;
   constexpr int kChunks = kH2BlockN / kCols;   // up to 8 (nchunks of them in this item); this warp handles chunks half, half+2, ...
   const bool sub_ok = sc.n < p.N;
   const bool has_res = !kNoRes && p.res != nullptr;   // (the dual-source variant never carries a residual)
 
-  __syncwarp();
+  // scale / bias of this item's output channels -> warp-private shared memory; only when they differ from what is staged
+  // (never again on layers with a single channel block: the 16 global loads + syncs per tile were a fifth of the
+  // epilogue's instructions on the short tiles of the early layers)
+  if (n_base * 16 + nchunks != staged_base) {
+    staged_base = n_base * 16 + nchunks;
+    __syncwarp();
 #pragma unroll
-  for (int j = 0; j < kH2BlockN / 32; ++j) {
-    if (j < nchunks) {
-      const int col = n_base + j * 32 + lane;
-      wvec[j * 32 + lane] = p.scale ? __ldg(p.scale + col) : 1.f;
-      wvec[kH2BlockN + j * 32 + lane] = p.bias ? __ldg(p.bias + col) : 0.f;
+    for (int j = 0; j < kH2BlockN / 32; ++j) {
+      if (j < nchunks) {
+        const int col = n_base + j * 32 + lane;
+        wvec[j * 32 + lane] = p.scale ? __ldg(p.scale + col) : 1.f;
+        wvec[kH2BlockN + j * 32 + lane] = p.bias ? __ldg(p.bias + col) : 0.f;
+      }
     }
+    __syncwarp();
   }
-  __syncwarp();
 
 #pragma unroll
   for (int ci = 0; ci < kChunks / 2; ++ci) {
@@ -289,11 +296,12 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
   stamp(-1, 10);
 
   if (warp_idx == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs, own halves)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs, own halves; the whole
+    // warp walks the loop, one elected lane issues)
+    {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      if constexpr (kResB) {
+      if (kResB && lane == 0) {
         // the whole filter, once: tap t -> slot t (this CTA's half of the output channels)
         const uint32_t b_bytes = (uint32_t)p.res_cols * 128u;
         for (int tap = 0; tap < 9; ++tap) {
@@ -313,20 +321,26 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
         const int b_row = nblk * kH2BlockN + it.ncol0 + (int)rank * (it.ncols >> 1);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(&a_empty[as], aph ^ 1);
-          if constexpr (kDual) {
-            mbar_arrive_expect_tx(&a_raw[as], 2 * kH2HaloBytes);
-            tma_load_4d(a_base + as * kH2ASlot, &tm.a, &a_raw[as], kc * 64, sc.w0 - 1, sc.h0 - 1, sc.n);
-            tma_load_4d(a2_base + as * kH2ASlot, &tm.a2, &a_raw[as], kc * 64, sc.w0 - 1, sc.h0 - 1, sc.n);
-          } else {
-            if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * kH2HaloBytes);
-            tma_load_4d_2sm(a_base + as * kH2ASlot, &tm.a, leader_smem_addr(&a_full[as]), kc * 64, sc.w0 - 1, sc.h0 - 1, sc.n);
+          if (elect_one()) {
+            if constexpr (kDual) {
+              mbar_arrive_expect_tx(&a_raw[as], 2 * kH2HaloBytes);
+              tma_load_4d(a_base + as * kH2ASlot, &tm.a, &a_raw[as], kc * 64, sc.w0 - 1, sc.h0 - 1, sc.n);
+              tma_load_4d(a2_base + as * kH2ASlot, &tm.a2, &a_raw[as], kc * 64, sc.w0 - 1, sc.h0 - 1, sc.n);
+            } else {
+              if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * kH2HaloBytes);
+              tma_load_4d_2sm(a_base + as * kH2ASlot, &tm.a, leader_smem_addr(&a_full[as]), kc * 64, sc.w0 - 1, sc.h0 - 1, sc.n);
+            }
           }
+          __syncwarp();
           if (++as == kAStg) { as = 0; aph ^= 1; }
           if constexpr (!kResB) {
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&b_empty[bs], bph ^ 1);
-              if (leader) mbar_arrive_expect_tx(&b_full[bs], b_bytes);
-              tma_load_3d_2sm(b_base + bs * kBSlotBytes, bmap, leader_smem_addr(&b_full[bs]), kc * 64, tap, b_row);
+              if (elect_one()) {
+                if (leader) mbar_arrive_expect_tx(&b_full[bs], b_bytes);
+                tma_load_3d_2sm(b_base + bs * kBSlotBytes, bmap, leader_smem_addr(&b_full[bs]), kc * 64, tap, b_row);
+              }
+              __syncwarp();
               if (++bs == kBStages) { bs = 0; bph ^= 1; }
             }
           }
@@ -439,6 +453,7 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
     uint8_t* wstage = staging + ew * 4096;
     float* wvec = vecs + ew * kH2VecFloats;
     int tl = 0, sbuf = 0;
+    int staged_base = -1;      // (first output channel, chunk count) whose scale / bias are staged in wvec
     const bool prof_warp = leader && ew == 0;
     long long prof_ld = 0, prof_st = 0, prof_wait = 0;
     const long long t_begin = (kH2Prof && p.prof) ? clock64() : 0;
@@ -498,7 +513,7 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
       tc_fence_after_sync();
 #define DYK_H2EPI(ACT) \
   halo2_epilogue<kBf16, ACT, kDual>(tm, p, sc, nblk * kH2BlockN + it.ncol0, nchunks, t_row, wstage, wvec, sbuf, tempty_leader, q, lane, half, \
-                             prof_warp, prof_ld, prof_st, rres_all)
+                             prof_warp, prof_ld, prof_st, rres_all, staged_base)
       switch (p.act) {
         case DYK_ACT_LEAKY: DYK_H2EPI(DYK_ACT_LEAKY); break;
         case DYK_ACT_MISH: DYK_H2EPI(DYK_ACT_MISH); break;

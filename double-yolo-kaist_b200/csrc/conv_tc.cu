@@ -374,8 +374,8 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
   stamp(-1, 10);
 
   if (warp_idx == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       long long t_wait = 0;
@@ -413,14 +413,17 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
             }
             uint8_t* sa = stage_base + stage * S::kStageBytes;
             uint8_t* sb = sa + S::kABytes;
-            mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-            tma_load_4d(sa, amap, &full_bar[stage], kc * BLOCK_K, tc.w0 + dw, tc.h0 + dh, tc.n0);
-            tma_load_3d(sb, &tm.b, &full_bar[stage], kc * BLOCK_K + b_k0, b_tap, tc.nblk * BLOCK_N);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+              tma_load_4d(sa, amap, &full_bar[stage], kc * BLOCK_K, tc.w0 + dw, tc.h0 + dh, tc.n0);
+              tma_load_3d(sb, &tm.b, &full_bar[stage], kc * BLOCK_K + b_k0, b_tap, tc.nblk * BLOCK_N);
+            }
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
-      if (kProf && p.prof) {
+      if (kProf && p.prof && lane == 0) {
         atomicAdd(p.prof + PROF_PRODUCER_WAIT_EMPTY, (unsigned long long)t_wait);
         atomicAdd(p.prof + PROF_PRODUCER_TOTAL, (unsigned long long)(clock64() - t_begin));
         atomicAdd(p.prof + PROF_CTAS, 1ull);

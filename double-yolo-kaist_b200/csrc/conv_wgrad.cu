@@ -117,7 +117,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradTmaps tm, const WgradKArgs p) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp_idx == 0) {
-    if (lane == 0) {
+    {   // TMA producer: whole warp in the loop, one elected lane issues (uniform-register operands)
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -127,6 +127,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradTmaps tm, const WgradKArgs p) {
         const int h0 = (rowt - n * p.fd_tiles_h.div) * 8;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * S::kStageBytes;
+        if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
         tma_load_4d(sa, &tm.dz, &full_bar[stage], cob * 128, w0, h0, n);
         tma_load_4d(sa + kBoxBytes, &tm.dz, &full_bar[stage], cob * 128 + 64, w0, h0, n);
@@ -146,11 +147,13 @@ conv_wgrad_kernel(const __grid_constant__ WgradTmaps tm, const WgradKArgs p) {
           for (int j = 0; j < BLOCK_N / 64; ++j)
             tma_load_4d(sb + j * kBoxBytes, &tm.x[map_idx], &full_bar[stage], cib * BLOCK_N + j * 64, w0 + dw, h0 + dh, n);
         }
+        }
+        __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp_idx == 1) {
-    if (lane == 0) {
+    {   // whole warp in the loop, one elected lane per tcgen05 instruction (uniform-register operands; see conv_halo2.cu)
       // both operands MN-major: bits 15 / 16 of the instruction descriptor
       constexpr uint32_t idesc = umma_idesc_f16(128, BLOCK_N, kBf16 ? 1 : 0) | (1u << 15) | (1u << 16);
       int stage = 0;
@@ -159,20 +162,25 @@ conv_wgrad_kernel(const __grid_constant__ WgradTmaps tm, const WgradKArgs p) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after_sync();
         const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int t = 0; t < kTaps; ++t) {
-          const uint32_t sb = sa + S::kABytes + t * S::kBBytes;
+          for (int t = 0; t < kTaps; ++t) {
+            const uint32_t sb = sa + S::kABytes + t * S::kBBytes;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {   // 16 pixels (= 2 groups of 8 K-rows = 2048 B) per MMA
-            const uint64_t adesc = umma_desc_mnmajor(sa + k * 2048, kBoxBytes);
-            const uint64_t bdesc = umma_desc_mnmajor(sb + k * 2048, kBoxBytes);
-            umma_f16_ss(tmem_base + t * BLOCK_N, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {   // 16 pixels (= 2 groups of 8 K-rows = 2048 B) per MMA
+              const uint64_t adesc = umma_desc_mnmajor(sa + k * 2048, kBoxBytes);
+              const uint64_t bdesc = umma_desc_mnmajor(sb + k * 2048, kBoxBytes);
+              umma_f16_ss(tmem_base + t * BLOCK_N, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+            }
           }
+          umma_commit(&empty_bar[stage]);
+          if (i == nkb - 1) umma_commit(done_bar);
         }
-        umma_commit(&empty_bar[stage]);
+        __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(done_bar);
+      if (nkb <= 0 && elect_one()) umma_commit(done_bar);
+      __syncwarp();
     }
   }
   // ------------------------------------------------------------------ epilogue: in-cluster reduction of the split-K tiles
