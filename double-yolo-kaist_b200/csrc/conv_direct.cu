@@ -207,7 +207,8 @@ dwconv_strip_kernel(const uint8_t* __restrict__ x, long long xs, const float* __
 
 namespace dyk {
 int stem_tc_try(const void* x, const float* w, const float* scale, const float* bias, void* y, int64_t ys, int N, int H,
-                int W, int Cin, int Cout, int k, int stride, int pad, int act, int dtype, int x_kind, cudaStream_t stream);
+                int W, int Cin, int Cout, int k, int stride, int pad, int act, int dtype, int x_kind, cudaStream_t stream,
+                int Hs, int Ws);
 }
 using namespace dyk;
 
@@ -229,7 +230,7 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_stem_nchw_fwd(c
   // CUDA-core kernel below, which also serves all other stem shapes
   static const bool stem_tc_off = getenv("DYK_STEM_TC") != nullptr && getenv("DYK_STEM_TC")[0] == '0';
   if (!stem_tc_off && (dtype == DYK_F16 || dtype == DYK_BF16)) {
-    const int rc = stem_tc_try(x, w, scale, bias, y, ys, N, H, W, Cin, Cout, k, stride, pad, act, dtype, x_kind, stream);
+    const int rc = stem_tc_try(x, w, scale, bias, y, ys, N, H, W, Cin, Cout, k, stride, pad, act, dtype, x_kind, stream, 0, 0);
     if (rc <= 0) return rc;
   }
   const long long total = (long long)N * Ho * Wo;
@@ -251,6 +252,20 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_stem_nchw_fwd(c
 #undef DYK_STEM_LAUNCH
   DYK_LAUNCH_OK("stem_conv_kernel");
   return DYK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dyk_conv2d_stem_nchw_resize_fwd(const void* x, const float* w, const float* scale,
+                                        const float* bias, void* y, int64_t ys, int32_t N, int32_t Hs, int32_t Ws, int32_t H,
+                                        int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride, int32_t pad,
+                                        int32_t act, int32_t dtype, int32_t x_kind, void* stream_) {
+  DYK_REQUIRE(x && w && y, "dyk_conv2d_stem_nchw_resize_fwd: null pointer");
+  DYK_REQUIRE(x_kind == 0 || x_kind == 1, "dyk_conv2d_stem_nchw_resize_fwd: x_kind=%d (0 = fp32, 1 = uint8)", x_kind);
+  DYK_REQUIRE(Hs > 0 && Ws > 0 && H > 0 && W > 0 && N > 0, "dyk_conv2d_stem_nchw_resize_fwd: bad sizes");
+  DYK_REQUIRE(ys % 8 == 0 && ys >= Cout && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "dyk_conv2d_stem_nchw_resize_fwd: y layout");
+  DYK_REQUIRE((dtype == DYK_F16 || dtype == DYK_BF16) && k == 3 && stride == 1 && pad == 1 && Cin == 3 && Cout == 32,
+              "dyk_conv2d_stem_nchw_resize_fwd: only the 3x3 / stride 1 / 3 -> 32 channel stem of the shipped cfgs has the fused resize");
+  return stem_tc_try(x, w, scale, bias, y, ys, N, H, W, Cin, Cout, k, stride, pad, act, dtype, x_kind,
+                     static_cast<cudaStream_t>(stream_), Hs, Ws);
 }
 
 extern "C" __attribute__((visibility("default"))) int dyk_dwconv2d_fwd(const void* x, int64_t xs, const float* w, const float* scale, const float* bias,

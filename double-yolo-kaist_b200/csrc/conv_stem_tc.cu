@@ -19,6 +19,7 @@
 #include "ptx.cuh"
 #include "act.cuh"
 #include "conv_common.cuh"
+#include "frame_sample.cuh"
 
 namespace dyk {
 
@@ -29,7 +30,8 @@ template <bool kBf16, typename TIn>
 __global__ void __launch_bounds__(128, 8)
 stem_tc_kernel(const TIn* __restrict__ x, const float* __restrict__ w /* [32][3][3][Cin] fp32 */,
                const float* __restrict__ scale, const float* __restrict__ bias, uint8_t* __restrict__ y, long long ys,
-               int N, int H, int W, int Cin, int act, int tiles_w, long long num_tiles) {
+               int N, int H, int W, int Cin, int act, int tiles_w, long long num_tiles, int Hs, int Ws, float rs_h, float rs_w) {
+  // Hs > 0: x holds Hs x Ws frames and the convolution runs over their bilinear resize to H x W (frame_sample.cuh)
   __shared__ __align__(1024) uint8_t sa[128 * 64];     // A: 128 pixels x 32 K (16-bit), SWIZZLE_64B
   __shared__ __align__(1024) uint8_t sb[32 * 64];      // B: 32 out channels x 32 K
   __shared__ uint64_t mma_bar;
@@ -87,7 +89,28 @@ stem_tc_kernel(const TIn* __restrict__ x, const float* __restrict__ w /* [32][3]
     };
     const long long plane = (long long)H * W;
     const TIn* xb = x + ((long long)n * kCin * H + (ho - 1)) * W + (wo - 1);     // top-left tap of channel 0
-    if (ho >= 1 && ho + 1 < H && wo >= 1 && wo + 1 < W) {                        // interior pixel: no bounds checks
+    if (Hs > 0) {                                                                // multi-scale: sample the resized frame
+#pragma unroll
+      for (int k = 0; k < 27; ++k) v[k] = 0.f;
+      if (wo < W) {
+        const TIn* xs = x + (long long)n * kCin * Hs * Ws;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int h = ho - 1 + r;
+          if (h < 0 || h >= H) continue;
+          const ResizeAxis ah = resize_axis(h, rs_h, Hs);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const int ww = wo - 1 + q;
+            if (ww < 0 || ww >= W) continue;
+            const ResizeAxis aw = resize_axis(ww, rs_w, Ws);
+#pragma unroll
+            for (int ci = 0; ci < kCin; ++ci)
+              v[(r * 3 + q) * kCin + ci] = frame_bilinear(xs + (long long)ci * Hs * Ws, Ws, ah, aw);
+          }
+        }
+      }
+    } else if (ho >= 1 && ho + 1 < H && wo >= 1 && wo + 1 < W) {                 // interior pixel: no bounds checks
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -162,8 +185,10 @@ stem_tc_kernel(const TIn* __restrict__ x, const float* __restrict__ w /* [32][3]
 
 // Returns DYK_OK after launching, 1 when the shape is not covered (the caller falls back to the CUDA-core kernel).
 int stem_tc_try(const void* x, const float* w, const float* scale, const float* bias, void* y, int64_t ys, int N, int H,
-                int W, int Cin, int Cout, int k, int stride, int pad, int act, int dtype, int x_kind, cudaStream_t stream) {
+                int W, int Cin, int Cout, int k, int stride, int pad, int act, int dtype, int x_kind, cudaStream_t stream,
+                int Hs, int Ws) {
   if (!(k == 3 && stride == 1 && pad == 1 && Cout == 32 && Cin == 3)) return 1;
+  const float rs_h = Hs > 0 ? (float)Hs / (float)H : 0.f, rs_w = Hs > 0 ? (float)Ws / (float)W : 0.f;
   const int tiles_w = ceil_div(W, 128);
   const long long num_tiles = (long long)N * H * tiles_w;
   long long grid = num_tiles;
@@ -171,7 +196,7 @@ int stem_tc_try(const void* x, const float* w, const float* scale, const float* 
   if (grid > cap) grid = cap;
 #define DYK_STEM_TC(BF, TIN)                                                                                             \
   stem_tc_kernel<BF, TIN><<<(unsigned)grid, 128, 0, stream>>>(static_cast<const TIN*>(x), w, scale, bias, (uint8_t*)y, ys, N, \
-                                                              H, W, Cin, act, tiles_w, num_tiles)
+                                                              H, W, Cin, act, tiles_w, num_tiles, Hs, Ws, rs_h, rs_w)
   if (dtype == DYK_BF16) {
     if (x_kind == 0) DYK_STEM_TC(true, float); else DYK_STEM_TC(true, uint8_t);
   } else {

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include "vec.cuh"
 #include "act.cuh"
+#include "frame_sample.cuh"
 
 namespace dyk {
 
@@ -840,8 +841,10 @@ __global__ void frames_to_nhwc8_kernel(const TIn* __restrict__ x, uint8_t* __res
 // y[n][h][w][ci*9 + r*3 + s] = frame[n][ci][h + r - 1][w + s - 1] (0 outside, channels 27..31 zero): with the 3x3
 // neighbourhood as 32 "channels" the stem weight gradient is the weight gradient of a 1x1 convolution, and the channel
 // order makes its [Cout][27] result the OIHW gradient itself.
+// Hs > 0: x holds Hs x Ws frames and the rows are taken from their bilinear resize to H x W (frame_sample.cuh).
 template <bool kBf16, typename TIn>
-__global__ void frames_to_im2col32_kernel(const TIn* __restrict__ x, uint8_t* __restrict__ y, int N, int H, int W) {
+__global__ void frames_to_im2col32_kernel(const TIn* __restrict__ x, uint8_t* __restrict__ y, int N, int H, int W, int Hs, int Ws,
+                                          float rs_h, float rs_w) {
   const long long total = (long long)N * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -862,6 +865,11 @@ __global__ void frames_to_im2col32_kernel(const TIn* __restrict__ x, uint8_t* __
         for (int q = 0; q < 3; ++q) {
           const int ww = w + q - 1;
           if (ww < 0 || ww >= W) continue;
+          if (Hs > 0) {
+            f[ci * 9 + r * 3 + q] = frame_bilinear(x + (n * 3 + ci) * (long long)Hs * Ws, Ws, resize_axis(hh, rs_h, Hs),
+                                                   resize_axis(ww, rs_w, Ws));
+            continue;
+          }
           const TIn v = __ldg(&x[((n * 3 + ci) * H + hh) * W + ww]);
           if constexpr (sizeof(TIn) == 1) f[ci * 9 + r * 3 + q] = (float)v / 255.0f;
           else f[ci * 9 + r * 3 + q] = (float)v;
@@ -1153,18 +1161,29 @@ DYK_EXPORT int dyk_pack_weights_dgrad(const float* w_oihw, void* w_packed, int32
   return DYK_OK;
 }
 
-DYK_EXPORT int dyk_frames_to_im2col32(const void* x_nchw, void* y, int32_t N, int32_t H, int32_t W, int32_t dtype,
-                                      int32_t x_kind, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int frames_to_im2col32(const void* x_nchw, void* y, int32_t N, int32_t Hs, int32_t Ws, int32_t H, int32_t W, int32_t dtype,
+                              int32_t x_kind, cudaStream_t stream) {
   DYK_REQUIRE(x_nchw && y && N > 0 && H > 0 && W > 0 && DYK_AL16(y), "dyk_frames_to_im2col32: bad arguments");
   const int grid = grid_for_t((long long)N * H * W, 128);
+  const float rs_h = Hs > 0 ? (float)Hs / (float)H : 0.f, rs_w = Hs > 0 ? (float)Ws / (float)W : 0.f;
   if (x_kind == 1) {
-    DYK_DISPATCH_DTYPE(dtype, (frames_to_im2col32_kernel<kBf16, uint8_t><<<grid, 128, 0, stream>>>((const uint8_t*)x_nchw, (uint8_t*)y, N, H, W)));
+    DYK_DISPATCH_DTYPE(dtype, (frames_to_im2col32_kernel<kBf16, uint8_t><<<grid, 128, 0, stream>>>((const uint8_t*)x_nchw, (uint8_t*)y, N, H, W, Hs, Ws, rs_h, rs_w)));
   } else {
-    DYK_DISPATCH_DTYPE(dtype, (frames_to_im2col32_kernel<kBf16, float><<<grid, 128, 0, stream>>>((const float*)x_nchw, (uint8_t*)y, N, H, W)));
+    DYK_DISPATCH_DTYPE(dtype, (frames_to_im2col32_kernel<kBf16, float><<<grid, 128, 0, stream>>>((const float*)x_nchw, (uint8_t*)y, N, H, W, Hs, Ws, rs_h, rs_w)));
   }
   DYK_LAUNCH_OK("frames_to_im2col32_kernel");
   return DYK_OK;
+}
+
+DYK_EXPORT int dyk_frames_to_im2col32(const void* x_nchw, void* y, int32_t N, int32_t H, int32_t W, int32_t dtype, int32_t x_kind,
+                                      void* stream_) {
+  return frames_to_im2col32(x_nchw, y, N, 0, 0, H, W, dtype, x_kind, static_cast<cudaStream_t>(stream_));
+}
+
+DYK_EXPORT int dyk_frames_to_im2col32_resize(const void* x_nchw, void* y, int32_t N, int32_t Hs, int32_t Ws, int32_t H, int32_t W,
+                                             int32_t dtype, int32_t x_kind, void* stream_) {
+  DYK_REQUIRE(Hs > 0 && Ws > 0, "dyk_frames_to_im2col32_resize: bad source size");
+  return frames_to_im2col32(x_nchw, y, N, Hs, Ws, H, W, dtype, x_kind, static_cast<cudaStream_t>(stream_));
 }
 
 DYK_EXPORT int dyk_pack_weights_multi(const int64_t* descs, int32_t n, int32_t total_tiles, int32_t dtype, void* stream_) {

@@ -49,6 +49,8 @@ SIGNATURES = {
     "dyk_conv2d_dual_source_supported": (_i32, [C.POINTER(ConvParams)]),
     "dyk_conv_set_profile": (_i32, [_vp]),
     "dyk_conv2d_stem_nchw_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64] + [_i32] * 11 + [_vp]),
+    "dyk_conv2d_stem_nchw_resize_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64] + [_i32] * 13 + [_vp]),
+    "dyk_frames_to_im2col32_resize": (_i32, [_vp, _vp] + [_i32] * 7 + [_vp]),
     "dyk_dwconv2d_fwd": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
                                 _i32, _i32, _i32, _vp]),
     "dyk_fused_add": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _i32, _vp]),

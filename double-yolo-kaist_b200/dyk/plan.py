@@ -716,7 +716,13 @@ class Plan:
     def run_stems(self, x, y):
         stem = ops.f32_stem if self.f32 else ops.nhwc_stem
         for which, e, out, kw in self.stem_steps:
-            stem(x if which == 0 else y, e["w"], e["scale"], e["bias"], out, **kw)
+            src = x if which == 0 else y
+            if (src.shape[2], src.shape[3]) != (out.H, out.W):       # model(x, y, input_size=...): resize fused into the stem
+                if self.f32 or (kw["k"], kw["stride"], kw["pad"]) != (3, 1, 1):
+                    raise nat.NativeError("input_size: the fused bilinear resize exists for the 3x3 / stride-1 stem in fp16 / bf16")
+                stem(src, e["w"], e["scale"], e["bias"], out, resize=True, **kw)
+            else:
+                stem(src, e["w"], e["scale"], e["bias"], out, **kw)
 
     def run_body(self):
         side = self.side_stream
@@ -814,7 +820,7 @@ class PlanCache:
         if self.bank.signature is not None:
             self.bank.signature = ("stale",)
 
-    def run(self, x, y):
+    def run(self, x, y, input_size=None):
         model = self.model
         if not isinstance(x, torch.Tensor) or x.dim() != 4:
             raise ValueError("YOLO.forward expects (B, 3, H, W) tensors")
@@ -838,6 +844,8 @@ class PlanCache:
         if y is not None and y.dtype != x.dtype:
             raise ValueError("visible and LWIR batches must have the same dtype")
         B, _, H, W = x.shape
+        if input_size is not None:
+            H, W = (int(input_size), int(input_size)) if isinstance(input_size, int) else (int(input_size[0]), int(input_size[1]))
         p0 = next(model.parameters())
         if p0.device != x.device:
             raise ValueError(f"model is on {p0.device} but the input is on {x.device}")

@@ -256,13 +256,24 @@ def dwconv_wgrad(x: View, dz: View, grad_w: torch.Tensor, *, k: int, stride: int
 
 
 def stem_wgrad_tc(x_nchw: torch.Tensor, dz: View, grad_w: torch.Tensor, *, k: int, stride: int, pad: int,
-                  accumulate: bool) -> None:
+                  accumulate: bool, resize: bool = False) -> None:
     """Stem weight gradient on the tensor cores: the frames are re-laid out once as NHWC with the channel dimension
     zero-padded to 8 (16-bit), then the generic split-K wgrad kernel runs with Cin = 8 and writes only the real
     input channels.  ~6x faster than the CUDA-core reduction below at 512x640 x 16."""
     N, Cin, H, W = x_nchw.shape
     kind = {torch.float32: 0, torch.uint8: 1}[x_nchw.dtype]
     dtype = dz.buf.dtype
+    if resize and (H, W) != (dz.H, dz.W):
+        # multi-scale step: the im2col rows are sampled from the bilinear resize of the original frames (dz has the resized size)
+        if not (Cin == 3 and k == 3 and stride == 1 and pad == 1):
+            raise nat.NativeError("stem_wgrad_tc: the fused resize exists for the 3x3 / stride-1 / 3-channel stem")
+        Hd, Wd = dz.H, dz.W
+        xc = scratch(2 * N * Hd * Wd * 32, x_nchw.device, "x32")[:2 * N * Hd * Wd * 32].view(dtype).view(N, Hd, Wd, 32)
+        nat.call("dyk_frames_to_im2col32_resize", _p(x_nchw), _p(xc), N, H, W, Hd, Wd, dz.dt, kind, _stream())
+        nat.count_launches()
+        conv_wgrad(View(xc, 0, 32), dz, grad_w.view(grad_w.shape[0], 27, 1, 1), k=1, stride=1, pad=0, accumulate=accumulate,
+                   cin_real=27)
+        return
     if Cin == 3 and k == 3 and stride == 1 and pad == 1:
         # the 3x3 neighbourhood as 32 im2col "channels" (order ci, r, s = OIHW): a 1x1 weight gradient with one tap and
         # half-filled operand boxes instead of nine taps over boxes that are 7/8 zero padding (1.55 -> ~0.5 ms at 512x640x16)

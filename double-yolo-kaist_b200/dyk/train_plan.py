@@ -147,12 +147,15 @@ class _WgradLane:
 
 
 class TrainPlan:
-    def __init__(self, model, B, H, W, dtype, dual, device, in_dtype=torch.float32):
+    def __init__(self, model, B, H, W, dtype, dual, device, in_dtype=torch.float32, src_hw=None):
         self.model, self.B, self.dtype, self.device, self.dual = model, B, dtype, device, dual
         # Static frame buffers: the caller's batches are copied in (31 MB per uint8 bs-16 pair), so every launch of a step
-        # reads fixed addresses and the whole step can be replayed as CUDA graphs.
-        self.in_x = torch.empty((B, 3, H, W), dtype=in_dtype, device=device)
-        self.in_y = torch.empty((B, 3, H, W), dtype=in_dtype, device=device) if dual else None
+        # reads fixed addresses and the whole step can be replayed as CUDA graphs.  src_hw != (H, W): multi-scale step, the
+        # buffers hold the ORIGINAL frames and the stem kernels (forward and weight gradient) sample their bilinear resize.
+        Hs, Ws = src_hw if src_hw is not None else (H, W)
+        self.resize = (Hs, Ws) != (H, W)
+        self.in_x = torch.empty((B, 3, Hs, Ws), dtype=in_dtype, device=device)
+        self.in_y = torch.empty((B, 3, Hs, Ws), dtype=in_dtype, device=device) if dual else None
         self.ops, self.layer_vals, self.img0, self.img1 = P.build_ops(model, H, W, dual)
         for op in self.ops:
             if isinstance(op, P.ConvOp):
@@ -301,7 +304,9 @@ class TrainPlan:
                 src = self.in_x if op.src is self.img0 else self.in_y
                 st["x_in"] = src
                 w = conv.weight.detach().float().permute(0, 2, 3, 1).contiguous()
-                ops.nhwc_stem(src, w, None, None, st["z"], k=k, stride=s, pad=p, act="linear")
+                if self.resize and (k, s, p) != (3, 1, 1):
+                    raise nat.NativeError("input_size: the fused bilinear resize exists for the 3x3 / stride-1 stem")
+                ops.nhwc_stem(src, w, None, None, st["z"], k=k, stride=s, pad=p, act="linear", resize=self.resize)
             elif st["dw"]:
                 st["w"] = T.dw_weight(conv)
                 ops.nhwc_dwconv(op.src.view, st["w"], None, None, st["z"], k=k, stride=s, pad=p, act="linear")
@@ -653,7 +658,7 @@ class TrainPlan:
                     o = self.offsets[id(conv.bias)]
                     T.chan_sum(dz, flat[o:o + dz.C], accumulate=True)     # dz.C = head_pad(Cout) = the padded slot of the bias
             if st["stem"]:
-                T.stem_wgrad_tc(st["x_in"], dz, gw, k=k, stride=s, pad=p, accumulate=True)
+                T.stem_wgrad_tc(st["x_in"], dz, gw, k=k, stride=s, pad=p, accumulate=True, resize=self.resize)
                 return
             gv, acc = gin
             if st["dw"]:
@@ -799,7 +804,7 @@ class TrainPlanCache:
         self.plans.clear()
         self.last_plan = None
 
-    def run(self, x, y):
+    def run(self, x, y, input_size=None):
         model = self.model
         ops._require_cuda(x, "YOLO.forward (training)")
         dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else model.compute_dtype
@@ -816,16 +821,19 @@ class TrainPlanCache:
             return t.detach().contiguous()
 
         x, y = prep(x), prep(y)
-        B, _, H, W = x.shape
+        B, _, Hs, Ws = x.shape
+        H, W = Hs, Ws
+        if input_size is not None:
+            H, W = (int(input_size), int(input_size)) if isinstance(input_size, int) else (int(input_size[0]), int(input_size[1]))
         if y is not None and y.dtype != x.dtype:
             raise ValueError("visible and LWIR batches must have the same dtype")
-        key = (B, H, W, dtype, y is not None, x.device, x.dtype)
+        key = (B, H, W, dtype, y is not None, x.device, x.dtype, Hs, Ws)
         plan = self.plans.pop(key, None)
         with torch.cuda.device(x.device):
             if plan is None:
                 while len(self.plans) >= self.keep:
                     self.plans.pop(next(iter(self.plans)))
-                plan = TrainPlan(model, B, H, W, dtype, y is not None, x.device, in_dtype=x.dtype)
+                plan = TrainPlan(model, B, H, W, dtype, y is not None, x.device, in_dtype=x.dtype, src_hw=(Hs, Ws))
             self.plans[key] = plan           # re-insert = most recently used
             self.last_plan = plan
             plan.reducer = getattr(model, "grad_reducer", None)

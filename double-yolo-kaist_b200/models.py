@@ -224,13 +224,16 @@ class YOLO(nn.Module):
         if '_plans' in self.__dict__:
             self._plans.mark_stale()
 
-    def forward(self, x, y=None):
+    def forward(self, x, y=None, input_size=None):
+        """input_size=(H, W) (not in the reference): the frames are bilinearly resized to H x W on the fly inside the stem
+        convolutions — the fused form of the multi-scale training loop's `imgs = F.interpolate(imgs, size=ns,
+        mode='bilinear', align_corners=False)` (train_utils/kaist_train_eval_utils.py:59-71); pass the ORIGINAL frames."""
         di = "second_index" in self.net_info and y is not None
         if self.training:
             if "second_index" in self.net_info and y is None:
                 raise ValueError("this cfg defines second_index: call model(visible, lwir) with both modalities")
-            return self._train_plans.run(x, y if di else None)   # list of raw head tensors with a grad_fn
-        io, p = self._plans.run(x, y if di else None)
+            return self._train_plans.run(x, y if di else None, input_size)   # list of raw head tensors with a grad_fn
+        io, p = self._plans.run(x, y if di else None, input_size)
         return io, p
 
 

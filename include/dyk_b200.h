@@ -119,6 +119,16 @@ int dyk_conv2d_stem_nchw_fwd(const void* x_nchw, const float* w, const float* sc
                              void* y, int64_t y_pix_stride, int32_t N, int32_t H, int32_t W, int32_t Cin,
                              int32_t Cout, int32_t k, int32_t stride, int32_t pad, int32_t act,
                              int32_t dtype, int32_t x_kind, void* stream);
+/* Multi-scale training (train_utils/kaist_train_eval_utils.py:59-71): every `accumulate` batches the reference picks a new
+ * size and runs `imgs = F.interpolate(imgs, size=ns, mode='bilinear', align_corners=False)` before the model, i.e. it
+ * reads the batch, writes a resized fp32 copy and the stem reads that again.  Here the stem convolution samples the resized
+ * frame while it gathers its 3x3 neighbourhood: x holds the ORIGINAL Hs x Ws frames (fp32, or uint8 as above), the
+ * convolution runs over their bilinear resize to H x W (PyTorch's align_corners = False arithmetic) and y is N x H x W.
+ * Available for the 3x3 / stride 1 / pad 1 / 3 -> 32 channel stem of the shipped cfgs (tensor-core stem kernel). */
+int dyk_conv2d_stem_nchw_resize_fwd(const void* x_nchw, const float* w_ohwi, const float* scale, const float* bias, void* y,
+                                    int64_t y_pix_stride, int32_t N, int32_t Hs, int32_t Ws, int32_t H, int32_t W, int32_t Cin,
+                                    int32_t Cout, int32_t k, int32_t stride, int32_t pad, int32_t act, int32_t dtype,
+                                    int32_t x_kind, void* stream);
 
 /* ---- depthwise convolution + BN + activation ---------------------------------------------------
  * Replaces nn.Conv2d(groups=C) (+BN+act): models.py:41 (groups key) and
@@ -316,6 +326,10 @@ int dyk_frames_to_nhwc8(const void* x_nchw, void* y, int32_t N, int32_t Cin, int
  * (27..31 zero).  dyk_conv2d_wgrad on it with k = 1, Cin = 32, Cin_real = 27 yields the stem's OIHW weight gradient. */
 int dyk_frames_to_im2col32(const void* x_nchw, void* y, int32_t N, int32_t H, int32_t W, int32_t dtype, int32_t x_kind,
                            void* stream);
+/* the same rows taken from the bilinear resize of Hs x Ws frames to H x W (see dyk_conv2d_stem_nchw_resize_fwd): the stem's
+ * weight gradient in a multi-scale training step without a resized copy of the batch. */
+int dyk_frames_to_im2col32_resize(const void* x_nchw, void* y, int32_t N, int32_t Hs, int32_t Ws, int32_t H, int32_t W,
+                                  int32_t dtype, int32_t x_kind, void* stream);
 /* weight gradient of the stem convolutions (Cin <= 4, NCHW fp32 / uint8 frames as in dyk_conv2d_stem_nchw_fwd).
  * workspace: DYK_STEM_WGRAD_STRIPS * Cout * k*k*Cin floats. */
 #define DYK_STEM_WGRAD_STRIPS 592
