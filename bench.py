@@ -207,23 +207,28 @@ def conv_breakdown(plan, x, y, iters=3):
                 dom["flops"] += fl
                 dom["n"] += 1
                 res = 1 if s.kw.get("res") is not None else 0
-                dom["bytes"] += 2.0 * (s.x.N * s.x.H * s.x.W * s.x.C + opix * cout * (1 + res) + cout * s.x.C * k * k)
+                srcs = 2 if s.kw.get("x2") is not None else 1          # dual-source modality fusion reads both tensors
+                dom["bytes"] += 2.0 * (srcs * s.x.N * s.x.H * s.x.W * s.x.C + opix * cout * (1 + res) + cout * s.x.C * k * k)
     return conv_ms, other_ms, flops, n_conv, dom
 
 
 def uses_halo2(step):
-    """Mirror of the dispatch rule in csrc/conv_halo2.cu (conv3x3_halo2_try): 3x3 stride-1 pad-1 layers with >= 256 stored
-    output channels, >= 64 input channels and a spatial size that fills >= 60 % of the 8x16-pixel sub-tiles."""
+    """Mirror of the dispatch rule in csrc/conv_halo2.cu (conv3x3_halo2_try): 3x3 stride-1 pad-1 layers whose spatial size
+    fills >= 60 % of the 8x16-pixel sub-tiles and that have either >= 256 stored output channels and >= 64 input channels
+    (streamed weights) or <= 64 input channels and 64 / 96 / 128 output channels (resident weights)."""
     kw = step.kw
     if os.environ.get("DYK_HALO2", "1") == "0" or os.environ.get("DYK_NO_HALO", "0") == "1":
         return False
     if not (kw["k"] == 3 and kw["stride"] == 1 and kw["pad"] == 1 and not kw["upsample2x"] and not kw.get("out_f32", False)):
         return False
     x, y = step.x, step.y
-    if y.C < 256 or x.C < 64:
+    subs = -(-x.W // 8) * -(-x.H // 16)
+    if x.W * x.H / (subs * 128) < 0.6:
         return False
-    eff = x.W * x.H / (-(-x.W // 8) * 8 * -(-x.H // 16) * 16)
-    return eff >= 0.6
+    if y.C >= 256 and x.C >= 64:
+        return True
+    resident = os.environ.get("DYK_HALO2_RES", "1") != "0" and kw.get("x2") is None
+    return resident and 16 <= x.C <= 64 and 64 <= y.C <= 128 and y.C % 32 == 0 and subs * x.N >= 148
 
 
 def conv_flops_per_frame(model, Hh, Ww):
@@ -400,24 +405,40 @@ def run_train(args, rank, local, world, dev, cfg=None, dtype=None, steps=None, w
     return line
 
 
+TRAFFIC_PROFILE = "profiles/r02_dram_traffic_dyolov3.txt"
+
+
+def _profile_traffic(families):
+    """Sum of `read + write` GB of the named kernel families in the committed ncu DRAM capture of one bs-16 dyolov3_add_sl
+    step (profiles/r02_dram_traffic_dyolov3.txt, written by tools/dram_summary.py from `ncu --metrics dram__bytes_read.sum,
+    dram__bytes_write.sum` over tools/one_forward.py) -> (bytes, launches); (None, 0) when the file is missing."""
+    import re
+    path = REPO / TRAFFIC_PROFILE
+    if not path.exists():
+        return None, 0
+    total, n = 0.0, 0
+    for ln in path.read_text().splitlines():
+        m = re.match(r"\s*(\S+)\s+n=\s*(\d+)\s+[\d.]+ ms\s+read\s+([\d.]+) GB\s+write\s+([\d.]+) GB", ln)
+        if m and m.group(1) in families:
+            total += (float(m.group(3)) + float(m.group(4))) * 1e9
+            n += int(m.group(2))
+    return (total, n) if n else (None, 0)
+
+
 def conv_dram_traffic(cfg, B):
-    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) moved by the convolution launches of one step, from the
-    committed ncu capture of this exact workload (profiles/r01_dram_traffic_dyolov3.txt); None for workloads that were not
-    captured.  It is below the algorithmic 11.04 GB because the 126 MB L2 keeps part of each layer's output for its consumer."""
+    """DRAM bytes moved by all convolution launches of one step, from the committed ncu capture of this exact workload; None
+    for workloads that were not captured.  It is below the algorithmic 11.04 GB because the 126 MB L2 keeps part of each
+    layer's output for its consumer."""
     if cfg == "kaist_dyolov3_add_sl.cfg" and B == 16:
-        return 8.139e9
+        return _profile_traffic({"conv3x3_halo2_kernel", "conv_tc_kernel", "conv3x3_halo_kernel", "stem_tc_kernel"})[0]
     return None
 
 
 def halo2_dram_traffic(cfg, B):
-    """DRAM bytes of the conv3x3_halo2_kernel launches of one step (52 launches, 2.008 GB read + 0.073 GB written) from
-    the committed ncu capture of this workload; None for workloads that were not captured."""
+    """DRAM bytes of the conv3x3_halo2_kernel launches of one step from the same capture."""
     if cfg == "kaist_dyolov3_add_sl.cfg" and B == 16:
-        return 2.081e9
+        return _profile_traffic({"conv3x3_halo2_kernel"})[0]
     return None
-
-
-TRAFFIC_PROFILE = "profiles/r01_dram_traffic_dyolov3.txt"
 
 
 def main():
@@ -611,13 +632,14 @@ def main():
                          "frac": achieved / peak_tf, "traffic": halo2_dram_traffic(args.cfg, B) if dom["bytes"] else None,
                          "traffic_source": {"from_profile": TRAFFIC_PROFILE, "measured_in_this_run": False},
                          "peak_source": peak_kind,
-                         "kernel": "conv3x3_halo2_kernel (tcgen05 cta_group::2 implicit GEMM, the 3x3 stride-1 layers with "
-                                   ">= 256 output channels): the dominant kernel of the step by time",
+                         "kernel": "conv3x3_halo2_kernel (tcgen05 cta_group::2 implicit GEMM: the 3x3 stride-1 layers with >= 256 "
+                                   "output channels, the dual-source modality-fusion convs and the resident-weights early "
+                                   "layers): the dominant kernel of the step by time",
                          "note": "a launch = one layer, so figures are sums over the kernel's launches of one step: "
                                  "achieved = algorithmic FLOPs / summed CUDA-event durations (each launch bracketed on "
                                  "the launching stream, run eagerly, so launch latency is inside the brackets); traffic = "
                                  "ncu dram__bytes_read.sum + dram__bytes_write.sum of the same launches "
-                                 "(profiles/r01_dram_traffic_dyolov3.txt)",
+                                 f"({TRAFFIC_PROFILE})",
                          "launches_per_step": dom["n"], "kernel_ms_per_step": dom["ms"],
                          "algorithmic_gflop_per_step": dom["flops"] / 1e9, "algorithmic_bytes_per_step": dom["bytes"],
                          "all_dense_convs": {"achieved": achieved_all, "frac": achieved_all / peak_tf, "launches_per_step": n_conv,

@@ -207,14 +207,14 @@ def conv_dual_source_supported(N, H, W, Cin, cout, cout_store, dtype, *, k, stri
     return bool(nat.load().dyk_conv2d_dual_source_supported(C.byref(p)))
 
 
-def nhwc_stem(x_nchw: torch.Tensor, w_f32_ohwi, scale, bias, y: View, *, k, stride, pad, act, resize=False) -> None:
-    """resize=True: the frames are read through a bilinear resize (F.interpolate(..., mode='bilinear', align_corners=False),
-    kaist_train_eval_utils.py:59-71) to the size the output `y` implies — the resized batch is never materialised."""
+def nhwc_stem(x_nchw: torch.Tensor, w_f32_ohwi, scale, bias, y: View, *, k, stride, pad, act, resize_to=None) -> None:
+    """resize_to=(H, W): the frames are read through a bilinear resize to H x W (F.interpolate(..., mode='bilinear',
+    align_corners=False), kaist_train_eval_utils.py:59-71) — the resized batch is never materialised."""
     N, Cin, H, W = x_nchw.shape
     kind = {torch.float32: 0, torch.uint8: 1}[x_nchw.dtype]
-    if resize and (H, W) != (y.H, y.W):
+    if resize_to is not None and tuple(resize_to) != (H, W):
         nat.call("dyk_conv2d_stem_nchw_resize_fwd", _p(x_nchw), _p(w_f32_ohwi), _p(scale), _p(bias), y.ptr, y.stride,
-                 N, H, W, y.H, y.W, Cin, y.C, k, stride, pad, nat.ACT_IDS[act], y.dt, kind, _stream())
+                 N, H, W, int(resize_to[0]), int(resize_to[1]), Cin, y.C, k, stride, pad, nat.ACT_IDS[act], y.dt, kind, _stream())
     else:
         nat.call("dyk_conv2d_stem_nchw_fwd", _p(x_nchw), _p(w_f32_ohwi), _p(scale), _p(bias), y.ptr, y.stride,
                  N, H, W, Cin, y.C, k, stride, pad, nat.ACT_IDS[act], y.dt, kind, _stream())

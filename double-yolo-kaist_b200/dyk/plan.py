@@ -492,6 +492,7 @@ class WeightBank:
 class Plan:
     def __init__(self, model, bank, B, H, W, dtype, dual, device):
         self.B, self.dtype, self.device, self.dual = B, dtype, device, dual
+        self.H, self.W = H, W
         raw, vals, self.img0, self.img1 = build_ops(model, H, W, dual)
         self.layer_vals = vals   # Value visible at every cfg layer index (diagnostics: tools/layer_parity.py)
         # fp32-accurate mode (compute_dtype = torch.float32, csrc/f32_path.cu): fp32 buffers, split-bf16 tensor-core convs,
@@ -717,10 +718,10 @@ class Plan:
         stem = ops.f32_stem if self.f32 else ops.nhwc_stem
         for which, e, out, kw in self.stem_steps:
             src = x if which == 0 else y
-            if (src.shape[2], src.shape[3]) != (out.H, out.W):       # model(x, y, input_size=...): resize fused into the stem
-                if self.f32 or (kw["k"], kw["stride"], kw["pad"]) != (3, 1, 1):
-                    raise nat.NativeError("input_size: the fused bilinear resize exists for the 3x3 / stride-1 stem in fp16 / bf16")
-                stem(src, e["w"], e["scale"], e["bias"], out, resize=True, **kw)
+            if (src.shape[2], src.shape[3]) != (self.H, self.W):     # model(x, y, input_size=...): resize fused into the stem
+                if self.f32:
+                    raise nat.NativeError("input_size: the fused bilinear resize exists in fp16 / bf16 only")
+                stem(src, e["w"], e["scale"], e["bias"], out, resize_to=(self.H, self.W), **kw)
             else:
                 stem(src, e["w"], e["scale"], e["bias"], out, **kw)
 

@@ -153,6 +153,7 @@ class TrainPlan:
         # reads fixed addresses and the whole step can be replayed as CUDA graphs.  src_hw != (H, W): multi-scale step, the
         # buffers hold the ORIGINAL frames and the stem kernels (forward and weight gradient) sample their bilinear resize.
         Hs, Ws = src_hw if src_hw is not None else (H, W)
+        self.H, self.W = H, W
         self.resize = (Hs, Ws) != (H, W)
         self.in_x = torch.empty((B, 3, Hs, Ws), dtype=in_dtype, device=device)
         self.in_y = torch.empty((B, 3, Hs, Ws), dtype=in_dtype, device=device) if dual else None
@@ -304,9 +305,8 @@ class TrainPlan:
                 src = self.in_x if op.src is self.img0 else self.in_y
                 st["x_in"] = src
                 w = conv.weight.detach().float().permute(0, 2, 3, 1).contiguous()
-                if self.resize and (k, s, p) != (3, 1, 1):
-                    raise nat.NativeError("input_size: the fused bilinear resize exists for the 3x3 / stride-1 stem")
-                ops.nhwc_stem(src, w, None, None, st["z"], k=k, stride=s, pad=p, act="linear", resize=self.resize)
+                ops.nhwc_stem(src, w, None, None, st["z"], k=k, stride=s, pad=p, act="linear",
+                              resize_to=(self.H, self.W) if self.resize else None)
             elif st["dw"]:
                 st["w"] = T.dw_weight(conv)
                 ops.nhwc_dwconv(op.src.view, st["w"], None, None, st["z"], k=k, stride=s, pad=p, act="linear")

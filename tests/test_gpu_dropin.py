@@ -49,8 +49,10 @@ class SyntheticPairs:
 
 
 def train_one_epoch(model, optimizer, dataloader, device, epoch, accumulate, img_size, grid_min, grid_max, gs, multi_scale,
-                    compute_loss):
-    """kaist_train_eval_utils.py:12-118 without MetricLogger / reduce_dict / warm-up scheduler."""
+                    compute_loss, fused_input=False):
+    """kaist_train_eval_utils.py:12-118 without MetricLogger / reduce_dict / warm-up scheduler.
+    fused_input=True is the integration INTEGRATION.md recommends: the uint8 frames go to the model as they are (`/ 255` in
+    the stem) and the multi-scale resize becomes `model(v, l, input_size=ns)` instead of two F.interpolate calls."""
     model.train()
     enable_amp = "cuda" in device.type                                        # :41
     scaler = amp.GradScaler(enabled=enable_amp)                               # :42
@@ -59,19 +61,24 @@ def train_one_epoch(model, optimizer, dataloader, device, epoch, accumulate, img
     history = []
     for i, (v_imgs, l_imgs, targets, paths, _, _) in enumerate(dataloader):
         ni = i + nb * epoch
-        v_imgs = v_imgs.to(device).float() / 255.0                            # :54-55
-        l_imgs = l_imgs.to(device).float() / 255.0
+        if fused_input:
+            v_imgs, l_imgs = v_imgs.to(device), l_imgs.to(device)
+        else:
+            v_imgs = v_imgs.to(device).float() / 255.0                        # :54-55
+            l_imgs = l_imgs.to(device).float() / 255.0
         targets = targets.to(device)
+        ns = None
         if multi_scale:                                                       # :59-71
             if ni % accumulate == 0:
                 img_size = random.randrange(grid_min, grid_max + 1) * gs
             sf = img_size / max(v_imgs.shape[2:])
             if sf != 1:
                 ns = [math.ceil(x * sf / gs) * gs for x in v_imgs.shape[2:]]
-                v_imgs = F.interpolate(v_imgs, size=ns, mode='bilinear', align_corners=False)
-                l_imgs = F.interpolate(l_imgs, size=ns, mode='bilinear', align_corners=False)
+                if not fused_input:
+                    v_imgs = F.interpolate(v_imgs, size=ns, mode='bilinear', align_corners=False)
+                    l_imgs = F.interpolate(l_imgs, size=ns, mode='bilinear', align_corners=False)
         with amp.autocast(enabled=enable_amp):                                # :74
-            pred = model(v_imgs, l_imgs)
+            pred = model(v_imgs, l_imgs, input_size=ns) if fused_input else model(v_imgs, l_imgs)
             loss_dict = compute_loss(pred, targets, model)
             losses = sum(loss for loss in loss_dict.values())
             loss_items = torch.cat((loss_dict["box_loss"], loss_dict["obj_loss"], loss_dict["class_loss"], losses)).detach()
@@ -145,6 +152,16 @@ def test_reference_training_loop_over_native_modules(native_lib, name, opt_kind)
     mloss, hist = train_one_epoch(model, optimizer, data, DEV, epoch=0, accumulate=2, img_size=W, grid_min=3, grid_max=5,
                                   gs=32, multi_scale=True, compute_loss=compute_loss)
     torch.cuda.synchronize()
+    if opt_kind == "fused_sgd":
+        # the same epoch with the fused input path (uint8 frames, resize inside the stem) follows the same loss trajectory
+        random.seed(0)
+        model2 = _model(name)
+        opt2 = optim.FusedSGD([p for p in model2.parameters() if p.requires_grad], lr=1e-3, momentum=0.937, weight_decay=5e-4,
+                              nesterov=True)
+        _, hist2 = train_one_epoch(model2, opt2, SyntheticPairs(batches=16, bs=2), DEV, epoch=0, accumulate=2, img_size=W,
+                                   grid_min=3, grid_max=5, gs=32, multi_scale=True, compute_loss=compute_loss, fused_input=True)
+        assert all(math.isfinite(h) for h in hist2)
+        assert abs(hist2[0] - hist[0]) < 0.02 * abs(hist[0]), (hist[0], hist2[0])
     assert all(math.isfinite(h) for h in hist) and bool(torch.isfinite(mloss).all())
     assert train_one_epoch.last_scale >= 1.0, "GradScaler collapsed: the backward pass produces non-finite gradients at any scale"
     assert any(not torch.equal(a, b.detach()) for a, b in zip(before, pg[:8])), \
