@@ -62,6 +62,7 @@ struct ConvKArgs {
   long long res_pix_stride;
   unsigned long long* prof;        // optional role-cycle counters (dyk_conv_set_profile), may be null
   int res_pf;                      // residual L2 prefetch mode (conv_common.cuh)
+  int b_img_rows;                  // per-image weights (SE gate folded into the consumer): weight rows per image, 0 = shared
 };
 
 // Role-cycle counters (diagnostics): where the three pipelines of the kernel wait.
@@ -416,7 +417,7 @@ conv_tc_kernel(const __grid_constant__ ConvTmaps tm, const ConvKArgs p) {
             if (elect_one()) {
               mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
               tma_load_4d(sa, amap, &full_bar[stage], kc * BLOCK_K, tc.w0 + dw, tc.h0 + dh, tc.n0);
-              tma_load_3d(sb, &tm.b, &full_bar[stage], kc * BLOCK_K + b_k0, b_tap, tc.nblk * BLOCK_N);
+              tma_load_3d(sb, &tm.b, &full_bar[stage], kc * BLOCK_K + b_k0, b_tap, tc.nblk * BLOCK_N + tc.n0 * p.b_img_rows);
             }
             __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -692,11 +693,12 @@ static bool dual_source_ok(const dyk_conv_params* p) {
 }
 
 // Spatial box (tw, th, tn) with tw*th*tn == 128 that wastes the fewest output pixels.
-static void pick_tile(int Wo, int Ho, int N, int* tw, int* th, int* tn) {
+static void pick_tile(int Wo, int Ho, int N, int* tw, int* th, int* tn, bool one_image = false) {
   double best = -1;
   for (int w = 1; w <= 128; w *= 2) {
     for (int h = 1; w * h <= 128; h *= 2) {
       const int n = 128 / (w * h);
+      if (one_image && n != 1) continue;      // per-image weights: a tile must not straddle images
       const long long covered = (long long)ceil_div(Wo, w) * w * (long long)ceil_div(Ho, h) * h *
                                 (long long)ceil_div(N, n) * n;
       double eff = (double)Wo * Ho * N / (double)covered;
@@ -842,8 +844,15 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   memset(&ka, 0, sizeof(ka));
 
   // 1x1 stride-1 convolutions are plain GEMMs over the flattened pixel index.
+  const bool per_image = p->w_image_stride != 0;
+  if (per_image) {
+    DYK_REQUIRE(p->kh == 1 && p->kw == 1 && p->stride == 1 && p->pad == 0 && !p->upsample2x && !p->y_plane && p->out_f32 != 2,
+                "dyk_conv2d_fwd: per-image weights are available for 1x1 stride-1 convolutions");
+    DYK_REQUIRE(p->w_image_stride % p->Cin == 0 && p->w_image_stride / p->Cin >= p->Cout && (p->w_image_stride * 2) % 16 == 0,
+                "dyk_conv2d_fwd: w_image_stride must be a whole number (>= Cout) of weight rows");
+  }
   const bool flat = (p->kh == 1 && p->kw == 1 && p->stride == 1 && p->pad == 0 && !p->upsample2x && !p->y_plane &&
-                     p->out_h == 0 && p->out_w == 0);
+                     p->out_h == 0 && p->out_w == 0 && !per_image);
   int tw, th, tn;
   int gW = Wo, gH = Ho, gN = p->N;  // logical output grid the tiles run over
   if (flat) {
@@ -851,7 +860,7 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
     DYK_REQUIRE((long long)p->N * p->H * p->W < (1ll << 31), "dyk_conv2d_fwd: too many pixels");
     gH = 1; gN = 1; tw = 128; th = 1; tn = 1;
   } else {
-    pick_tile(Wo, Ho, p->N, &tw, &th, &tn);
+    pick_tile(Wo, Ho, p->N, &tw, &th, &tn, per_image);
   }
   const cuuint32_t abox[4] = {(cuuint32_t)BK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
   const long long xs = p->x_pix_stride * 2;  // bytes per pixel step
@@ -902,10 +911,13 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
     const cuuint32_t box[3] = {64, 1, (cuuint32_t)BN};
     if ((rc = encode_map(&tm.b, p->w, 3, dims, str, box, swz, "B/pair"))) return rc;
   } else {
-    const cuuint64_t dims[3] = {(cuuint64_t)p->Cin, (cuuint64_t)taps, (cuuint64_t)p->Cout};
+    const long long img_rows = per_image ? p->w_image_stride / p->Cin : 0;      // (1x1: one tap)
+    const cuuint64_t rows = per_image ? (cuuint64_t)(img_rows * (p->N - 1) + p->Cout) : (cuuint64_t)p->Cout;
+    const cuuint64_t dims[3] = {(cuuint64_t)p->Cin, (cuuint64_t)taps, rows};
     const cuuint64_t str[2] = {(cuuint64_t)p->Cin * 2, (cuuint64_t)p->Cin * 2 * taps};
     const cuuint32_t box[3] = {(cuuint32_t)BK, 1, (cuuint32_t)BN};
     if ((rc = encode_map(&tm.b, p->w, 3, dims, str, box, swz, "B"))) return rc;
+    ka.b_img_rows = (int)img_rows;
   }
   if (!p->out_f32) {
     // every epilogue warp stores 32-row x storeC-channel sub-boxes of the tile (see epilogue_tile)

@@ -16,10 +16,13 @@ static inline int grid_for(long long work, int block) {
 
 // ------------------------------------------------------------------ WeightedFeatureFusion
 // reference: build_utils/layers.py:63-85   x*w[0] + a*w[1]  (or plain x + a)
+// gate != nullptr: operand a is a SqueezeExcitation input whose `scale * x` (layers.py:190) has not been materialised: it is
+// formed here, rounded to the storage type like dyk_scale_channels would have stored it, and then enters the sum.
 template <bool kBf16>
 __global__ void fused_add_kernel(const uint8_t* __restrict__ a, long long as, const uint8_t* __restrict__ b,
                                  long long bs, uint8_t* __restrict__ y, long long ys, long long npix, int cv,
-                                 const float* __restrict__ wts) {
+                                 const float* __restrict__ wts, const float* __restrict__ gate = nullptr,
+                                 long long gate_stride = 0, int HW = 1) {
   float w0 = 1.f, w1 = 1.f;
   if (wts) { w0 = __ldg(wts); w1 = __ldg(wts + 1); }
   const long long total = npix * cv;
@@ -32,6 +35,12 @@ __global__ void fused_add_kernel(const uint8_t* __restrict__ a, long long as, co
     float fa[8], fb[8], fo[8];
     unpack8<kBf16>(va, fa);
     unpack8<kBf16>(vb, fb);
+    if (gate) {
+      const float* g = gate + (pix / HW) * gate_stride + c * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) fa[k] *= __ldg(g + k);
+      unpack8<kBf16>(pack8<kBf16>(fa), fa);      // the rounding of the (never stored) gated tensor
+    }
     if (wts) {
       // reference order: x = x * w0 (rounded to the tensor dtype), a = a * w1 (rounded), then x + a
 #pragma unroll
@@ -261,6 +270,25 @@ __global__ void __launch_bounds__(256) fold_bn_multi_kernel(const long long* __r
   }
 }
 
+// SqueezeExcitation gate folded into the weights of the consuming 1x1 convolution: out[n][co][ci] = w[co][ci] * gate[n][ci]
+template <bool kBf16>
+__global__ void scale_weights_per_image_kernel(const uint8_t* __restrict__ w, const float* __restrict__ gate, long long gs,
+                                               uint8_t* __restrict__ out, int N, int Cout, int cv) {
+  const long long per = (long long)Cout * cv;
+  const long long total = per * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / per, r = i - n * per;
+    const int c = (int)(r % cv);
+    float f[8];
+    unpack8<kBf16>(__ldg(reinterpret_cast<const uint4*>(w) + r), f);
+    const float* g = gate + n * gs + c * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] *= __ldg(g + k);
+    reinterpret_cast<uint4*>(out)[i] = pack8<kBf16>(f);
+  }
+}
+
 // [N][C][HW] fp32 -> [N][HW][ys] dtype through a 32x32 smem transpose
 template <bool kBf16>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, void* __restrict__ y, long long ys, int C, int HW) {
@@ -312,6 +340,36 @@ extern "C" __attribute__((visibility("default"))) int dyk_fused_add(const void* 
   DYK_DISPATCH_DTYPE(dtype, (fused_add_kernel<kBf16><<<grid, 256, 0, stream>>>(
                                 (const uint8_t*)a, as, (const uint8_t*)b, bs, (uint8_t*)y, ys, npix, cv, wts)));
   DYK_LAUNCH_OK("fused_add_kernel");
+  return DYK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dyk_fused_add_gated(const void* a, int64_t as, const float* gate, int64_t gate_stride,
+                             int32_t HW, const void* b, int64_t bs, void* y, int64_t ys, int64_t npix, int32_t C,
+                             const float* wts, int32_t dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYK_REQUIRE(a && b && y && gate && HW > 0, "dyk_fused_add_gated: null pointer");
+  DYK_REQUIRE(C > 0 && C % 8 == 0 && as % 8 == 0 && bs % 8 == 0 && ys % 8 == 0 && gate_stride >= C,
+              "dyk_fused_add_gated: C and strides must be multiples of 8 (C=%d)", C);
+  DYK_REQUIRE(DYK_ALIGNED16(a) && DYK_ALIGNED16(b) && DYK_ALIGNED16(y), "dyk_fused_add_gated: 16-byte alignment");
+  if (npix == 0) return DYK_OK;
+  const int cv = C / 8;
+  const int grid = grid_for(npix * cv, 256);
+  DYK_DISPATCH_DTYPE(dtype, (fused_add_kernel<kBf16><<<grid, 256, 0, stream>>>(
+                                (const uint8_t*)a, as, (const uint8_t*)b, bs, (uint8_t*)y, ys, npix, cv, wts, gate, gate_stride, HW)));
+  DYK_LAUNCH_OK("fused_add_kernel");
+  return DYK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int dyk_scale_weights_per_image(const void* w_packed, const float* gate, int64_t gate_stride,
+                             void* out, int32_t N, int32_t Cout, int32_t Cin, int32_t dtype, void* stream_) {
+  DYK_REQUIRE(w_packed && gate && out && N > 0 && Cout > 0, "dyk_scale_weights_per_image: bad arguments");
+  DYK_REQUIRE(Cin > 0 && Cin % 8 == 0 && gate_stride >= Cin && DYK_ALIGNED16(w_packed) && DYK_ALIGNED16(out),
+              "dyk_scale_weights_per_image: Cin must be a multiple of 8, 16-byte aligned tensors");
+  const int cv = Cin / 8;
+  const int grid = grid_for((long long)N * Cout * cv, 256);
+  DYK_DISPATCH_DTYPE(dtype, (scale_weights_per_image_kernel<kBf16><<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+                                (const uint8_t*)w_packed, gate, gate_stride, (uint8_t*)out, N, Cout, cv)));
+  DYK_LAUNCH_OK("scale_weights_per_image_kernel");
   return DYK_OK;
 }
 

@@ -37,6 +37,7 @@ class ConvParams(C.Structure):
         ("act", _i32), ("dtype", _i32), ("upsample2x", _i32), ("out_f32", _i32),
         ("out_h", _i32), ("out_w", _i32), ("y_plane", _i32),
         ("x2", _vp), ("x2_pix_stride", _i64), ("x_wts_raw", _vp),
+        ("w_image_stride", _i64),
     ]
 
 
@@ -47,6 +48,8 @@ SIGNATURES = {
     "dyk_check_device": (_i32, []),
     "dyk_conv2d_fwd": (_i32, [C.POINTER(ConvParams), _vp]),
     "dyk_conv2d_dual_source_supported": (_i32, [C.POINTER(ConvParams)]),
+    "dyk_scale_weights_per_image": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "dyk_fused_add_gated": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp, _i64, _i64, _i32, _vp, _i32, _vp]),
     "dyk_conv_set_profile": (_i32, [_vp]),
     "dyk_conv2d_stem_nchw_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64] + [_i32] * 11 + [_vp]),
     "dyk_conv2d_stem_nchw_resize_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64] + [_i32] * 13 + [_vp]),

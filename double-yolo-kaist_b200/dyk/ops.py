@@ -160,8 +160,9 @@ def pack_conv_weights_multi(items, dtype) -> None:
 
 # ------------------------------------------------------------------------------------------ NHWC launches
 def _conv_params(x: View, w_packed, scale, bias, y: View, *, k, stride, pad, act, res: View = None, upsample2x=False,
-                 out_f32=False, cout=None, x2: View = None, x_wts_raw=None):
+                 out_f32=False, cout=None, x2: View = None, x_wts_raw=None, w_image_stride=0):
     p = nat.ConvParams()
+    p.w_image_stride = int(w_image_stride)
     p.x, p.x_pix_stride = x.ptr, x.stride
     p.w = None if w_packed is None else w_packed.data_ptr()
     p.scale = None if scale is None else scale.data_ptr()
@@ -187,12 +188,28 @@ def _conv_params(x: View, w_packed, scale, bias, y: View, *, k, stride, pad, act
 
 
 def nhwc_conv(x: View, w_packed: torch.Tensor, scale, bias, y: View, *, k, stride, pad, act, res: View = None,
-              upsample2x=False, out_f32=False, cout=None, x2: View = None, x_wts_raw=None) -> None:
+              upsample2x=False, out_f32=False, cout=None, x2: View = None, x_wts_raw=None, w_image_stride=0) -> None:
     """x2 / x_wts_raw: the convolution's input is sigmoid(w)[0] * x + sigmoid(w)[1] * x2 (WeightedFeatureFusion fused into
-    its consumer, build_utils/layers.py:63-85); see conv_dual_source_supported."""
+    its consumer, build_utils/layers.py:63-85); see conv_dual_source_supported.
+    w_image_stride != 0: w_packed holds one weight tensor per image, w_image_stride elements apart (a SqueezeExcitation
+    gate folded into the consuming 1x1 convolution, scale_weights_per_image); pass cout explicitly."""
     p = _conv_params(x, w_packed, scale, bias, y, k=k, stride=stride, pad=pad, act=act, res=res, upsample2x=upsample2x,
-                     out_f32=out_f32, cout=cout, x2=x2, x_wts_raw=x_wts_raw)
+                     out_f32=out_f32, cout=cout, x2=x2, x_wts_raw=x_wts_raw, w_image_stride=w_image_stride)
     nat.call("dyk_conv2d_fwd", C.byref(p), _stream())
+    nat.count_launches()
+
+
+def conv_gated_input_supported(H, W, Cin, *, k, stride, pad, upsample2x=False, out_f32=False) -> bool:
+    """Can a SqueezeExcitation gate be folded into this convolution's weights (per-image weights, dyk_conv_params.
+    w_image_stride)?  1x1 / stride 1 / pad 0 on maps large enough that one-image tiles of 128 pixels are not mostly padding."""
+    return k == 1 and stride == 1 and pad == 0 and not upsample2x and Cin % 8 == 0 and H * W >= 64
+
+
+def scale_weights_per_image(w_packed: torch.Tensor, gate: torch.Tensor, out: torch.Tensor) -> None:
+    """out[n] = w_packed * gate[n] (1x1 convolution weights [Cout][1][1][Cin]; gate (N, Cin) fp32)."""
+    Cout, Cin = w_packed.shape[0], w_packed.shape[-1]
+    nat.call("dyk_scale_weights_per_image", _p(w_packed), _p(gate), gate.shape[-1], _p(out), gate.shape[0], Cout, Cin,
+             _DT[w_packed.dtype], _stream())
     nat.count_launches()
 
 
@@ -227,9 +244,14 @@ def nhwc_dwconv(x: View, w_kkc, scale, bias, y: View, *, k, stride, pad, act) ->
     nat.count_launches()
 
 
-def nhwc_add(a: View, b: View, y: View, wts=None) -> None:
-    nat.call("dyk_fused_add", a.ptr, a.stride, b.ptr, b.stride, y.ptr, y.stride, a.npix, y.C, _p(wts), a.dt,
-             _stream())
+def nhwc_add(a: View, b: View, y: View, wts=None, gate=None) -> None:
+    """gate (N, C) fp32: operand a is seen through a SqueezeExcitation gate that was not materialised (dyk_fused_add_gated)."""
+    if gate is not None:
+        nat.call("dyk_fused_add_gated", a.ptr, a.stride, _p(gate), gate.shape[-1], a.H * a.W, b.ptr, b.stride, y.ptr, y.stride,
+                 a.npix, y.C, _p(wts), a.dt, _stream())
+    else:
+        nat.call("dyk_fused_add", a.ptr, a.stride, b.ptr, b.stride, y.ptr, y.stride, a.npix, y.C, _p(wts), a.dt,
+                 _stream())
     nat.count_launches()
 
 
@@ -250,6 +272,20 @@ def nhwc_maxpool(x: View, y: View, k, stride) -> None:
 
 def nhwc_upsample(x: View, y: View, s) -> None:
     nat.call("dyk_upsample_nearest", x.ptr, x.stride, y.ptr, y.stride, x.N, x.H, x.W, x.C, s, x.dt, _stream())
+    nat.count_launches()
+
+
+def nhwc_se_gate(x: View, w1, b1, w2, b2, pooled, gate) -> None:
+    """Only the gate of a SqueezeExcitation block (pool -> fc1 -> relu -> fc2 -> hardsigmoid, layers.py:184-189): gate[n, c];
+    the `scale * x` is applied by the consumers (per-image weights of nhwc_conv / nhwc_add gate)."""
+    nat.call("dyk_se_gate", x.ptr, x.stride, x.N, x.H * x.W, x.C, _p(w1), _p(b1), _p(w2), _p(b2), w1.shape[0],
+             _p(pooled), _p(gate), x.dt, _stream())
+    nat.count_launches(3)
+
+
+def scale_channels(x: View, gate: torch.Tensor, y: View) -> None:
+    """y = x * gate[n, c] (the last line of SqueezeExcitation.forward, layers.py:190)."""
+    nat.call("dyk_scale_channels", x.ptr, x.stride, _p(gate), y.ptr, y.stride, x.N, x.H * x.W, x.C, x.dt, _stream())
     nat.count_launches()
 
 

@@ -66,6 +66,7 @@ class ConvOp(Op):
         self.tag = tag
         self.src2 = None        # dual-source input: src = w0 * src + w1 * src2 (fused WeightedFeatureFusion)
         self.fusion = None      # ... and the module that owns the raw weights
+        self.gate_of = None     # SEOp whose gate multiplies src on the fly (fused SqueezeExcitation scale)
 
     @property
     def flavor(self):
@@ -78,7 +79,8 @@ class ConvOp(Op):
                               f"({c.in_channels}->{c.out_channels}) has no native kernel")
 
     def inputs(self):
-        return [self.src] + ([self.src2] if self.src2 is not None else []) + ([self.res] if self.res is not None else [])
+        return [self.src] + ([self.src2] if self.src2 is not None else []) + ([self.res] if self.res is not None else []) \
+            + ([self.gate_of.out] if self.gate_of is not None else [])      # (the gate: a virtual Value the SE op produces)
 
 
 class AddOp(Op):
@@ -86,9 +88,10 @@ class AddOp(Op):
 
     def __init__(self, layer, x, others, out, module):
         self.layer, self.x, self.others, self.out, self.module = layer, x, others, out, module
+        self.gate_of = None     # SEOp whose gate multiplies x on the fly
 
     def inputs(self):
-        return [self.x] + list(self.others)
+        return [self.x] + list(self.others) + ([self.gate_of.out] if self.gate_of is not None else [])
 
 
 class ConcatOp(Op):
@@ -127,6 +130,8 @@ class SEOp(Op):
 
     def __init__(self, layer, src, out, module):
         self.layer, self.src, self.out, self.module = layer, src, out, module
+        self.gate_only = False  # True: only gate[n, c] is computed; every consumer applies it while loading (fuse_se_gates)
+        self.gate = None
 
     def inputs(self):
         return [self.src]
@@ -302,6 +307,54 @@ def fuse_weighted_adds(ops_, B, dtype):
         out.virtual = True
         drop.add(id(op))
     return [op for op in ops_ if id(op) not in drop]
+
+
+def fuse_se_gates(ops_, B, dtype):
+    """SqueezeExcitation (layers.py:184-190) without its `scale * x` pass: when every consumer of an [se] block can take the
+    gate itself — a 1x1 convolution (conv(x * g_n) = x . (W * g_n): per-image weights, dyk_conv_params.w_image_stride) or
+    a [shortcut] whose first operand is the block's output (dyk_fused_add_gated) — the block only computes gate[n, c] and
+    the consumers read the block's INPUT.  The gated activation tensor (the largest tensor of the block) is never written
+    or re-read.  Rounding: a gated [shortcut] rounds x * g exactly like the materialised form; a gated convolution rounds
+    W * g_n instead of x * g_n (same error class; the oracle models it, oracle/darknet_ref.py `gated`)."""
+    if os.environ.get("DYK_FUSE_SE", "1") == "0":
+        return ops_
+    consumers = {}
+    for op in ops_:
+        for v in op.inputs():
+            consumers.setdefault(id(v), []).append(op)
+    for se in ops_:
+        if not isinstance(se, SEOp) or se.src.ext or se.src.f32:
+            continue
+        out, x = se.out, se.src
+        cons = consumers.get(id(out), [])
+        if not cons or out.uses != len(cons):
+            continue
+        ok = True
+        for c in cons:
+            if isinstance(c, ConvOp) and c.flavor == "dense" and c.src is out and c.res is not out and c.src2 is None \
+                    and c.gate_of is None:
+                k, s, p = c.conv.kernel_size[0], c.conv.stride[0], c.conv.padding[0]
+                ok = ok and ops.conv_gated_input_supported(x.H, x.W, x.C, k=k, stride=s, pad=p, upsample2x=c.upsample2x,
+                                                           out_f32=c.out_f32)
+            elif isinstance(c, AddOp) and c.x is out and len(c.others) == 1 and c.others[0] is not out and c.gate_of is None \
+                    and c.others[0].C == out.C:
+                pass
+            else:
+                ok = False
+            if not ok:
+                break
+        if not ok:
+            continue
+        for c in cons:
+            if isinstance(c, ConvOp):
+                c.src = x
+            else:
+                c.x = x
+            c.gate_of = se
+            x.uses += 1
+        out.virtual = True
+        se.gate_only = True
+    return ops_
 
 
 def cascade_pools(ops_):
@@ -498,7 +551,7 @@ class Plan:
         # fp32-accurate mode (compute_dtype = torch.float32, csrc/f32_path.cu): fp32 buffers, split-bf16 tensor-core convs,
         # no residual / upsample fusion into the conv epilogue (its fp32 store path is the plain one), one lane
         self.f32 = dtype == torch.float32
-        self.ops = raw if self.f32 else fuse_weighted_adds(fuse(raw), B, dtype)
+        self.ops = raw if self.f32 else fuse_se_gates(fuse_weighted_adds(fuse(raw), B, dtype), B, dtype)
         cascade_pools(self.ops)
         mark_heads(self.ops)
         place_concats(self.ops)
@@ -520,7 +573,7 @@ class Plan:
         order = []
         for k, op in enumerate(self.ops):
             v = getattr(op, "out", None)
-            if v is None:
+            if v is None or v.virtual:          # a virtual value (gate-only SE output) owns no buffer
                 continue
             root = v.place[0] if v.place else v
             if id(root) not in roots:
@@ -648,7 +701,12 @@ class Plan:
                               upsample2x=op.upsample2x, out_f32=op.out_f32)
                     if op.src2 is not None:
                         kw.update(x2=op.src2.view, x_wts_raw=op.fusion.w)
-                    self.steps.append(_ConvStep(op.src.view, e, op.out.view, kw))
+                    if op.gate_of is not None:       # SE gate folded into per-image weights (1x1): scale kernel + conv
+                        cout, cin = op.conv.out_channels, op.conv.in_channels
+                        wimg = torch.empty((self.B, cout, 1, 1, cin), dtype=self.dtype, device=dev)
+                        self.steps.append(_GatedConvStep(op.src.view, e, op.out.view, kw, op.gate_of, wimg))
+                    else:
+                        self.steps.append(_ConvStep(op.src.view, e, op.out.view, kw))
                 else:
                     self.steps.append(_Call(ops.nhwc_dwconv, op.src.view, e["w"], e["scale"], e["bias"], op.out.view,
                                             k=k, stride=s, pad=p, act=op.act))
@@ -670,7 +728,12 @@ class Plan:
                 self._se_holds = getattr(self, "_se_holds", []) + [hold]
                 pooled = torch.empty((self.B, 32, op.src.C), dtype=torch.float32, device=dev)   # DYK_SE_MAX_SLABS partials
                 gate = torch.empty((self.B, op.src.C), dtype=torch.float32, device=dev)
-                self.steps.append(_Call(ops.f32_se if self.f32 else ops.nhwc_se, op.src.view, op.out.view, w1, b1, w2, b2, pooled, gate))
+                op.gate = gate
+                if op.gate_only:       # every consumer applies the gate while it loads (fuse_se_gates)
+                    self.steps.append(_Call(ops.nhwc_se_gate, op.src.view, w1, b1, w2, b2, pooled, gate))
+                    self.steps[-1].launches = 3
+                else:
+                    self.steps.append(_Call(ops.f32_se if self.f32 else ops.nhwc_se, op.src.view, op.out.view, w1, b1, w2, b2, pooled, gate))
             elif isinstance(op, YoloOp):
                 m = op.module
                 ny, nx = op.src.H, op.src.W
@@ -705,7 +768,10 @@ class Plan:
                     f"layer {op.layer}: channel-mismatched / >2-way weighted shortcut is only available through "
                     "build_utils.layers.WeightedFeatureFusion.forward (no shipped cfg uses it)")
             dst = op.out.view if last else ops.new_view(self.B, x.H, x.W, x.C, self.dtype, self.device)
-            self.steps.append(_Call(ops.f32_add if self.f32 else ops.nhwc_add, cur, a.view, dst, wall))
+            if op.gate_of is not None and i == 0:
+                self.steps.append(_Call(ops.nhwc_add, cur, a.view, dst, wall, gate=op.gate_of.gate))
+            else:
+                self.steps.append(_Call(ops.f32_add if self.f32 else ops.nhwc_add, cur, a.view, dst, wall))
             cur = dst
 
     def refresh_se(self):
@@ -798,6 +864,22 @@ class _ConvStep:
     def __call__(self):
         e = self.e
         ops.nhwc_conv(self.x, e["w"], e["scale"], e["bias"], self.y, cout=e["conv"].out_channels, **self.kw)
+
+
+class _GatedConvStep(_ConvStep):
+    """1x1 convolution whose input carries a SqueezeExcitation gate: the gate is folded into per-image weights."""
+    launches = 2
+
+    def __init__(self, x, e, y, kw, se_op, wimg):
+        super().__init__(x, e, y, kw)
+        self.se_op, self.wimg = se_op, wimg
+
+    def __call__(self):
+        e = self.e
+        ops.scale_weights_per_image(e["w"], self.se_op.gate, self.wimg)
+        cout = e["conv"].out_channels
+        ops.nhwc_conv(self.x, self.wimg, e["scale"], e["bias"], self.y, cout=cout,
+                      w_image_stride=cout * e["conv"].in_channels, **self.kw)
 
 
 class PlanCache:

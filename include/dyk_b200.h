@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DYK_ABI_VERSION 5
+#define DYK_ABI_VERSION 6
 
 enum { DYK_F16 = 0, DYK_BF16 = 1 };
 
@@ -93,11 +93,21 @@ typedef struct dyk_conv_params {
   const void* x2;
   int64_t x2_pix_stride;
   const float* x_wts_raw;
+  /* ---- ABI v6 addition (zero = previous behaviour): per-image weights ----
+   * SqueezeExcitation.forward's `scale * x` (build_utils/layers.py:184-190) folded into the 1x1 convolution that consumes
+   * it: conv(x * gate[n]) = x . (W * gate[n]) — image n is convolved with its own weight tensor at w + n * w_image_stride
+   * (elements; a whole number >= Cout of [Cin]-rows), written by dyk_scale_weights_per_image.  The gated activation tensor
+   * is never written or read; tiles are kept inside one image.  1x1, stride 1, pad 0 only. */
+  int64_t w_image_stride;
 } dyk_conv_params;
 int dyk_conv2d_fwd(const dyk_conv_params* p, void* stream);
 /* 1 when dyk_conv2d_fwd accepts x2 != NULL for this layer (3x3, stride 1, pad 1, >= 256 output channels, Cin % 64 == 0:
  * the CTA-pair halo kernel), else 0.  Only the shape / flag fields of p are read. */
 int dyk_conv2d_dual_source_supported(const dyk_conv_params* p);
+/* out[n][co][ci] = round_dtype(w_packed[co][ci] * gate[n * gate_stride + ci]) for a 1x1 convolution's packed weights
+ * ([Cout][Cin], dtype): the per-image weights of dyk_conv_params.w_image_stride (= Cout * Cin here). */
+int dyk_scale_weights_per_image(const void* w_packed, const float* gate, int64_t gate_stride, void* out, int32_t N, int32_t Cout,
+                                int32_t Cin, int32_t dtype, void* stream);
 
 /* Diagnostics (no reference counterpart): when dev_counters != NULL, every later dyk_conv2d_fwd launch adds
  * its role-cycle counters into dev_counters[0..7] (device memory, 8 x uint64, caller zeroes them):
@@ -146,6 +156,11 @@ int dyk_dwconv2d_fwd(const void* x, int64_t x_pix_stride, const float* w, const 
 int dyk_fused_add(const void* a, int64_t a_pix_stride, const void* b, int64_t b_pix_stride, void* y,
                   int64_t y_pix_stride, int64_t npix, int32_t C, const float* wts, int32_t dtype,
                   void* stream);
+/* the same with operand a seen through a SqueezeExcitation gate that was not materialised (layers.py:184-190 followed by
+ * layers.py:63-85): a[n,h,w,c] * gate[n * gate_stride + c], rounded to the storage type, enters the sum in place of a. */
+int dyk_fused_add_gated(const void* a, int64_t a_pix_stride, const float* gate, int64_t gate_stride, int32_t HW, const void* b,
+                        int64_t b_pix_stride, void* y, int64_t y_pix_stride, int64_t npix, int32_t C, const float* wts,
+                        int32_t dtype, void* stream);
 /* w_out[i] = sigmoid(w_raw[i]) * 2 / n   (layers.py:66) */
 int dyk_fusion_weights(const float* w_raw, float* w_out, int32_t n, void* stream);
 

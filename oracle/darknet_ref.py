@@ -196,10 +196,23 @@ class DarknetRef:
             return F.batch_norm(x, rm, rv, w, b, True, mom, 1e-5)
         return F.batch_norm(x, rm, rv, w, b, False, 0.0, 1e-5)
 
-    def _conv_bn_act(self, x, st, pconv, pbn, stride, pad, groups, act, training, mom):
+    def _conv_bn_act(self, x, st, pconv, pbn, stride, pad, groups, act, training, mom, gate=None):
         w = st[pconv + ".weight"]
         if self._round is not None and groups == 1 and w.shape[1] > 4:
             w = w.to(self._round).float()   # dense tensor-core convs hold their weights in the 16-bit dtype
+        if gate is not None:
+            # storage-rounding model of a SqueezeExcitation gate folded into the consuming 1x1 convolution (dyk/plan.py
+            # fuse_se_gates): image n is convolved with its own weights round(W * gate[n]); x is the [se] block's INPUT
+            outs = []
+            for n in range(x.shape[0]):
+                wn = w * gate[n].reshape(1, -1, 1, 1)
+                if self._round is not None:
+                    wn = wn.to(self._round).float()
+                outs.append(F.conv2d(x[n:n + 1], wn, st.get(pconv + ".bias"), stride, pad, 1, groups))
+            x = torch.cat(outs, 0)
+            if pbn is not None:
+                x = self._bn(x, st, pbn, training, mom)
+            return activation(x, act)
         elif (self._round is not None and groups == 1 and tuple(w.shape) == (32, 3, 3, 3) and stride == 1 and pad == 1):
             # the 3 -> 32 stem runs on the tensor cores too (csrc/conv_stem_tc.cu): frames and weights are rounded to the
             # 16-bit type when the im2col rows are built; other stem shapes stay on the fp32 CUDA-core kernel
@@ -218,7 +231,8 @@ class DarknetRef:
 
     # -- models.py:279-315 -------------------------------------------------------------------------
     def forward(self, st: dict, x: torch.Tensor, y: torch.Tensor = None, training: bool = False,
-                bn_momentum=0.1, keep_layers: bool = False, round_dtype=None, unrounded=(), teacher=None):
+                bn_momentum=0.1, keep_layers: bool = False, round_dtype=None, unrounded=(), teacher=None, gated=None,
+                teacher_gates=None):
         """Returns what YOLO.forward returns: train -> [p...]; eval -> (cat(io, 1), (p...)).
         With keep_layers=True also returns the list of every layer's output (for per-layer checks).
 
@@ -234,6 +248,10 @@ class DarknetRef:
         rounding somewhere, and within ~5 layers two correct implementations sit a full rounding-noise floor
         apart), so end-to-end comparisons can only bound drift; the teacher-forced comparison is tight (<= 1-2 ulp
         of the storage type per layer) for every layer of the real network at its real shape."""
+        # gated ({conv layer: se layer}, from the native plan): those 1x1 convolutions read the [se] block's input and fold its
+        # gate into per-image weights instead of reading the gated tensor (same mathematics, rounding at another place)
+        gated = gated or {}
+        se_in, se_gate = {}, {}
         self._round = round_dtype
         rnd = (lambda t: t.to(round_dtype).float()) if round_dtype is not None else (lambda t: t)
         di = "second_index" in self.net and y is not None
@@ -249,8 +267,11 @@ class DarknetRef:
             pre = f"module_list.{i}"
             if t == "convolutional":
                 src = y if (di and i == self.net["second_index"]) else x
+                g = None
+                if i in gated:
+                    src, g = se_in[gated[i]], se_gate[gated[i]]
                 x = self._conv_bn_act(src, st, pre + ".Conv2d", pre + ".BatchNorm2d" if m["bn"] else None, m["stride"],
-                                      m["pad"], m["groups"], d["activation"], training, bn_momentum)
+                                      m["pad"], m["groups"], d["activation"], training, bn_momentum, gate=g)
             elif t == "depthwiseconvolutional":
                 c = x.shape[1]
                 x = rnd(self._conv_bn_act(x, st, pre + ".conv.0", pre + ".conv.1", m["stride"], 1, c, "relu6", training,
@@ -269,6 +290,13 @@ class DarknetRef:
                 s = F.adaptive_avg_pool2d(x, (1, 1))
                 s = F.relu(F.conv2d(s, st[pre + ".fc1.weight"], st[pre + ".fc1.bias"]))
                 s = F.hardsigmoid(F.conv2d(s, st[pre + ".fc2.weight"], st[pre + ".fc2.bias"]))
+                if teacher_gates is not None and i in teacher_gates:
+                    # teacher forcing of a gate-only block: its consumers are checked against the gate the native run used
+                    # (the gate itself is checked here, to fp32 accumulation order)
+                    tg = teacher_gates[i].reshape(s.shape)
+                    assert float((tg - s).abs().max()) < 2e-5, ("SE gate", i, float((tg - s).abs().max()))
+                    s = tg
+                se_in[i], se_gate[i] = x, s.flatten(1)
                 x = s * x
             elif t == "maxpool":
                 k = d["size"]

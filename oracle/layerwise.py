@@ -34,12 +34,21 @@ def native_layers(model):
     return got, unrounded
 
 
+def gated_convs(model):
+    """{conv layer index: se layer index} of the 1x1 convolutions that fold a SqueezeExcitation gate into per-image weights."""
+    plan = model._plans.last_plan
+    return {op.layer: op.gate_of.layer for op in plan.ops if getattr(op, "kind", "") == "conv" and getattr(op, "gate_of", None) is not None}
+
+
 def compare(model, ref, st, v, l, dtype):
     """Returns a list of per-layer records {layer, type, max_diff, over_2ulp, n, frac_diff, rel_rms}.
     v, l: the fp32 NCHW frames (already /255) the native run was given (l None for single-stream cfgs)."""
     got, unrounded = native_layers(model)
     with torch.no_grad():
-        _, every = ref.forward(st, v, l, keep_layers=True, round_dtype=dtype, unrounded=unrounded, teacher=got)
+        plan = model._plans.last_plan
+        gates = {op.layer: op.gate.float().cpu() for op in plan.ops if getattr(op, "kind", "") == "se" and getattr(op, "gate_only", False)}
+        _, every = ref.forward(st, v, l, keep_layers=True, round_dtype=dtype, unrounded=unrounded, teacher=got,
+                               gated=gated_convs(model), teacher_gates=gates)
     ulp = ULP[dtype]
     rows = []
     for i, nat_out in sorted(got.items()):

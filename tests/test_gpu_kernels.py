@@ -290,3 +290,57 @@ def test_weighted_fusion_fused_into_consumer_conv(shape, dtype):
                         * scale[:Cout].view(1, -1, 1, 1) + bias[:Cout].view(1, -1, 1, 1), 0.1)
     eps = 2e-3 if dtype == torch.float16 else 1.6e-2
     _close(ops.to_nchw(y1), want, rtol=eps, atol=eps, what=f"dual-source conv {shape} {dtype}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(3, 72, 10, 14, 24), (2, 120, 16, 20, 40), (4, 672, 8, 10, 112), (2, 960, 9, 8, 160),
+                                   (2, 1024, 16, 20, 512), (5, 64, 9, 9, 256)], ids=lambda s: "x".join(map(str, s)))
+def test_se_gate_folded_into_consumer_conv(shape, dtype):
+    """SqueezeExcitation's `scale * x` (layers.py:184-190) folded into the consuming 1x1 convolution as per-image weights:
+    conv(x * g_n) = x . (W * g_n).  Bit-identical to running the same kernel image by image with the scaled weights, and
+    within storage precision of conv(x * g) in fp32 (the reference's order)."""
+    from dyk import ops
+    from dyk.ops import View
+    N, Cin, H, W, Cout = shape
+    g = torch.Generator().manual_seed(Cin + 3 * Cout)
+    assert ops.conv_gated_input_supported(H, W, Cin, k=1, stride=1, pad=0)
+    assert not ops.conv_gated_input_supported(H, W, Cin, k=3, stride=1, pad=1)
+    xf = _q(torch.randn((N, Cin, H, W), generator=g), dtype).to(DEV)
+    x = ops.to_nhwc(xf, dtype)
+    gate = torch.rand((N, Cin), generator=g).to(DEV)
+    wf = _q(torch.randn((Cout, Cin, 1, 1), generator=g) / Cin ** 0.5, dtype).to(DEV)
+    w = ops.pack_conv_weight(wf, dtype)
+    scale = (torch.rand(1024, generator=g) + 0.5).to(DEV)
+    bias = (torch.randn(1024, generator=g) * 0.1).to(DEV)
+    wimg = torch.empty((N, Cout, 1, 1, Cin), dtype=dtype, device=DEV)
+    ops.scale_weights_per_image(w, gate, wimg)
+    assert torch.equal(wimg.view(N, Cout, Cin), (w.view(1, Cout, Cin).float() * gate.view(N, 1, Cin)).to(dtype))
+    y1 = ops.new_view(N, H, W, Cout, dtype, DEV)
+    ops.nhwc_conv(x, wimg, scale, bias, y1, k=1, stride=1, pad=0, act="hard-swish", cout=Cout, w_image_stride=Cout * Cin)
+    for n in range(N):                       # the same kernel, one image at a time, shared-weights path
+        xn = View(x.buf[n:n + 1], 0, Cin)
+        yn = ops.new_view(1, H, W, Cout, dtype, DEV)
+        ops.nhwc_conv(xn, wimg[n].contiguous(), scale, bias, yn, k=1, stride=1, pad=0, act="hard-swish")
+        assert torch.equal(y1.buf[n], yn.buf[0]), f"image {n}: per-image-weight convolution differs"
+    want = F.hardswish(F.conv2d(xf * gate.view(N, Cin, 1, 1), wf) * scale[:Cout].view(1, -1, 1, 1) + bias[:Cout].view(1, -1, 1, 1))
+    eps = 2e-3 if dtype == torch.float16 else 1.6e-2
+    _close(ops.to_nchw(y1), want, rtol=eps, atol=eps, what=f"gate folded into weights {shape} {dtype}")
+
+
+def test_se_gate_fused_into_weighted_shortcut():
+    """dyk_fused_add_gated == dyk_scale_channels followed by dyk_fused_add, bit for bit (weighted and plain)."""
+    from dyk import ops
+    g = torch.Generator().manual_seed(13)
+    N, C, H, W = 3, 96, 7, 9
+    x = ops.to_nhwc(_q(torch.randn((N, C, H, W), generator=g), torch.float16).to(DEV), torch.float16)
+    b = ops.to_nhwc(_q(torch.randn((N, C, H, W), generator=g), torch.float16).to(DEV), torch.float16)
+    gate = torch.rand((N, C), generator=g).to(DEV)
+    wall = torch.tensor([0.7, 1.2], device=DEV)
+    xs = ops.new_view(N, H, W, C, torch.float16, DEV)
+    ops.scale_channels(x, gate, xs)
+    for wts in (wall, None):
+        y1 = ops.new_view(N, H, W, C, torch.float16, DEV)
+        y2 = ops.new_view(N, H, W, C, torch.float16, DEV)
+        ops.nhwc_add(x, b, y1, wts, gate=gate)
+        ops.nhwc_add(xs, b, y2, wts)
+        assert torch.equal(y1.buf, y2.buf)
