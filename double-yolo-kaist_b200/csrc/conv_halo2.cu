@@ -375,6 +375,18 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(a_base + as * kH2ASlot);
           const int ksteps = kc == p.k_chunks - 1 ? p.k_last_steps : 4;
+          // descriptor of tap (0, 0); a tap only adds a compile-time row offset once the loop is unrolled (the issue loop
+          // is a chain of dependent uniform-datapath instructions: every one removed is ~7 cycles per tap)
+          uint64_t adesc0 = 0;
+          adesc0 |= static_cast<uint64_t>((sa & 0x3FFFF) >> 4);
+          adesc0 |= static_cast<uint64_t>(1) << 16;
+          adesc0 |= static_cast<uint64_t>((kH2HaloW * 128) >> 4) << 32;
+          adesc0 |= static_cast<uint64_t>(1) << 46;
+          adesc0 |= static_cast<uint64_t>(2) << 61;
+          // (unrolled only in the resident-weights variant, whose taps are a dozen instructions each once the slot index and
+          // the row offset are constants; for the streamed-weights variants the 9x larger loop body measured slightly slower)
+          constexpr int kTapUnroll = kResB ? 9 : 1;
+#pragma unroll kTapUnroll
           for (int tap = 0; tap < 9; ++tap) {
             if constexpr (kResB) {
               if (tl == 0) { H2WAIT(&b_full[tap], 0, w_data); tc_fence_after_sync(); }     // the filter arrives once
@@ -385,16 +397,18 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
             }
             const uint64_t bdesc = umma_desc_kmajor<128>(smem_u32(b_base + bs * kBSlotBytes));
             const int r = tap / 3, s = tap - 3 * r;
-            uint64_t adesc = 0;
-            adesc |= static_cast<uint64_t>(((sa + (r * kH2HaloW + s) * 128) & 0x3FFFF) >> 4);
-            adesc |= static_cast<uint64_t>(1) << 16;
-            adesc |= static_cast<uint64_t>((kH2HaloW * 128) >> 4) << 32;
-            adesc |= static_cast<uint64_t>(1) << 46;
-            adesc |= static_cast<uint64_t>(2) << 61;
+            // (the operand ring lies below 256 KB of shared memory: the 14-bit address field cannot carry into bit 16)
+            const uint64_t adesc = adesc0 + static_cast<uint64_t>(((r * kH2HaloW + s) * 128) >> 4);
             if (elect_one()) {
+              if (ksteps == 4) {           // the common case without per-MMA predicates (shorter dependent chain)
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (k < ksteps) umma_f16_ss_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                  umma_f16_ss_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (k < ksteps) umma_f16_ss_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              }
               if constexpr (!kResB) umma_commit_2sm(&b_empty[bs]);
             }
             __syncwarp();
