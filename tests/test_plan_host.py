@@ -64,3 +64,49 @@ def test_gradient_ready_schedule_covers_the_flat_buffer_once(name, dual):
     assert sum(hi - lo for lo, hi in red.sent) == plan.grad_numel
     if plan.grad_numel * 4 > 4 * (8 << 20):
         assert early >= 1, "no bucket was ready half-way through the backward pass"
+
+
+def _eval_ops(name, H=512, W=640, B=16, dtype=torch.float16):
+    from dyk import plan as P
+    m = _model(name, (H, W)).eval()
+    dual = "second_index" in m.net_info
+    raw, vals, _, _ = P.build_ops(m, H, W, dual)
+    ops_ = P.fuse_se_gates(P.fuse_weighted_adds(P.fuse(raw), B, dtype), B, dtype)
+    return P, ops_, vals
+
+
+def test_modality_fusion_moves_into_the_consuming_conv(native_lib):
+    """dyolov3_add_sl (the bench model): the three weighted [shortcut]s (visible + LWIR at strides 8 / 16 / 32,
+    layers.py:63-85) have a 3x3 stride-1 consumer each and disappear into it (dual-source operand); dyolov4_fshare's four
+    feed stride-2 convolutions and stay stand-alone."""
+    P, ops_, vals = _eval_ops("kaist_dyolov3_add_sl.cfg")
+    assert not [o for o in ops_ if isinstance(o, P.AddOp) and o.module.weight]
+    duals = [o for o in ops_ if isinstance(o, P.ConvOp) and o.src2 is not None]
+    assert [(o.src.C, o.src.H) for o in duals] == [(256, 64), (512, 32), (1024, 16)]
+    assert all(o.fusion.weight and o.conv.kernel_size == (3, 3) for o in duals)
+    assert sum(1 for v in vals if v is not None and v.virtual) == 3          # the three fused sums own no buffer
+    P, ops_, _ = _eval_ops("kaist_dyolov4_fshare_global_concat_se3.cfg")
+    assert len([o for o in ops_ if isinstance(o, P.AddOp) and o.module.weight]) == 4
+    # small maps (test sizes) fall below the sub-tile efficiency threshold: nothing is fused, nothing breaks
+    P, ops_, _ = _eval_ops("kaist_dyolov3_add_sl.cfg", 64, 96, 2)
+    assert len([o for o in ops_ if isinstance(o, P.AddOp) and o.module.weight]) + \
+        len([o for o in ops_ if isinstance(o, P.ConvOp) and o.src2 is not None]) == 3
+
+
+@pytest.mark.parametrize("name,blocks", [("kaist_dyolov4_fshare_global_concat_se3.cfg", 3),
+                                         ("kaist_dyolov4_mobilenetv3_fshare_global_cse3.cfg", 19)])
+def test_se_blocks_hand_their_gate_to_the_consumers(native_lib, name, blocks):
+    """Every [se] block of the two BASELINE models that have them computes only its gate (layers.py:184-189); the
+    `scale * x` (:190) is applied by the consumers, which read the block's input."""
+    P, ops_, _ = _eval_ops(name)
+    ses = [o for o in ops_ if isinstance(o, P.SEOp)]
+    assert len(ses) == blocks and all(o.gate_only and o.out.virtual for o in ses)
+    for se in ses:
+        cons = [o for o in ops_ if getattr(o, "gate_of", None) is se]
+        assert cons, "a gate-only block without a consumer"
+        for c in cons:
+            if isinstance(c, P.ConvOp):
+                assert c.src is se.src and c.conv.kernel_size == (1, 1)
+            else:
+                assert isinstance(c, P.AddOp) and c.x is se.src
+        assert not [o for o in ops_ if se.out in o.inputs() and getattr(o, "gate_of", None) is not se]
