@@ -226,7 +226,9 @@ conv3x3_halo_kernel(const __grid_constant__ HaloTmaps tm, const HaloKArgs p) {
   uint64_t* tempty = tfull + 2;                     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp_idx = threadIdx.x >> 5;
+  // warp index through a shuffle (as CUTLASS' canonical_warp_idx_sync): the compiler then knows it is warp-uniform and keeps
+  // everything derived from it (role, TMEM lane quarter, staging addresses, TMA-store operands) in uniform registers
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (warp_idx == 0 && lane == 0) {

@@ -263,7 +263,9 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
   uint64_t* a_raw = tempty + 2;                     // [2]  (per CTA; dual source: both halo windows landed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_raw + kH2MaxAStages);
 
-  const int warp_idx = threadIdx.x >> 5;
+  // warp index through a shuffle (as CUTLASS' canonical_warp_idx_sync): the compiler then knows it is warp-uniform and keeps
+  // everything derived from it (role, TMEM lane quarter, staging addresses, TMA-store operands) in uniform registers
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;

@@ -37,7 +37,7 @@ stem_tc_kernel(const TIn* __restrict__ x, const float* __restrict__ w /* [32][3]
   __shared__ uint64_t mma_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float ssc[32], sbi[32];
-  const int t = threadIdx.x, warp = t >> 5;
+  const int t = threadIdx.x, warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // (warp-uniform for the compiler)
   constexpr int kCin = 3;                              // the only stem shape routed here (K = 27 padded to 32)
   constexpr int KK = 9 * kCin;
   (void)Cin;

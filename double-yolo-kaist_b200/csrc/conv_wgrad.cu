@@ -90,7 +90,9 @@ conv_wgrad_kernel(const __grid_constant__ WgradTmaps tm, const WgradKArgs p) {
   uint64_t* done_bar = bars + 2 * kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
 
-  const int warp_idx = threadIdx.x >> 5;
+  // warp index through a shuffle (as CUTLASS' canonical_warp_idx_sync): the compiler then knows it is warp-uniform and keeps
+  // everything derived from it (role, TMEM lane quarter, staging addresses, TMA-store operands) in uniform registers
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   // work item: (co block, ci block, tap group, split)
