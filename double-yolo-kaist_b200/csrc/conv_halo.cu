@@ -244,7 +244,7 @@ conv3x3_halo_kernel(const __grid_constant__ HaloTmaps tm, const HaloKArgs p) {
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // (same value in every lane: tell the compiler)
   griddep_wait();   // PDL: everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp_idx == 0) {

@@ -293,7 +293,7 @@ conv3x3_halo2_kernel(const __grid_constant__ Halo2Tmaps tm, const Halo2KArgs p) 
   __syncthreads();         // (the cluster barrier below already orders the CTA; this one is what compute-sanitizer models)
   cluster_sync_all();      // barriers of both CTAs initialised before any remote arrive / TMA credit
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // (same value in every lane: tell the compiler)
   griddep_wait();   // PDL: everything above overlapped the previous kernel's tail; its results are visible from here on
   stamp(-1, 10);
 

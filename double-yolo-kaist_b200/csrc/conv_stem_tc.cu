@@ -72,7 +72,7 @@ stem_tc_kernel(const TIn* __restrict__ x, const float* __restrict__ w /* [32][3]
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
   uint32_t phase = 0;
   for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int tw = (int)(tile % tiles_w);

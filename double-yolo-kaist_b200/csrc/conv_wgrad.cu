@@ -116,7 +116,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradTmaps tm, const WgradKArgs p) {
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // (same value in every lane: tell the compiler)
 
   if (warp_idx == 0) {
     {   // TMA producer: whole warp in the loop, one elected lane issues (uniform-register operands)
