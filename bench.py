@@ -176,6 +176,10 @@ def conv_breakdown(plan, x, y, iters=3):
     per = []
     for it in range(iters + 1):
         plan.run_stems(x, y)
+        # keep the device busy (~6 ms) while the host enqueues the ~140 bracketed launches: each launch costs ~18 us of host
+        # work (ctypes + tensor-map encoding), and with an empty queue that host time would sit inside the event bracket
+        # (tools/chain_bench.py: 58.9 us eager bracket vs 40.8 us per launch inside a graph for the same kernel)
+        torch.cuda._sleep(12_000_000)
         evs = []
         for s in plan.steps:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -544,12 +548,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    debug = os.environ.get("DYK_BENCH_DEBUG") == "1"
+
     def timed(fn, steps, d2h=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        marks, host = [], []
         for i in range(steps):
+            t0 = time.perf_counter()
             fn(i)
+            if debug:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append(ev)
+                host.append((time.perf_counter() - t0) * 1e3)
+        if debug and rank == 0:
+            torch.cuda.synchronize()
+            dev_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+            print("DEBUG", fn.__name__, "host ms/step", [round(h, 2) for h in host], "device ms between step ends",
+                  [round(d, 2) for d in dev_ms], file=sys.stderr, flush=True)
         last = (pipe_h if d2h else pipe).flush()   # the last batch's NMS (and read-back) belongs to the timed region
         if d2h and last is not None:
             int(last[1].sum())
@@ -582,6 +600,13 @@ def main():
     pipe_h.flush()
     pipe._staged = None
     pipe_h._staged = None
+    torch.cuda.synchronize()
+    # back to the device-resident loop for a few untimed steps: the first resident steps after the e2e warm-up were seen (one
+    # box in four) to run host-bound at ~7.8 ms per step for both models alike while the allocator pools of the three
+    # streams re-balance; the same loop is fast again in the sustained leg
+    for i in range(8):
+        step_resident(i)
+    pipe.flush()
     torch.cuda.synchronize()
     sampler.mark()
     l0 = nat.launch_count()
@@ -636,8 +661,9 @@ def main():
                                    "output channels, the dual-source modality-fusion convs and the resident-weights early "
                                    "layers): the dominant kernel of the step by time",
                          "note": "a launch = one layer, so figures are sums over the kernel's launches of one step: "
-                                 "achieved = algorithmic FLOPs / summed CUDA-event durations (each launch bracketed on "
-                                 "the launching stream, run eagerly, so launch latency is inside the brackets); traffic = "
+                                 "achieved = algorithmic FLOPs / summed CUDA-event durations (each launch bracketed by events on "
+                                 "the launching stream in an eager single-stream pass that is enqueued behind a ~6 ms device-side "
+                                 "sleep, so the brackets hold device time, not the host's per-launch work); traffic = "
                                  "ncu dram__bytes_read.sum + dram__bytes_write.sum of the same launches "
                                  f"({TRAFFIC_PROFILE})",
                          "launches_per_step": dom["n"], "kernel_ms_per_step": dom["ms"],
