@@ -176,10 +176,10 @@ def conv_breakdown(plan, x, y, iters=3):
     per = []
     for it in range(iters + 1):
         plan.run_stems(x, y)
-        # keep the device busy (~6 ms) while the host enqueues the ~140 bracketed launches: each launch costs ~18 us of host
+        # keep the device busy (~20 ms) while the host enqueues the ~140 bracketed launches: each launch costs ~18 us of host
         # work (ctypes + tensor-map encoding), and with an empty queue that host time would sit inside the event bracket
         # (tools/chain_bench.py: 58.9 us eager bracket vs 40.8 us per launch inside a graph for the same kernel)
-        torch.cuda._sleep(12_000_000)
+        torch.cuda._sleep(40_000_000)
         evs = []
         for s in plan.steps:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -662,7 +662,7 @@ def main():
                                    "layers): the dominant kernel of the step by time",
                          "note": "a launch = one layer, so figures are sums over the kernel's launches of one step: "
                                  "achieved = algorithmic FLOPs / summed CUDA-event durations (each launch bracketed by events on "
-                                 "the launching stream in an eager single-stream pass that is enqueued behind a ~6 ms device-side "
+                                 "the launching stream in an eager single-stream pass that is enqueued behind a ~20 ms device-side "
                                  "sleep, so the brackets hold device time, not the host's per-launch work); traffic = "
                                  "ncu dram__bytes_read.sum + dram__bytes_write.sum of the same launches "
                                  f"({TRAFFIC_PROFILE})",
