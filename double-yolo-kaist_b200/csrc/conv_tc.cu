@@ -62,6 +62,7 @@ struct ConvKArgs {
   long long res_pix_stride;
   unsigned long long* prof;        // optional role-cycle counters (dyk_conv_set_profile), may be null
   int res_pf;                      // residual L2 prefetch mode (conv_common.cuh)
+  int flat;                        // 1x1 stride-1 convolution run as a GEMM over the flattened pixel index (tw = 128)
   int b_img_rows;                  // per-image weights (SE gate folded into the consumer): weight rows per image, 0 = shared
 };
 
@@ -110,6 +111,19 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord tile_coord(const ConvKArgs& p, int tile) {
   TileCoord t;
+  if (p.flat) {      // 1x1 convolutions over the flattened pixel index: no spatial decomposition (three dependent
+    t.h0 = 0;        // multiply-high chains per tile and role otherwise, ~6 % of the epilogue's stall samples on short tiles)
+    t.n0 = 0;
+    if (p.n_blocks == 1) {
+      t.nblk = 0;
+      t.w0 = tile << 7;
+    } else {
+      const unsigned m = fd_div((unsigned)tile, p.fd_nblocks);
+      t.nblk = tile - (int)(m * p.fd_nblocks.div);
+      t.w0 = (int)m << 7;
+    }
+    return t;
+  }
   const unsigned mt = fd_div((unsigned)tile, p.fd_nblocks);
   t.nblk = tile - (int)(mt * p.fd_nblocks.div);
   const unsigned rowt = fd_div(mt, p.fd_tiles_w);            // tile row index over (tiles_h * tiles_b)
@@ -948,6 +962,7 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   }
 
   ka.tw = tw; ka.th = th; ka.tn = tn;
+  ka.flat = flat ? 1 : 0;
   ka.tiles_w = ceil_div(gW, tw); ka.tiles_h = ceil_div(gH, th); ka.tiles_b = ceil_div(gN, tn);
   ka.n_blocks = ceil_div(p->Cout_store, BN);
   for (ka.tw_log2 = 0; (1 << ka.tw_log2) < tw; ++ka.tw_log2) {}
