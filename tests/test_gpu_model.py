@@ -131,6 +131,28 @@ def test_model_full_size_vs_oracle(native_lib, name, monkeypatch):
             assert np.array_equal(a.cpu().numpy(), b)
 
 
+@pytest.mark.parametrize("name,B", [("kaist_dyolov3_add_sl.cfg", 16), ("kaist_dyolov4_fshare_global_concat_se3.cfg", 16),
+                                    ("kaist_dyolov4_mobilenetv3_fshare_global_cse3.cfg", 64)])
+def test_bench_shape_batch_equals_small_batches(native_lib, name, B):
+    """The BASELINE batch sizes (16 / 64 paired frames at 512x640: the shapes bench.py runs, with their own tile counts,
+    partial last rounds, two-lane CUDA graph and buffer recycling) give, frame for frame and BIT FOR BIT, what the batch-2
+    plan gives — the shape whose every layer is checked against the oracle above.  Every output element sums its products
+    in the same order whatever the tiling, so any difference would be an indexing / scheduling / aliasing bug."""
+    m, _, _ = _build(name, 512, 640)
+    g = torch.Generator().manual_seed(11)
+    v = torch.randint(0, 256, (B, 3, 512, 640), dtype=torch.uint8, generator=g).to(DEV)
+    l = torch.randint(0, 256, (B, 3, 512, 640), dtype=torch.uint8, generator=g).to(DEV)
+    with torch.no_grad():
+        io_big, p_big = m(v, l)
+        io_big2, _ = m(v, l)                     # second call replays the captured graph
+        assert torch.equal(io_big, io_big2)
+        for k in range(0, B, 2):
+            io_s, p_s = m(v[k:k + 2], l[k:k + 2])
+            assert torch.equal(io_big[k:k + 2], io_s), (name, "frames", k, k + 1)
+            for a, b in zip(p_big, p_s):
+                assert torch.equal(a[k:k + 2], b)
+
+
 def test_weights_refresh_after_inplace_update(native_lib):
     m, ref, st = _build("kaist_yolov3.cfg", 64, 96)
     v, _ = _frames(False, 1, 64, 96)
