@@ -485,6 +485,7 @@ class TrainPlan:
             for v in op.inputs():
                 consumers.setdefault(id(v), []).append(op)
         grads = {}
+        self.aux_bwd = []
 
         def gslot(v):
             g = grads.get(id(v))
@@ -564,6 +565,7 @@ class TrainPlan:
                 self._conv_bwd(st, dy, claim if not st["stem"] else None)
             elif isinstance(op, P.AddOp):
                 m = op.module
+                self.aux_bwd.append(("add", op, dy))      # (diagnostics: oracle/layerwise.compare_backward_aux)
                 for i, operand in enumerate([op.x, op.others[0]]):
                     gv, acc = claim(operand)
                     self.bwd.append(lambda flat, dps, d=dy, g=gv, a=acc, o=op, i=i:
@@ -589,6 +591,7 @@ class TrainPlan:
                 self.bwd.append(lambda flat, dps, o=op, d=dy, g=gv, a=acc: T.upsample_bwd(d, g, o.s, a))
             elif isinstance(op, P.SEOp):
                 gv, acc = claim(op.src)
+                self.aux_bwd.append(("se", op, dy))
 
                 def se(flat, dps, o=op, d=dy, g=gv, a=acc):
                     m = o.module

@@ -155,3 +155,43 @@ def compare_backward(plan, frames):
             row["dx"] = rel(_nchw(st["gin"][0]), x_grad)
         rows.append(row)
     return rows
+
+
+def compare_backward_aux(plan):
+    """Teacher-forced check of the parameter gradients that do not belong to a convolution block: the fusion weights `w` of
+    weighted [shortcut]s (build_utils/layers.py:63-85) and the fc1 / fc2 parameters of [se] blocks (layers.py:175-190).
+    As in compare_backward, the oracle recomputes the op in fp32 torch from the *native* operands, back-propagates the
+    native gradient dy of the op's output with autograd and compares the parameter gradients the native backward wrote into
+    the flat gradient buffer.  Returns [{layer, kind, <param>: relative L2 error}]."""
+    import torch.nn.functional as F
+    flat = plan.last_flat
+    rows = []
+
+    def rel(got, want):
+        return float((got.detach().float().cpu().reshape(want.shape) - want).norm() / (want.norm() + 1e-20))
+
+    for kind, op, dy_view in plan.aux_bwd:
+        dy = _nchw(dy_view)
+        if kind == "add":
+            m = op.module
+            if not m.weight:
+                continue
+            x, a = _nchw(op.x.view), _nchw(op.others[0].view)
+            w = m.w.detach().float().cpu().clone().requires_grad_(True)
+            ws = torch.sigmoid(w) * (2 / 2)
+            (x * ws[0] + a * ws[1]).backward(dy)
+            rows.append(dict(layer=op.layer, kind="shortcut.w", w=rel(plan._pgrad(flat, m.w), w.grad)))
+        else:
+            m = op.module
+            x = _nchw(op.src.view)
+            prm = {n: getattr(getattr(m, f), k).detach().float().cpu().clone().requires_grad_(True)
+                   for n, (f, k) in dict(w1=("fc1", "weight"), b1=("fc1", "bias"), w2=("fc2", "weight"), b2=("fc2", "bias")).items()}
+            s_ = F.adaptive_avg_pool2d(x, (1, 1))
+            s_ = F.relu(F.conv2d(s_, prm["w1"], prm["b1"]))
+            s_ = F.hardsigmoid(F.conv2d(s_, prm["w2"], prm["b2"]))
+            (s_ * x).backward(dy)
+            rows.append(dict(layer=op.layer, kind="se", fc1_w=rel(plan._pgrad(flat, m.fc1.weight), prm["w1"].grad),
+                             fc1_b=rel(plan._pgrad(flat, m.fc1.bias), prm["b1"].grad),
+                             fc2_w=rel(plan._pgrad(flat, m.fc2.weight), prm["w2"].grad),
+                             fc2_b=rel(plan._pgrad(flat, m.fc2.bias), prm["b2"].grad)))
+    return rows

@@ -33,6 +33,21 @@ def _teacher_forced(tol):
     return rows
 
 
+def _teacher_forced_aux(tol, expect):
+    """Fusion weights of the weighted shortcuts and SE fc parameters: native gradients against autograd of the same op on
+    the native operands (oracle/layerwise.compare_backward_aux)."""
+    from oracle import layerwise
+    from oracle.train_check import LAST
+    rows = layerwise.compare_backward_aux(LAST["plan"])
+    kinds = sorted({r["kind"] for r in rows})
+    assert kinds == sorted(expect), (kinds, expect)
+    for r in rows:
+        for k, v in r.items():
+            if k not in ("layer", "kind"):
+                assert v < tol, ("teacher-forced backward (shortcut / se parameters)", r)
+    return rows
+
+
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_tiny_net_training_step(native_lib, dtype):
     from oracle.train_check import run
@@ -58,6 +73,8 @@ def test_baseline_models_training_step(native_lib, name, dtype):
     assert all(r == r and r < 10 for _, r, _ in rows), "non-finite gradient"
     assert max(e for _, e in stats) < (0.05 if dtype == torch.float16 else 0.3), ("running statistics drift", max(e for _, e in stats))
     _teacher_forced(1e-3 if dtype == torch.float16 else 6e-3)
+    # the parameters outside the convolution blocks: 3 fusion weights (dyolov3_add_sl) / 4 fusion weights + 3 SE blocks (dyolov4)
+    _teacher_forced_aux(2e-3 if dtype == torch.float16 else 1e-2, ["shortcut.w"] if "dyolov3" in name else ["se", "shortcut.w"])
 
 
 def test_training_is_deterministic_and_updates_eval(native_lib):
