@@ -18,7 +18,7 @@
 //
 // Dual-source variant (kDual; WeightedFeatureFusion, build_utils/layers.py:63-85, fused into the convolution that
 // consumes it): the A operand is w0 * x + w1 * x2, formed in shared memory.  Each CTA's producer loads the halo windows
-// of BOTH tensors (same box, same swizzle, so element i of one slot corresponds to element i of the other) and four extra
+// of BOTH tensors (same box, same swizzle, so element i of one slot corresponds to element i of the other) and eight extra
 // "combiner" warps overwrite the x slot with the rounded weighted sum — once per 64-channel chunk, for all nine taps —
 // then publish it to the MMA issuer (fence.proxy.async + arrive on the leader's "full" barrier).  The fused sum is never
 // written to memory: both modality tensors are read once.  The two extra halo slots are paid for with three weight stages.
@@ -97,7 +97,7 @@ constexpr int kH2VecFloats = 2 * kH2BlockN;
 constexpr int kH2VecBytes = kH2EpiWarps * kH2VecFloats * 4;
 constexpr int kH2Total = kH2AStages * kH2ASlot + kH2BStages * kH2BSlot + kH2StagingBytes + kH2VecBytes + 1024 + 1024;
 static_assert(kH2Total <= 227 * 1024, "halo2 shared memory budget");
-constexpr int kH2CombWarps = 4;                                // dual-source variant: combiner warps per CTA
+constexpr int kH2CombWarps = 8;                                // dual-source variant: combiner warps per CTA
 constexpr int kH2BStagesDual = 5;
 constexpr int kH2TotalDual = 2 * kH2AStages * kH2ASlot + kH2BStagesDual * kH2BSlot + kH2StagingBytes + kH2VecBytes + 1024 + 1024;
 static_assert(kH2TotalDual <= 227 * 1024, "halo2 (dual source) shared memory budget");

@@ -16,7 +16,14 @@ SHAPES = [  # (N, Cin, H, W, Cout, k, res)
     (16, 256, 64, 80, 128, 1, False), (16, 512, 32, 40, 256, 1, False), (16, 1024, 16, 20, 512, 1, False),
     (16, 128, 64, 80, 256, 3, True), (16, 256, 32, 40, 512, 3, True), (16, 512, 16, 20, 1024, 3, True),
     (16, 64, 256, 320, 32, 1, False), (16, 32, 256, 320, 64, 3, True), (16, 64, 128, 160, 128, 3, True),
+    # CSPDarknet53 (dyolov4_fshare) residual stages
+    (16, 128, 64, 80, 128, 3, True), (16, 256, 32, 40, 256, 3, True), (16, 512, 16, 20, 512, 3, True),
+    (16, 64, 256, 320, 64, 1, False), (16, 128, 128, 160, 128, 1, False), (16, 256, 64, 80, 256, 1, False),
 ]
+SHAPES += [(16, 256, 64, 80, 256, 3, False), (16, 512, 32, 40, 512, 3, False), (16, 1024, 16, 20, 1024, 3, False)]   # 15-17: the fusion convs
+DUAL = os.environ.get("DYK_CHAIN_DUAL") == "1"      # run them with the dual-source operand (fused modality fusion)
+if os.environ.get("DYK_CHAIN_ONLY"):
+    SHAPES = [SHAPES[int(i)] for i in os.environ["DYK_CHAIN_ONLY"].split(",")]
 n = 40
 for (N, Cin, H, W, Cout, k, res) in SHAPES:
     x = View(torch.randn((N, H, W, Cin), device="cuda").to(dt), 0, Cin)
@@ -24,7 +31,10 @@ for (N, Cin, H, W, Cout, k, res) in SHAPES:
     r = View(torch.randn((N, H, W, Cout), device="cuda").to(dt), 0, Cout) if res else None
     w = (torch.randn((Cout, k, k, Cin), device="cuda") / (Cin * k * k) ** 0.5).to(dt)
     sc, bi = torch.ones(2048, device="cuda"), torch.zeros(2048, device="cuda")
-    run = lambda i: ops.nhwc_conv(x, w, sc, bi, ys[i & 1], k=k, stride=1, pad=k // 2, act="leaky", res=r)
+    kw = {}
+    if DUAL and k == 3 and not res and Cout >= 256:
+        kw = dict(x2=View(torch.randn((N, H, W, Cin), device="cuda").to(dt), 0, Cin), x_wts_raw=torch.tensor([0.3, -0.2], device="cuda"))
+    run = lambda i: ops.nhwc_conv(x, w, sc, bi, ys[i & 1], k=k, stride=1, pad=k // 2, act="leaky", res=r, **kw)
     for i in range(3):
         run(i)
     torch.cuda.synchronize()
