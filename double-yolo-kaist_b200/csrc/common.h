@@ -47,6 +47,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn get_encode_tiled();
 
 int num_sms();
+// SMs a convolution launch may occupy (dyk_conv_params.sm_limit; even, >= 2)
+static inline int sm_budget(int sm_limit) {
+  const int all = num_sms();
+  if (sm_limit <= 0 || sm_limit >= all) return all;
+  return sm_limit < 2 ? 2 : (sm_limit & ~1);
+}
 
 // Launch with programmatic stream serialization: the kernel may begin (prologue only — it calls griddepcontrol.wait before
 // touching global data) while the tail of the previous kernel in the stream is still running.  DYK_PDL=0 disables it.

@@ -50,6 +50,7 @@ struct HaloKArgs {
   const void* res;              // may be null
   long long res_pix_stride;
   unsigned long long* prof;     // role-cycle counters (-DDYK_CONV_PROFILE builds only), may be null
+  int grid_cap;                 // SM budget of this launch (sm_budget)
   int res_pf;                   // residual L2 prefetch mode (conv_common.cuh)
 };
 
@@ -425,7 +426,7 @@ static int launch_halo(const HaloTmaps& tm, const HaloKArgs& ka, cudaStream_t st
     DYK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
-  const int grid = ka.num_tiles < num_sms() ? ka.num_tiles : num_sms();
+  const int grid = ka.num_tiles < ka.grid_cap ? ka.num_tiles : ka.grid_cap;
   DYK_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kHaloThreads), S::kTotal, stream, tm, ka));
   DYK_LAUNCH_OK("conv3x3_halo_kernel");
   return DYK_OK;
@@ -458,7 +459,7 @@ int conv3x3_halo_try(const dyk_conv_params* p, cudaStream_t stream) {
   if (force_bn == 64 || force_bn == 128 || force_bn == 256) BN = force_bn;
   const int n_blocks = ceil_div(p->Cout_store, BN);
   const int k_chunks = ceil_div(p->Cin, 64);
-  const int kSub = BN == 256 ? 1 : ((ceil_div64(num_subs, 2) * n_blocks >= num_sms()) ? 2 : 1);
+  const int kSub = BN == 256 ? 1 : ((ceil_div64(num_subs, 2) * n_blocks >= sm_budget(p->sm_limit)) ? 2 : 1);
 
   HaloTmaps tm;
   HaloKArgs ka;
@@ -499,6 +500,7 @@ int conv3x3_halo_try(const dyk_conv_params* p, cudaStream_t stream) {
   ka.scale = p->scale; ka.bias = p->bias;
   ka.res = p->res; ka.res_pix_stride = p->res_pix_stride;
   ka.prof = g_conv_prof;
+  ka.grid_cap = sm_budget(p->sm_limit);
   ka.res_pf = res_prefetch_mode();
 
   const bool bf = p->dtype == DYK_BF16;

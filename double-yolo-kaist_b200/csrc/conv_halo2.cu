@@ -64,6 +64,7 @@ constexpr bool kH2Prof = false;
 struct Halo2KArgs {
   unsigned long long* prof;
   int res_pf;                   // residual L2 prefetch mode (conv_common.cuh)
+  int cluster_cap;              // SM pairs this launch may occupy (sm_budget / 2)
   int H, W, N;
   int num_subs;
   int n_blocks, num_tiles;      // pair tiles = ceil(num_subs / 2) * n_blocks, n-block fastest
@@ -567,7 +568,7 @@ static int launch_halo2(const Halo2Tmaps& tm, const Halo2KArgs& ka, cudaStream_t
     DYK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
-  int clusters = num_sms() / 2;
+  int clusters = ka.cluster_cap;
   if (ka.num_items < clusters) clusters = ka.num_items;
   DYK_CUDA_OK(launch_pdl(kern, dim3(2 * clusters), dim3(kH2Threads + (kDual ? 32 * kH2CombWarps : 0)), (size_t)kSmem, stream, tm, ka));
   DYK_LAUNCH_OK("conv3x3_halo2_kernel");
@@ -653,7 +654,8 @@ int conv3x3_halo2_try(const dyk_conv_params* p, cudaStream_t stream) {
     // full barrier -> MMA -> commit -> empty barrier), so narrowing N barely shortens it.  Worth 2 us on the 55 us
     // layers (256->512 @32x40: 57.3 -> 55.3 us); the real fix for the partial round is a split along K.
     static const int force = getenv("DYK_H2_TAIL") ? atoi(getenv("DYK_H2_TAIL")) : 0;   // 1, 2, 4 force; 0 = cost model
-    const int clusters = num_sms() / 2;
+    const int clusters = sm_budget(p->sm_limit) / 2;
+    ka.cluster_cap = clusters;
     const int tail = resident ? 0 : ka.num_tiles % clusters;
     int lg = 0;
     if (tail > 0) {

@@ -62,6 +62,7 @@ struct ConvKArgs {
   long long res_pix_stride;
   unsigned long long* prof;        // optional role-cycle counters (dyk_conv_set_profile), may be null
   int res_pf;                      // residual L2 prefetch mode (conv_common.cuh)
+  int grid_cap;                    // SM budget of this launch (sm_budget)
   int flat;                        // 1x1 stride-1 convolution run as a GEMM over the flattened pixel index (tw = 128)
   int b_img_rows;                  // per-image weights (SE gate folded into the consumer): weight rows per image, 0 = shared
 };
@@ -734,7 +735,7 @@ static int launch_conv(const ConvTmaps& tm, const ConvKArgs& ka, cudaStream_t st
     DYK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
-  int grid = ka.num_tiles < num_sms() ? ka.num_tiles : num_sms();
+  int grid = ka.num_tiles < ka.grid_cap ? ka.num_tiles : ka.grid_cap;
   DYK_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(num_threads<kSplit>()), S::kTotal, stream, tm, ka));
   DYK_LAUNCH_OK("conv_tc_kernel");
   return DYK_OK;
@@ -760,8 +761,7 @@ static int dispatch_n(int block_n, int split, const ConvTmaps& tm, const ConvKAr
 
 // Picks the N tile by a small cycle model: a k-block costs max(MMA issue, L2->SM operand fetch at ~42 B/clk/SM),
 // a tile adds a fixed epilogue/hand-off cost, and the grid runs in waves over the SMs.
-static int pick_block_n(int cout_store, long long m_tiles, int num_kb, int block_k) {
-  const int sms = num_sms();
+static int pick_block_n(int cout_store, long long m_tiles, int num_kb, int block_k, int sms) {
   int best_n = 32;
   double best_cost = 1e30;
   const int cands[4] = {256, 128, 64, 32};
@@ -912,7 +912,7 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
   const int taps = pair_w ? 6 : p->kh * p->kw;
   const int cin_eff = pair_w ? 64 : p->Cin;
   const long long m_tiles = (long long)ceil_div(gW, tw) * ceil_div(gH, th) * ceil_div(gN, tn);
-  int BN = pick_block_n(p->Cout_store, m_tiles, taps * ceil_div(cin_eff, BK), BK);
+  int BN = pick_block_n(p->Cout_store, m_tiles, taps * ceil_div(cin_eff, BK), BK, sm_budget(p->sm_limit));
   const bool acc32 = p->out_f32 == 2;
   if (acc32) BN = 64;      // 2 x 32 register accumulators per epilogue thread
   // 16 epilogue warps when the tile time is the epilogue's: short main loop (<= 16 k-blocks) and an activation that costs
@@ -963,6 +963,7 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
 
   ka.tw = tw; ka.th = th; ka.tn = tn;
   ka.flat = flat ? 1 : 0;
+  ka.grid_cap = sm_budget(p->sm_limit);
   ka.tiles_w = ceil_div(gW, tw); ka.tiles_h = ceil_div(gH, th); ka.tiles_b = ceil_div(gN, tn);
   ka.n_blocks = ceil_div(p->Cout_store, BN);
   for (ka.tw_log2 = 0; (1 << ka.tw_log2) < tw; ++ka.tw_log2) {}

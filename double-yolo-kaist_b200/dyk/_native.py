@@ -37,7 +37,7 @@ class ConvParams(C.Structure):
         ("act", _i32), ("dtype", _i32), ("upsample2x", _i32), ("out_f32", _i32),
         ("out_h", _i32), ("out_w", _i32), ("y_plane", _i32),
         ("x2", _vp), ("x2_pix_stride", _i64), ("x_wts_raw", _vp),
-        ("w_image_stride", _i64),
+        ("w_image_stride", _i64), ("sm_limit", _i32),
     ]
 
 

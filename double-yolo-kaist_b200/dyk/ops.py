@@ -160,9 +160,10 @@ def pack_conv_weights_multi(items, dtype) -> None:
 
 # ------------------------------------------------------------------------------------------ NHWC launches
 def _conv_params(x: View, w_packed, scale, bias, y: View, *, k, stride, pad, act, res: View = None, upsample2x=False,
-                 out_f32=False, cout=None, x2: View = None, x_wts_raw=None, w_image_stride=0):
+                 out_f32=False, cout=None, x2: View = None, x_wts_raw=None, w_image_stride=0, sm_limit=0):
     p = nat.ConvParams()
     p.w_image_stride = int(w_image_stride)
+    p.sm_limit = int(sm_limit)
     p.x, p.x_pix_stride = x.ptr, x.stride
     p.w = None if w_packed is None else w_packed.data_ptr()
     p.scale = None if scale is None else scale.data_ptr()
@@ -188,13 +189,14 @@ def _conv_params(x: View, w_packed, scale, bias, y: View, *, k, stride, pad, act
 
 
 def nhwc_conv(x: View, w_packed: torch.Tensor, scale, bias, y: View, *, k, stride, pad, act, res: View = None,
-              upsample2x=False, out_f32=False, cout=None, x2: View = None, x_wts_raw=None, w_image_stride=0) -> None:
+              upsample2x=False, out_f32=False, cout=None, x2: View = None, x_wts_raw=None, w_image_stride=0,
+              sm_limit=0) -> None:
     """x2 / x_wts_raw: the convolution's input is sigmoid(w)[0] * x + sigmoid(w)[1] * x2 (WeightedFeatureFusion fused into
     its consumer, build_utils/layers.py:63-85); see conv_dual_source_supported.
     w_image_stride != 0: w_packed holds one weight tensor per image, w_image_stride elements apart (a SqueezeExcitation
     gate folded into the consuming 1x1 convolution, scale_weights_per_image); pass cout explicitly."""
     p = _conv_params(x, w_packed, scale, bias, y, k=k, stride=stride, pad=pad, act=act, res=res, upsample2x=upsample2x,
-                     out_f32=out_f32, cout=cout, x2=x2, x_wts_raw=x_wts_raw, w_image_stride=w_image_stride)
+                     out_f32=out_f32, cout=cout, x2=x2, x_wts_raw=x_wts_raw, w_image_stride=w_image_stride, sm_limit=sm_limit)
     nat.call("dyk_conv2d_fwd", C.byref(p), _stream())
     nat.count_launches()
 

@@ -460,7 +460,26 @@ def assign_lanes(ops_):
             lane = 0 if last[0] is None else 1
         lanes.append(lane)
         last[lane] = k
-    return lanes, producer
+    return lanes, producer, anc
+
+
+def dual_phase(lanes, anc):
+    """For every op: is there an op on the OTHER lane that neither depends on it nor is depended on by it, i.e. can the two
+    lanes be busy at the same time here?  (True for the two modality backbones between fusion points, False for the neck /
+    heads.)  Convolutions of such ops are launched with half the SMs each (dyk_conv_params.sm_limit): both lanes' kernels
+    are then resident together, a kernel boundary on one lane idles half the machine instead of all of it, and the tiles
+    of the two launches are rounded up over 74 SMs each instead of one after the other over 148."""
+    n = len(lanes)
+    by_lane = {0: [k for k in range(n) if lanes[k] == 0], 1: [k for k in range(n) if lanes[k] == 1]}
+    out = [False] * n
+    for k in range(n):
+        if lanes[k] < 0:
+            continue
+        for j in by_lane[1 - lanes[k]]:
+            if not (anc[k] >> j) & 1 and not (anc[j] >> k) & 1:
+                out[k] = True
+                break
+    return out
 
 
 class WeightBank:
@@ -557,9 +576,15 @@ class Plan:
         place_concats(self.ops)
         liveness(self.ops)
         self.two_lanes = os.environ.get("DYK_LANES", "2") != "1" and not self.f32
-        self.lanes, self.producer = assign_lanes(self.ops)
+        self.lanes, self.producer, anc = assign_lanes(self.ops)
         if not self.two_lanes:
             self.lanes = [min(l, 0) for l in self.lanes]
+        # measured (A/B in one session, bs 16 / 64): splitting the machine is 3 - 5 % SLOWER on all three dual models (dyolov3
+        # 3110 -> 3015 frames/s, dyolov4 2363 -> 2238, MobileNetV3 6292 -> 6019): the lanes drift, and a lane that is in a
+        # light layer or at a kernel boundary lends its SMs to the other one only when grids are not capped.  Off by default.
+        split = self.two_lanes and device.type == "cuda" and os.environ.get("DYK_SM_SPLIT", "0") == "1"
+        self.dual = dual_phase(self.lanes, anc) if split else [False] * len(self.ops)
+        self.half_sms = (torch.cuda.get_device_properties(device).multi_processor_count // 2) if split else 0
         self._allocate()
         self._bind(model, bank)
         bank.flush()
@@ -662,6 +687,8 @@ class Plan:
             for st in self.steps[n_before:]:
                 if not isinstance(st, _Sync):
                     st.lane = max(lane, 0)
+                    if isinstance(st, _ConvStep) and self.dual[k]:
+                        st.kw["sm_limit"] = self.half_sms
             if lane >= 0 and self.side_stream is not None and self._has_cross_lane_consumer(k):
                 ev = torch.cuda.Event()
                 events[k] = ev

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DYK_ABI_VERSION 6
+#define DYK_ABI_VERSION 7
 
 enum { DYK_F16 = 0, DYK_BF16 = 1 };
 
@@ -99,6 +99,12 @@ typedef struct dyk_conv_params {
    * (elements; a whole number >= Cout of [Cin]-rows), written by dyk_scale_weights_per_image.  The gated activation tensor
    * is never written or read; tiles are kept inside one image.  1x1, stride 1, pad 0 only. */
   int64_t w_image_stride;
+  /* ---- ABI v7 addition (zero = previous behaviour): SM budget ----
+   * Upper bound on the SMs (= persistent CTAs) this launch occupies; 0 = all.  The two modality backbones of a dual-stream
+   * model are independent between fusion points and run on two CUDA streams: with half the machine each, both kernels are
+   * resident at once, a kernel boundary of one stream idles half the SMs instead of all, and the two launches' tiles are
+   * rounded up to whole rounds over 74 SMs each instead of one after the other over 148. */
+  int32_t sm_limit;
 } dyk_conv_params;
 int dyk_conv2d_fwd(const dyk_conv_params* p, void* stream);
 /* 1 when dyk_conv2d_fwd accepts x2 != NULL for this layer (3x3, stride 1, pad 1, >= 256 output channels, Cin % 64 == 0:

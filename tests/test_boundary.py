@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(native_lib):
     for s in syms:
         assert hasattr(native_lib, s), f"{s} declared in include/dyk_b200.h but not exported"
     assert sorted(_native.SIGNATURES) == syms, "ctypes prototypes and header went out of sync"
-    assert native_lib.dyk_abi_version() == 6
+    assert native_lib.dyk_abi_version() == 7
 
 
 def test_library_is_sm100a_tcgen05(native_lib):
