@@ -57,6 +57,7 @@ bool pdl_enabled() {
 }  // namespace dyk
 
 extern "C" __attribute__((visibility("default"))) int dyk_abi_version(void) { return DYK_ABI_VERSION; }
+extern "C" __attribute__((visibility("default"))) int dyk_conv_params_size(void) { return (int)sizeof(dyk_conv_params); }
 
 extern "C" __attribute__((visibility("default"))) const char* dyk_last_error(void) { return dyk::g_err; }
 

@@ -44,6 +44,7 @@ class ConvParams(C.Structure):
 # name -> (restype, argtypes); must list every symbol the header declares (tests check this).
 SIGNATURES = {
     "dyk_abi_version": (_i32, []),
+    "dyk_conv_params_size": (_i32, []),
     "dyk_last_error": (C.c_char_p, []),
     "dyk_check_device": (_i32, []),
     "dyk_conv2d_fwd": (_i32, [C.POINTER(ConvParams), _vp]),
@@ -139,6 +140,9 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here means header and library went out of sync
         fn.restype = res
         fn.argtypes = args
+    if lib.dyk_conv_params_size() != C.sizeof(ConvParams):
+        raise NativeError(f"struct dyk_conv_params is {lib.dyk_conv_params_size()} bytes in {LIB_PATH.name} but {C.sizeof(ConvParams)} "
+                          "in dyk/_native.py: header and binding are out of sync")
     _lib = lib
     return lib
 

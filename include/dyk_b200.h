@@ -47,6 +47,8 @@ enum {
 };
 
 int dyk_abi_version(void);
+/* sizeof(dyk_conv_params) as this library was compiled: lets a binding (ctypes / cgo / JNI struct mirror) verify its layout. */
+int dyk_conv_params_size(void);
 const char* dyk_last_error(void);
 /* 0 when the current device is a compute-capability-10.x GPU and the driver entry points resolve. */
 int dyk_check_device(void);
