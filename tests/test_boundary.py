@@ -24,8 +24,8 @@ def test_library_exports_every_declared_symbol(native_lib):
     assert sorted(_native.SIGNATURES) == syms, "ctypes prototypes and header went out of sync"
     assert native_lib.dyk_abi_version() == 7
     import ctypes
-    from dyk import _native
-    assert native_lib.dyk_conv_params_size() == ctypes.sizeof(_native.ConvParams)      # the ctypes mirror has the C layout
+    from dyk import _native as nat_mod
+    assert native_lib.dyk_conv_params_size() == ctypes.sizeof(nat_mod.ConvParams)      # the ctypes mirror has the C layout
 
 
 def test_library_is_sm100a_tcgen05(native_lib):
