@@ -209,6 +209,8 @@ namespace dyk {
 int stem_tc_try(const void* x, const float* w, const float* scale, const float* bias, void* y, int64_t ys, int N, int H,
                 int W, int Cin, int Cout, int k, int stride, int pad, int act, int dtype, int x_kind, cudaStream_t stream,
                 int Hs, int Ws);
+int dwconv_tile_try(const void* x, int64_t xs, const float* w, const float* scale, const float* bias, void* y, int64_t ys,
+                    int N, int H, int W, int C, int k, int stride, int pad, int act, int dtype, cudaStream_t stream);
 }
 using namespace dyk;
 
@@ -280,6 +282,11 @@ extern "C" __attribute__((visibility("default"))) int dyk_dwconv2d_fwd(const voi
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   DYK_REQUIRE(Ho > 0 && Wo > 0, "dyk_dwconv2d_fwd: empty output");
   const int cv = C / 8;
+  {  // TMA-staged tile kernel (dwconv_tile.cu) for the 3x3 / 5x5 shapes; DYK_DW_TILE=0 keeps the strip kernel below
+    const int rc = dwconv_tile_try(x, xs, w, scale, bias, y, ys, N, H, W, C, k, stride, pad, act, dtype,
+                                   static_cast<cudaStream_t>(stream_));
+    if (rc <= 0) return rc;
+  }
   if ((k == 3 || k == 5) && (stride == 1 || stride == 2)) {
     const int strips = (Wo + kDwStrip - 1) / kDwStrip;
     const long long tot = (long long)N * Ho * strips * cv;

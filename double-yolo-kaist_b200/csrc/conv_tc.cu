@@ -674,6 +674,7 @@ int encode_map_generic(CUtensorMap* map, const void* base, int rank, const cuuin
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 0  ? CU_TENSOR_MAP_SWIZZLE_NONE
                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, rank, const_cast<void*>(base), dims, strides_bytes, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -149,6 +149,45 @@ def test_depthwise_conv(k, stride, C):
     _close(got, want, rtol=2e-3, atol=2e-3, what="dwconv")
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("k,stride,C,H,W,slack", [
+    (3, 1, 16, 37, 50, 0), (3, 1, 72, 33, 41, 8), (3, 2, 64, 30, 45, 0), (3, 2, 128, 17, 20, 64), (5, 1, 120, 19, 23, 0),
+    (5, 2, 40, 21, 37, 0), (5, 1, 960, 16, 20, 0), (3, 1, 184, 9, 11, 0), (5, 1, 200, 12, 10, 16), (3, 1, 296, 7, 9, 0),
+    (5, 2, 672, 32, 40, 0), (3, 1, 8, 24, 70, 8), (3, 1, 480, 5, 3, 0)])
+def test_depthwise_tile_kernel_equals_strip_kernel(dt, k, stride, C, H, W, slack):
+    """The TMA-staged tile kernel (csrc/dwconv_tile.cu) against the strip kernel it replaces (bit-identical: same fp32
+    accumulation order, zero padding adds exact zeros) and against fp32 torch (models.py:41 groups == C), on channel-slice
+    views (pixel stride > C), ragged tiles, channel counts without a friendly block size and both strides."""
+    import os
+    from dyk import ops
+    from dyk.ops import View
+    g = torch.Generator().manual_seed(1000 * k + C + H)
+    N = 3
+    xb = torch.randn((N, H, W, C + slack), generator=g).to(dt).to(DEV)
+    x = View(xb, slack, C)
+    w = torch.randn((k, k, C), generator=g).to(DEV)
+    sc = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    bi = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    Ho, Wo = (H + 2 * (k // 2) - k) // stride + 1, (W + 2 * (k // 2) - k) // stride + 1
+    outs = []
+    for mode in ("1", "0"):
+        os.environ["DYK_DW_TILE"] = mode
+        try:
+            yb = torch.full((N, Ho, Wo, C + 8), 7.0, dtype=dt, device=DEV)
+            ops.nhwc_dwconv(x, w, sc, bi, View(yb, 0, C), k=k, stride=stride, pad=k // 2, act="hard-swish")
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("DYK_DW_TILE", None)
+        assert torch.all(yb[..., C:] == 7.0), "wrote outside the channel slice"
+        outs.append(yb[..., :C])
+    assert torch.equal(outs[0], outs[1]), "tile kernel differs from the strip kernel"
+    xf = xb[..., slack:].float().permute(0, 3, 1, 2)
+    want = F.hardswish(F.conv2d(xf, w.permute(2, 0, 1).unsqueeze(1), None, stride, k // 2, 1, C) * sc.view(1, -1, 1, 1)
+                       + bi.view(1, -1, 1, 1))
+    tol = 2e-3 if dt == torch.float16 else 1.6e-2
+    _close(outs[0].permute(0, 3, 1, 2).float(), want, rtol=tol, atol=tol, what="dwconv tile")
+
+
 def test_weighted_fusion_and_plain_shortcut():
     from dyk import ops
     g = torch.Generator().manual_seed(5)
