@@ -696,6 +696,7 @@ static inline int encode_map(CUtensorMap* map, const void* base, int rank, const
   return encode_map_generic(map, base, rank, dims, strides_bytes, box, swizzle_bytes, what);
 }
 
+int conv1x1_thin_try(const dyk_conv_params* p, cudaStream_t stream);   // conv_thin.cu
 int conv3x3_halo_try(const dyk_conv_params* p, cudaStream_t stream);   // conv_halo.cu
 int conv3x3_halo2_try(const dyk_conv_params* p, cudaStream_t stream);  // conv_halo2.cu (CTA pairs)
 bool conv3x3_halo2_eligible(const dyk_conv_params* p);
@@ -836,6 +837,11 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_fwd(const dyk_c
     DYK_REQUIRE(dual_source_ok(p), "dyk_conv2d_fwd: the dual-source input is not available for this layer "
                 "(see dyk_conv2d_dual_source_supported)");
     return conv3x3_halo2_try(p, stream);
+  }
+  // 1x1 layers with Cin * Cout <= 2048 (MobileNet expand / project convs): CUDA-core kernel, conv_thin.cu
+  {
+    const int tr = conv1x1_thin_try(p, stream);
+    if (tr <= 0) return tr;
   }
   // 3x3 stride-1 layers: halo kernel (every input pixel loaded once per tile instead of once per tap)
   static const bool no_halo = getenv("DYK_NO_HALO") != nullptr && getenv("DYK_NO_HALO")[0] == '1';

@@ -141,6 +141,7 @@ __global__ void se_pool_kernel(const uint8_t* __restrict__ x, long long xs, int 
 #pragma unroll
   for (int q = 0; q < 8; ++q) acc[q] = 0.f;
   if (cvec * 8 < C) {
+#pragma unroll 4          // four independent 16-byte loads in flight per thread (the sums stay in pixel order)
     for (int pidx = p0 + plane; pidx < p1; pidx += 32) {
       const long long pix = (long long)n * HW + pidx;
       float f[8];

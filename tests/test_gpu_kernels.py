@@ -66,6 +66,16 @@ CONV_CASES = [
     (2, 64, 96, 80, 128, 3, 1, "mish", True, False, True),
     (3, 48, 70, 83, 96, 3, 1, "leaky", False, False, True),     # ragged tiles, 3 K steps, 96 output channels
     (5, 16, 50, 64, 64, 3, 1, "relu", False, False, True),
+    # 1x1 layers with Cin * Cout <= 2048: CUDA-core kernel (conv_thin.cu), output slabs of 32 / 24 / 16 / 8 channels
+    (2, 16, 33, 47, 16, 1, 1, "relu", True, False, True),
+    (3, 72, 12, 14, 24, 1, 1, "linear", True, False, True),
+    (2, 64, 9, 11, 24, 1, 1, "linear", False, False, True),
+    (2, 8, 13, 9, 40, 1, 1, "relu", False, False, True),
+    (2, 24, 21, 21, 72, 1, 2, "hard-swish", False, False, True),
+    (2, 32, 10, 12, 64, 1, 1, "mish", True, False, True),
+    (3, 40, 17, 19, 120, 1, 1, "relu", False, False, True),
+    (2, 120, 11, 13, 40, 1, 1, "linear", True, False, True),
+    (1, 64, 5, 7, 128, 1, 2, "leaky", False, False, True),
 ]
 
 
@@ -356,11 +366,16 @@ def test_se_gate_folded_into_consumer_conv(shape, dtype):
     assert torch.equal(wimg.view(N, Cout, Cin), (w.view(1, Cout, Cin).float() * gate.view(N, 1, Cin)).to(dtype))
     y1 = ops.new_view(N, H, W, Cout, dtype, DEV)
     ops.nhwc_conv(x, wimg, scale, bias, y1, k=1, stride=1, pad=0, act="hard-swish", cout=Cout, w_image_stride=Cout * Cin)
-    for n in range(N):                       # the same kernel, one image at a time, shared-weights path
-        xn = View(x.buf[n:n + 1], 0, Cin)
-        yn = ops.new_view(1, H, W, Cout, dtype, DEV)
-        ops.nhwc_conv(xn, wimg[n].contiguous(), scale, bias, yn, k=1, stride=1, pad=0, act="hard-swish")
-        assert torch.equal(y1.buf[n], yn.buf[0]), f"image {n}: per-image-weight convolution differs"
+    import os
+    os.environ["DYK_THIN"] = "0"             # the same (tcgen05) kernel, one image at a time, shared-weights path;
+    try:                                     # without the switch the thin-layer kernel (conv_thin.cu) would take some shapes
+        for n in range(N):
+            xn = View(x.buf[n:n + 1], 0, Cin)
+            yn = ops.new_view(1, H, W, Cout, dtype, DEV)
+            ops.nhwc_conv(xn, wimg[n].contiguous(), scale, bias, yn, k=1, stride=1, pad=0, act="hard-swish")
+            assert torch.equal(y1.buf[n], yn.buf[0]), f"image {n}: per-image-weight convolution differs"
+    finally:
+        os.environ.pop("DYK_THIN", None)
     want = F.hardswish(F.conv2d(xf * gate.view(N, Cin, 1, 1), wf) * scale[:Cout].view(1, -1, 1, 1) + bias[:Cout].view(1, -1, 1, 1))
     eps = 2e-3 if dtype == torch.float16 else 1.6e-2
     _close(ops.to_nchw(y1), want, rtol=eps, atol=eps, what=f"gate folded into weights {shape} {dtype}")
