@@ -140,6 +140,43 @@ def test_stem_conv_reads_nchw_frames(in_dtype):
     _close(got, want, rtol=2e-3, atol=2e-3, what="stem")
 
 
+@pytest.mark.parametrize("in_dtype", [torch.float32, torch.uint8])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("Cout,stride,H,W", [(16, 2, 40, 56), (16, 2, 37, 45), (16, 1, 21, 30), (32, 2, 33, 64), (32, 2, 18, 7)])
+def test_stem_unrolled_kernel_equals_generic_kernel(Cout, stride, H, W, dt, in_dtype):
+    """The unrolled 3x3 / Cin 3 stem (stem3x3_kernel: the MobileNet stems, models.py:35-36 with stride 2) against the generic
+    CUDA-core stem it replaces (DYK_STEM_FAST=0): bit-identical (same fp32 order, byte -> v / 255 through a table of the same
+    IEEE quotients, out-of-frame taps add exact zeros), and against fp32 torch."""
+    import os
+    from dyk import ops
+    g = torch.Generator().manual_seed(Cout * 100 + H)
+    N = 3
+    if in_dtype == torch.uint8:
+        x = torch.randint(0, 256, (N, 3, H, W), dtype=torch.uint8, generator=g).to(DEV)
+        xf = x.float() / 255.0
+    else:
+        x = torch.rand((N, 3, H, W), generator=g).to(DEV)
+        xf = x
+    w = (torch.randn((Cout, 3, 3, 3), generator=g) * 0.3).to(DEV)              # OIHW
+    sc = (torch.rand(Cout, generator=g) + 0.5).to(DEV)
+    bi = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
+    Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+    outs = []
+    for mode in ("1", "0"):
+        os.environ["DYK_STEM_FAST"] = mode
+        try:
+            y = ops.new_view(N, Ho, Wo, Cout, dt, DEV)
+            ops.nhwc_stem(x, w.permute(0, 2, 3, 1).contiguous(), sc, bi, y, k=3, stride=stride, pad=1, act="hard-swish")
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("DYK_STEM_FAST", None)
+        outs.append(y.buf)
+    assert torch.equal(outs[0], outs[1]), "unrolled stem differs from the generic stem"
+    want = F.hardswish(F.conv2d(xf, w, None, stride, 1) * sc.view(1, -1, 1, 1) + bi.view(1, -1, 1, 1))
+    tol = 2e-3 if dt == torch.float16 else 1.6e-2
+    _close(outs[0].permute(0, 3, 1, 2).float(), want, rtol=tol, atol=tol, what="stem3x3")
+
+
 @pytest.mark.parametrize("k,stride,C", [(3, 1, 64), (3, 2, 72), (5, 1, 120), (5, 2, 40), (3, 1, 960)])
 def test_depthwise_conv(k, stride, C):
     from dyk import ops
