@@ -56,7 +56,7 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <bool kBf16, int KS_MAX, int kAct>
+template <bool kBf16, int KS_MAX, int kAct, bool kRes>
 __global__ void __launch_bounds__(256)
 conv1x1_mma_kernel(const MmaArgs m) {
   const ThinArgs& a = m.t;
@@ -84,6 +84,7 @@ conv1x1_mma_kernel(const MmaArgs m) {
   __syncthreads();                                        // while the current group is multiplied, finished and stored
 
   const int c8n = a.Cin >> 3, c8pad = m.KS * 2;
+  const int KS = m.KS, NT = m.NT, Cout = a.Cout, o_pitch = m.o_pitch;
   // this lane's pixel of group `grp` -> row `lane` of `dst` (asynchronous; channels beyond Cin and pixels beyond the tensor
   // zero-filled)
   auto fetch = [&](unsigned grp, uint8_t* dst) {
@@ -122,16 +123,29 @@ conv1x1_mma_kernel(const MmaArgs m) {
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int ks = 0; ks < KS_MAX; ++ks) {
-        if (ks < m.KS) {
+        if (ks < KS) {
           const uint32_t addr = smem_u32(tile + (mt * 16 + (lane & 15)) * m.a_pitch + (ks * 16 + (lane >> 4) * 8) * 2);
           asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                        : "=r"(af[mt][ks][0]), "=r"(af[mt][ks][1]), "=r"(af[mt][ks][2]), "=r"(af[mt][ks][3]) : "r"(addr));
         }
       }
     __syncwarp();                                  // the tile is free: it now collects the output
-    const unsigned prow[4] = {grp * 32 + g, grp * 32 + g + 8, grp * 32 + g + 16, grp * 32 + g + 24};
+    // per-lane row bases of the four (half, 8-row block) fragments, computed once per group: the output rows in the warp tile
+    // and (kRes: compiled out otherwise — predicated-off residual code was half of the epilogue's issue slots) the residual rows
+    uint8_t* orow[4];
+    const uint8_t* rrow[4];
+    bool rok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      orow[k] = tile + (k * 8 + g) * o_pitch + t4 * 4;
+      if constexpr (kRes) {
+        const unsigned rp = grp * 32 + k * 8 + g;
+        rok[k] = rp < a.npix;
+        rrow[k] = a.res + ((long long)(rok[k] ? rp : 0) * a.rs) * 2 + t4 * 4;
+      }
+    }
     // ---- 4 output tiles (32 channels) at a time
-    for (int n0 = 0; n0 < m.NT; n0 += 4) {
+    for (int n0 = 0; n0 < NT; n0 += 4) {
       float acc[2][4][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -141,11 +155,11 @@ conv1x1_mma_kernel(const MmaArgs m) {
           for (int e = 0; e < 4; ++e) acc[mt][j][e] = 0.f;
 #pragma unroll
       for (int ks = 0; ks < KS_MAX; ++ks) {
-        if (ks < m.KS) {
+        if (ks < KS) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if (n0 + j < m.NT) {
-              const uint2 b = bsm[(ks * m.NT + n0 + j) * 32 + lane];
+            if (n0 + j < NT) {
+              const uint2 b = bsm[(ks * NT + n0 + j) * 32 + lane];
               mma16816<kBf16>(acc[0][j], af[0][ks], b.x, b.y);
               mma16816<kBf16>(acc[1][j], af[1][ks], b.x, b.y);
             }
@@ -154,32 +168,34 @@ conv1x1_mma_kernel(const MmaArgs m) {
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (n0 + j < m.NT) {
-          const int col = (n0 + j) * 8 + t4 * 2;
-          const float2 sc = *reinterpret_cast<const float2*>(ssm + col);
-          const float2 bi = *reinterpret_cast<const float2*>(ssm + a.Cout + col);
+        if (n0 + j < NT) {
+          const int cb = (n0 + j) * 16;            // byte offset of the tile's first channel in a 16-bit row
+          const float2 sc = *reinterpret_cast<const float2*>(ssm + (n0 + j) * 8 + t4 * 2);
+          const float2 bi = *reinterpret_cast<const float2*>(ssm + Cout + (n0 + j) * 8 + t4 * 2);
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {          // rows g + 16*mt + 8*h
               float o0 = act_apply<kAct>(fmaf(acc[mt][j][2 * h], sc.x, bi.x));
               float o1 = act_apply<kAct>(fmaf(acc[mt][j][2 * h + 1], sc.y, bi.y));
-              const unsigned rp = prow[mt * 2 + h];
-              if (a.res && rp < a.npix) {
-                const float2 r = unpack2<kBf16>(__ldg(reinterpret_cast<const uint32_t*>(a.res + ((long long)rp * a.rs + col) * 2)));
-                o0 += r.x;
-                o1 += r.y;
+              if constexpr (kRes) {
+                if (rok[mt * 2 + h]) {
+                  const float2 r = unpack2<kBf16>(__ldg(reinterpret_cast<const uint32_t*>(rrow[mt * 2 + h] + cb)));
+                  o0 += r.x;
+                  o1 += r.y;
+                }
               }
-              *reinterpret_cast<uint32_t*>(tile + (mt * 16 + h * 8 + g) * m.o_pitch + col * 2) = pack2<kBf16>(o0, o1);
+              *reinterpret_cast<uint32_t*>(orow[mt * 2 + h] + cb) = pack2<kBf16>(o0, o1);
             }
         }
       }
     }
     __syncwarp();
     if (ok) {
-      const uint4* row = reinterpret_cast<const uint4*>(tile + lane * m.o_pitch);
+      const uint4* row = reinterpret_cast<const uint4*>(tile + lane * o_pitch);
       uint4* yp = reinterpret_cast<uint4*>(a.y + (long long)pix * a.ys * 2);
-      for (int c = 0; c < m.NT; ++c) yp[c] = row[c];
+#pragma unroll 4
+      for (int c = 0; c < NT; ++c) yp[c] = row[c];
     }
     __syncwarp();                                  // before the group after next is fetched into this tile
   }
@@ -223,11 +239,11 @@ int conv1x1_thin_try(const dyk_conv_params* p, cudaStream_t stream) {
     if (grid > cap) grid = cap;
 #define DYK_MMA(KSM)                                                                                                \
   DYK_DISPATCH_ACT(p->act, DYK_DISPATCH_DTYPE(p->dtype, {                                                            \
-    auto kern = conv1x1_mma_kernel<kBf16, KSM, kAct>;                                                                \
-    static bool configured = false;                                                                                \
-    if (!configured) {                                                                                             \
+    auto kern = p->res ? conv1x1_mma_kernel<kBf16, KSM, kAct, true> : conv1x1_mma_kernel<kBf16, KSM, kAct, false>;   \
+    static bool configured[2] = {false, false};                                                                    \
+    if (!configured[p->res ? 1 : 0]) {                                                                             \
       DYK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));            \
-      configured = true;                                                                                           \
+      configured[p->res ? 1 : 0] = true;                                                                           \
     }                                                                                                              \
     kern<<<(unsigned)grid, 256, smem, stream>>>(m);                                                                \
   }))
