@@ -172,7 +172,7 @@ def run_reference_arm(args, rank):
 def conv_breakdown(plan, x, y, iters=3):
     """Per-launch CUDA-event timing of the captured plan run eagerly: time and FLOPs of the tcgen05 conv
     launches and total of everything else (each launch is bracketed by events on the launching stream)."""
-    from dyk.plan import _ConvStep
+    from dyk.plan import _ConvStep, _Call
     per = []
     for it in range(iters + 1):
         plan.run_stems(x, y)
@@ -213,6 +213,16 @@ def conv_breakdown(plan, x, y, iters=3):
                 res = 1 if s.kw.get("res") is not None else 0
                 srcs = 2 if s.kw.get("x2") is not None else 1          # dual-source modality fusion reads both tensors
                 dom["bytes"] += 2.0 * (srcs * s.x.N * s.x.H * s.x.W * s.x.C + opix * cout * (1 + res) + cout * s.x.C * k * k)
+    # depthwise launches (dwconv_tile_kernel): HBM-bound, algorithmic bytes = (in + out) * 2 B
+    from dyk import ops as _ops
+    dw = {"ms": 0.0, "bytes": 0.0, "n": 0}
+    for t, s in zip(mean, plan.steps):
+        if isinstance(s, _Call) and s.fn is _ops.nhwc_dwconv:
+            xin, yout = s.args[0], s.args[4]
+            dw["ms"] += t
+            dw["bytes"] += 2.0 * (xin.N * xin.H * xin.W * xin.C + yout.N * yout.H * yout.W * yout.C)
+            dw["n"] += 1
+    dom["dw"] = dw
     return conv_ms, other_ms, flops, n_conv, dom
 
 
@@ -677,6 +687,23 @@ def main():
                                         "graph in which the two backbones overlap, so those sums can exceed ms_per_step"},
             "cuda_graph": plan.graph is not None,
         }
+        dwk = dom.get("dw") or {"n": 0}
+        if not dom["n"] or (dwk["n"] and dwk["ms"] > dom["ms"]):
+            # MobileNet backbones: the depthwise kernel is the dominant kernel by time and it is HBM-bound
+            gbs = dwk["bytes"] / (dwk["ms"] / 1e3) / 1e9
+            line["roofline"] = {
+                "bound": "hbm", "achieved": gbs, "peak": peak_gb, "unit": "GB/s", "frac": gbs / peak_gb, "traffic": None,
+                "peak_source": peak_kind,
+                "kernel": "dwconv_tile_kernel (TMA-staged depthwise 3x3 / 5x5, csrc/dwconv_tile.cu): the dominant kernel of the "
+                          "step by time on the MobileNet backbones",
+                "note": "sums over the kernel's launches of one step: achieved = algorithmic bytes ((in + out) * 2 B per "
+                        "launch) / summed CUDA-event durations of an eager single-stream pass enqueued behind a device-side "
+                        "sleep; ncu of the same kernel (profiles/r02_ncu_mnv3_kernels.txt): DRAM bytes = algorithmic",
+                "launches_per_step": dwk["n"], "kernel_ms_per_step": dwk["ms"], "algorithmic_bytes_per_step": dwk["bytes"],
+                "all_dense_convs": {"achieved": achieved_all, "unit": "TFLOP/s", "frac_of_tensor_peak": achieved_all / peak_tf,
+                                    "launches_per_step": n_conv, "ms_per_step": conv_ms,
+                                    "algorithmic_gflop_per_step": flops / 1e9},
+                "other_kernels_ms_per_step": other_ms - dwk["ms"]}
         if not args.no_cpu_baseline and world == 1:      # contract: rank 0 at N = 1 only (at N > 1 the other ranks would spin)
             torch.set_num_threads(os.cpu_count())
             fps, done, dt = time_cpu_port(ref, st, args.ref_frames, 40, 1, budget_s=15.0)   # ~15 s of host work

@@ -219,7 +219,8 @@ dwconv_tile_kernel(const __grid_constant__ CUtensorMap xmap, const DwtArgs a) {
 // Tile geometry.  Every candidate (channel block CB | C, output tile TH x TW) whose input box fits the stage budget is
 // scored with a small model of what the sweep in tools/dw_bench.py --sweep measures:
 //   compute efficiency = active threads / threads  x  units / (rounds x pixel slots)  x  useful outputs / covered outputs,
-//                        with a fixed per-tile cost (barrier, index math, pipeline bubble) of ~1/3 round;
+//                        with a fixed per-tile cost (barrier, index math, pipeline bubble) of one round
+//                        (fitted to the sweep: 1/3 round picked tiles that were too small on the C = 16 and C = 128 layers);
 //   memory cost        = (input re-read through the halo + output) / algorithmic bytes.
 // Picks are cached per (C, Ho, Wo, k, stride, N).
 struct DwtGeom { int CB, TW, TH, in_cols, in_rows; };
@@ -259,7 +260,7 @@ static bool dwt_search(int C, int Ho, int Wo, int k, int S, int N, DwtGeom* out)
         const int tiles_h = ceil_div(Ho, TH), tiles_w = ceil_div(Wo, TW);
         const int units = TH * (TW / strip), rounds = ceil_div(units, PT);
         const double cover = ((double)Ho * Wo) / ((double)tiles_h * TH * tiles_w * TW);
-        const double comp = ((double)PT * cvb / T) * ((double)units / ((double)rounds * PT)) * cover * chan * rounds / (rounds + 0.35);
+        const double comp = ((double)PT * cvb / T) * ((double)units / ((double)rounds * PT)) * cover * chan * rounds / (rounds + 1.0);
         const double amp = ((double)in_rows * in_cols) / ((double)TH * TW * S * S) / cover / chan;
         const double mem = (amp * S * S + 1.0) / (S * S + 1.0);
         const double nt = (double)N * tiles_h * tiles_w * ncb;
