@@ -638,6 +638,7 @@ def main():
         conv_ms, other_ms, flops, n_conv, dom = conv_breakdown(plan, v, l if dual else None)
         peak_tf, peak_gb, peak_kind = peaks()
         achieved_all = flops / (conv_ms / 1e3) / 1e12
+        dwk, no_pair_kernel = dom.get("dw") or {"n": 0, "ms": 0.0}, not dom["n"]
         if dom["n"]:
             achieved = dom["flops"] / (dom["ms"] / 1e3) / 1e12
         else:                      # models without a CTA-pair layer (MobileNet): all dense convs together
@@ -687,8 +688,7 @@ def main():
                                         "graph in which the two backbones overlap, so those sums can exceed ms_per_step"},
             "cuda_graph": plan.graph is not None,
         }
-        dwk = dom.get("dw") or {"n": 0}
-        if not dom["n"] or (dwk["n"] and dwk["ms"] > dom["ms"]):
+        if dwk["n"] and (no_pair_kernel or dwk["ms"] > dom["ms"]):
             # MobileNet backbones: the depthwise kernel is the dominant kernel by time and it is HBM-bound
             gbs = dwk["bytes"] / (dwk["ms"] / 1e3) / 1e9
             line["roofline"] = {
