@@ -9,12 +9,6 @@
 
 namespace dyk {
 
-__device__ __forceinline__ float2 dw_ffma2(float2 x, float2 y, float2 z) {   // two IEEE fp32 FMAs per instruction (FFMA2)
-  uint64_t ux = *reinterpret_cast<uint64_t*>(&x), uy = *reinterpret_cast<uint64_t*>(&y), uz = *reinterpret_cast<uint64_t*>(&z), ud;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ud) : "l"(ux), "l"(uy), "l"(uz));
-  return *reinterpret_cast<float2*>(&ud);
-}
-
 // ------------------------------------------------------------------ stem: NCHW fp32 -> NHWC dtype
 // One thread = one output pixel x COUT_T output channels; consecutive threads walk along W, so the
 // per-plane input reads are coalesced and each thread stores COUT_T*2 contiguous bytes.
@@ -78,102 +72,6 @@ stem_conv_kernel(const TIn* __restrict__ x, const float* __restrict__ w, const f
         o[q] = act_apply<kAct>(fmaf(acc[c8 * 8 + q], sc, bi));
       }
       *(reinterpret_cast<uint4*>(yp) + c8) = pack8<kBf16>(o);
-    }
-  }
-}
-
-// ------------------------------------------------------------------ stem, 3x3 / Cin = 3 / pad 1 specialisation
-// The generic kernel above runs the MobileNet stems (3 -> 16 / 32, stride 2; stem_tc covers only 3 -> 32 stride 1) at a
-// tenth of their HBM rate (ncu, MobileNetV3-dual bs 64: 468 us per modality for 231 MB = 11.8 % of the step): run-time
-// loops over k and Cin, 64-bit index math and an IEEE division per input byte, one scalar FMA per weight read.  Here
-// everything is unrolled for k = 3, Cin = 3; a thread owns two W-adjacent output pixels (their windows share columns, the
-// weight reads are shared), the byte -> v / 255 conversion is a 256-entry table of the same IEEE quotients, the weights
-// are read as float4 broadcasts and multiplied with FFMA2.  Accumulation order (r, s, ci) and arithmetic per element are
-// those of the generic kernel; taps outside the frame contribute fmaf(0, w, acc) = acc: bit-identical results.
-template <int COUT_T, int S, bool kBf16, typename TIn, int kAct>
-__global__ void __launch_bounds__(128)
-stem3x3_kernel(const TIn* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
-               const float* __restrict__ bias, uint8_t* __restrict__ y, long long ys, int N, int H, int W, int Ho, int Wo) {
-  __shared__ __align__(16) float wsm[27 * COUT_T];   // [(r*3+s)*3+ci][co]
-  __shared__ __align__(16) float ssm[2 * COUT_T];
-  __shared__ float lut[256];
-  for (int i = threadIdx.x; i < 27 * COUT_T; i += blockDim.x) {
-    const int t = i / COUT_T, co = i - t * COUT_T;
-    wsm[i] = __ldg(&w[co * 27 + t]);
-  }
-  for (int i = threadIdx.x; i < COUT_T; i += blockDim.x) {
-    ssm[i] = scale ? __ldg(&scale[i]) : 1.f;
-    ssm[COUT_T + i] = bias ? __ldg(&bias[i]) : 0.f;
-  }
-  if constexpr (sizeof(TIn) == 1)
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 255.f);
-  __syncthreads();
-  constexpr int kCols = S + 3;                      // input columns under two adjacent outputs
-  const int pairs_w = (Wo + 1) >> 1;
-  const unsigned total = (unsigned)N * Ho * pairs_w;
-  const int plane = H * W;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int pw = (int)(i % (unsigned)pairs_w);
-    const unsigned t2 = i / (unsigned)pairs_w;
-    const int ho = (int)(t2 % (unsigned)Ho), n = (int)(t2 / (unsigned)Ho);
-    const int wo = pw * 2, h0 = ho * S - 1, w0 = wo * S - 1;
-    const TIn* xn = x + (long long)n * 3 * plane;
-    float2 acc[2][COUT_T / 2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int c = 0; c < COUT_T / 2; ++c) acc[j][c] = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int h = h0 + r;
-      const bool hok = h >= 0 && h < H;
-      float v[kCols][3];
-#pragma unroll
-      for (int col = 0; col < kCols; ++col) {
-        const int ww = w0 + col;
-        const bool ok = hok && ww >= 0 && ww < W;
-#pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
-          float f = 0.f;
-          if (ok) {
-            const TIn raw = __ldg(xn + ci * plane + h * W + ww);
-            if constexpr (sizeof(TIn) == 1) f = lut[raw];
-            else f = raw;
-          }
-          v[col][ci] = f;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 3; ++q)
-#pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
-          const float4* wp = reinterpret_cast<const float4*>(wsm + ((r * 3 + q) * 3 + ci) * COUT_T);
-          const float a0 = v[q][ci], a1 = v[q + S][ci];
-#pragma unroll
-          for (int c4 = 0; c4 < COUT_T / 4; ++c4) {
-            const float4 w4 = wp[c4];
-            acc[0][2 * c4] = dw_ffma2(make_float2(a0, a0), make_float2(w4.x, w4.y), acc[0][2 * c4]);
-            acc[0][2 * c4 + 1] = dw_ffma2(make_float2(a0, a0), make_float2(w4.z, w4.w), acc[0][2 * c4 + 1]);
-            acc[1][2 * c4] = dw_ffma2(make_float2(a1, a1), make_float2(w4.x, w4.y), acc[1][2 * c4]);
-            acc[1][2 * c4 + 1] = dw_ffma2(make_float2(a1, a1), make_float2(w4.z, w4.w), acc[1][2 * c4 + 1]);
-          }
-        }
-    }
-    const long long pix = ((long long)n * Ho + ho) * Wo + wo;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (wo + j >= Wo) break;
-      uint8_t* yp = y + (pix + j) * ys * 2;
-#pragma unroll
-      for (int c8 = 0; c8 < COUT_T / 8; ++c8) {
-        float o[8];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          o[2 * q] = act_apply<kAct>(fmaf(acc[j][c8 * 4 + q].x, ssm[c8 * 8 + 2 * q], ssm[COUT_T + c8 * 8 + 2 * q]));
-          o[2 * q + 1] = act_apply<kAct>(fmaf(acc[j][c8 * 4 + q].y, ssm[c8 * 8 + 2 * q + 1], ssm[COUT_T + c8 * 8 + 2 * q + 1]));
-        }
-        *(reinterpret_cast<uint4*>(yp) + c8) = pack8<kBf16>(o);
-      }
     }
   }
 }
@@ -311,6 +209,8 @@ namespace dyk {
 int stem_tc_try(const void* x, const float* w, const float* scale, const float* bias, void* y, int64_t ys, int N, int H,
                 int W, int Cin, int Cout, int k, int stride, int pad, int act, int dtype, int x_kind, cudaStream_t stream,
                 int Hs, int Ws);
+int stem3x3_try(const void* x, const float* w, const float* scale, const float* bias, void* y, int64_t ys, int N, int H, int W,
+                int Cin, int Cout, int k, int stride, int pad, int act, int dtype, int x_kind, cudaStream_t stream);
 int dwconv_tile_try(const void* x, int64_t xs, const float* w, const float* scale, const float* bias, void* y, int64_t ys,
                     int N, int H, int W, int C, int k, int stride, int pad, int act, int dtype, cudaStream_t stream);
 }
@@ -338,26 +238,9 @@ extern "C" __attribute__((visibility("default"))) int dyk_conv2d_stem_nchw_fwd(c
     if (rc <= 0) return rc;
   }
   const long long total = (long long)N * Ho * Wo;
-  {   // 3x3 / Cin 3 / pad 1 stems with 16 or 32 output channels: unrolled kernel (DYK_STEM_FAST=0: the generic one below)
-    const char* env = getenv("DYK_STEM_FAST");
-    const bool fast = !(env != nullptr && env[0] == '0') && k == 3 && Cin == 3 && pad == 1 && (stride == 1 || stride == 2) &&
-                      (Cout == 16 || Cout == 32) && (dtype == DYK_F16 || dtype == DYK_BF16) && total < (1ll << 31);
-    if (fast) {
-      const long long units = (long long)N * Ho * ((Wo + 1) / 2);
-      long long g = (units + 127) / 128;
-      const long long gcap = (long long)num_sms() * 16;
-      if (g > gcap) g = gcap;
-#define DYK_STEM3(CT, SS, TIN)                                                                                          \
-  DYK_DISPATCH_ACT(act, DYK_DISPATCH_DTYPE(dtype, (stem3x3_kernel<CT, SS, kBf16, TIN, kAct><<<(unsigned)g, 128, 0, stream>>>( \
-                                static_cast<const TIN*>(x), w, scale, bias, (uint8_t*)y, ys, N, H, W, Ho, Wo))))
-#define DYK_STEM3_S(CT, TIN) do { if (stride == 1) DYK_STEM3(CT, 1, TIN); else DYK_STEM3(CT, 2, TIN); } while (0)
-      if (Cout == 16) { if (x_kind == 0) DYK_STEM3_S(16, float); else DYK_STEM3_S(16, uint8_t); }
-      else { if (x_kind == 0) DYK_STEM3_S(32, float); else DYK_STEM3_S(32, uint8_t); }
-#undef DYK_STEM3_S
-#undef DYK_STEM3
-      DYK_LAUNCH_OK("stem3x3_kernel");
-      return DYK_OK;
-    }
+  {   // 3x3 / Cin 3 / pad 1 stems with 16 or 32 output channels: unrolled kernel, conv_stem3.cu (DYK_STEM_FAST=0: the generic one)
+    const int rc = stem3x3_try(x, w, scale, bias, y, ys, N, H, W, Cin, Cout, k, stride, pad, act, dtype, x_kind, stream);
+    if (rc <= 0) return rc;
   }
   const int ct = (Cout % 32 == 0) ? 32 : 16;
   long long gx = (total + 127) / 128;
