@@ -105,6 +105,61 @@ __global__ void maxpool_kernel(const uint8_t* __restrict__ x, long long xs, uint
   }
 }
 
+// 5x5 / stride 1 (every SPP pool: k = 9 and 13 are cascades of this one): the kernel above issues 25 predicated 16-byte loads,
+// 200 conversions and 200 fp32 max per 8-channel output with 64-bit index math (21 us for 21 MB in + 21 MB out at bs 16,
+// a tenth of the HBM rate).  Here a thread owns one 8-channel vector and a strip of four outputs along W: the 5 x 8 input
+// window is loaded once and slides, the loops are unrolled, and the maximum is taken on the packed 16-bit pairs (HMNMX2 —
+// exact: the result is one of the inputs).
+template <bool kBf16>
+__device__ __forceinline__ uint32_t max2_packed(uint32_t a, uint32_t b) {
+  if constexpr (kBf16) {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  } else {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+}
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+maxpool5_kernel(const uint8_t* __restrict__ x, long long xs, uint8_t* __restrict__ y, long long ys, int N, int H, int W, int cv,
+                int strips_w, unsigned total) {
+  constexpr uint32_t kNegInf = kBf16 ? 0xFF80FF80u : 0xFC00FC00u;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned c = i % (unsigned)cv;
+    unsigned t = i / (unsigned)cv;
+    const unsigned sw = t % (unsigned)strips_w; t /= (unsigned)strips_w;
+    const int ho = (int)(t % (unsigned)H), n = (int)(t / (unsigned)H);
+    const int wo0 = (int)sw * 4;
+    uint4 m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = make_uint4(kNegInf, kNegInf, kNegInf, kNegInf);
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      const int h = ho - 2 + r;
+      const bool hok = h >= 0 && h < H;
+      const uint8_t* xrow = x + (((long long)n * H + (hok ? h : 0)) * W) * xs * 2;
+#pragma unroll
+      for (int col = 0; col < 8; ++col) {
+        const int w = wo0 - 2 + col;
+        uint4 v = make_uint4(kNegInf, kNegInf, kNegInf, kNegInf);
+        if (hok && w >= 0 && w < W) v = __ldg(reinterpret_cast<const uint4*>(xrow + (long long)w * xs * 2) + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (col - j >= 0 && col - j < 5) {
+            m[j].x = max2_packed<kBf16>(m[j].x, v.x); m[j].y = max2_packed<kBf16>(m[j].y, v.y);
+            m[j].z = max2_packed<kBf16>(m[j].z, v.z); m[j].w = max2_packed<kBf16>(m[j].w, v.w);
+          }
+        }
+      }
+    }
+    uint8_t* yp = y + ((((long long)n * H + ho) * W + wo0) * ys) * 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (wo0 + j < W) *(reinterpret_cast<uint4*>(yp + (long long)j * ys * 2) + c) = m[j];
+  }
+}
+
 // ------------------------------------------------------------------ nn.Upsample(scale_factor=s), nearest
 __global__ void upsample_kernel(const uint8_t* __restrict__ x, long long xs, uint8_t* __restrict__ y, long long ys,
                                 int N, int H, int W, int cv, int s) {
@@ -404,6 +459,16 @@ extern "C" __attribute__((visibility("default"))) int dyk_maxpool2d(const void* 
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   DYK_REQUIRE(Ho > 0 && Wo > 0, "dyk_maxpool2d: empty output");
   const int cv = C / 8;
+  if (k == 5 && stride == 1 && (dtype == DYK_F16 || dtype == DYK_BF16)) {          // SPP pools (models.py:91-94 with size=5, stride=1)
+    const int strips = (W + 3) / 4;
+    const long long tot = (long long)N * H * strips * cv;
+    if (tot < (1ll << 31)) {
+      DYK_DISPATCH_DTYPE(dtype, (maxpool5_kernel<kBf16><<<grid_for(tot, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+                                    (const uint8_t*)x, xs, (uint8_t*)y, ys, N, H, W, cv, strips, (unsigned)tot)));
+      DYK_LAUNCH_OK("maxpool5_kernel");
+      return DYK_OK;
+    }
+  }
   const int grid = grid_for((long long)N * Ho * Wo * cv, 256);
   DYK_DISPATCH_DTYPE(dtype, (maxpool_kernel<kBf16><<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
                                 (const uint8_t*)x, xs, (uint8_t*)y, ys, N, H, W, cv, k, stride, pad, Ho, Wo)));

@@ -266,6 +266,25 @@ def test_maxpool_same(k):
     assert torch.equal(got, want), "max-pool must be exact"
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(3, 72, 13, 19), (2, 512, 16, 20), (1, 8, 3, 2), (2, 40, 33, 41)])
+def test_maxpool5_strip_kernel_exact(shape, dt):
+    """The 5x5 / stride-1 SPP pool (maxpool5_kernel: packed 16-bit max over a sliding window, models.py:91-94) is exact for
+    fp16 and bf16 on ragged widths, maps smaller than the window and channel-slice outputs."""
+    from dyk import ops
+    from dyk.ops import View
+    g = torch.Generator().manual_seed(sum(shape))
+    N, C, H, W = shape
+    x = torch.randn(shape, generator=g).to(dt).to(DEV)
+    want = F.max_pool2d(x.float(), 5, 1, 2).to(dt)
+    xv = ops.to_nhwc(x, dt)
+    yb = torch.full((N, H, W, C + 8), 3.0, dtype=dt, device=DEV)
+    ops.nhwc_maxpool(xv, View(yb, 8, C), 5, 1)
+    torch.cuda.synchronize()
+    assert torch.all(yb[..., :8] == 3.0), "wrote outside the channel slice"
+    assert torch.equal(yb[..., 8:].permute(0, 3, 1, 2), want), "max-pool must be exact"
+
+
 def test_upsample_and_concat_exact():
     from dyk import ops
     g = torch.Generator().manual_seed(1)
