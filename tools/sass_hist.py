@@ -6,7 +6,7 @@ import collections, re, subprocess, sys
 from pathlib import Path
 lib = Path(__file__).resolve().parent.parent / "double-yolo-kaist_b200" / "libdyk_b200.so"
 KEY = ("UTCHMMA", "UTCQMMA", "UTCBAR", "UTCCP", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "UTMACCTL", "SYNCS", "HMMA", "MUFU",
-       "LDG", "STG", "LDS", "STS", "BRX", "ATOM", "RED", "F2FP", "HFMA2", "FFMA", "SHFL", "BAR", "UCGABAR", "ACQBULK", "LDSM")
+       "LDG", "STG", "LDS", "STS", "BRX", "ATOM", "RED", "F2FP", "HFMA2", "FFMA", "FFMA2", "LDGSTS", "HMNMX2", "SHFL", "BAR", "UCGABAR", "ACQBULK", "LDSM")
 proc = subprocess.Popen(["cuobjdump", "-sass", str(lib)], stdout=subprocess.PIPE, text=True)
 hist, name = {}, None
 for line in proc.stdout:
