@@ -60,6 +60,8 @@ int dyk_check_device(void);
  *   y[n,ho,wo,co] = act(scale[co] * sum_{r,s,ci} x[n, ho*stride+r-pad, wo*stride+s-pad, ci] * w[co,r,s,ci]
  *                       + bias[co]) (+ res[n,ho,wo,co])
  * Requirements: groups == 1, Cin % 8 == 0, Cout_stride/x strides % 8 == 0, stride in {1,2}.
+ * 1x1 layers with fewer than 64 input channels (MobileNet expand / project convs) are served by a warp-MMA kernel
+ * (csrc/conv_thin.cu) with the same epilogue arithmetic; the dispatch is internal.
  */
 typedef struct dyk_conv_params {
   const void* x;          /* input slice, NHWC                                   */
@@ -151,6 +153,8 @@ int dyk_conv2d_stem_nchw_resize_fwd(const void* x_nchw, const float* w_ohwi, con
 /* ---- depthwise convolution + BN + activation ---------------------------------------------------
  * Replaces nn.Conv2d(groups=C) (+BN+act): models.py:41 (groups key) and
  * build_utils/layers.py:224-226 (DepthwiseSeparableConv2d).  w is fp32 [k][k][C].
+ * k in {3, 5} with stride in {1, 2}: TMA-staged tile kernel (csrc/dwconv_tile.cu; the zero padding is the TMA out-of-bounds
+ * fill); other shapes: CUDA-core strip / generic kernels.  All paths accumulate in fp32 in (r, s) order: identical results.
  */
 int dyk_dwconv2d_fwd(const void* x, int64_t x_pix_stride, const float* w, const float* scale,
                      const float* bias, void* y, int64_t y_pix_stride, int32_t N, int32_t H, int32_t W,
